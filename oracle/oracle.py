@@ -1,0 +1,152 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+
+oracle.py — ctypes driver for libtspice_oracle.so (the C++ restatement of the reference solver,
+see engine.hpp).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  PARITY UNPINNED (no Go toolchain, no reference
+golden vectors): the pins this oracle does have are listed in DESIGN.md §Oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from . import netlist as nlmod
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OrcJob(C.Structure):
+    _fields_ = [("analysis", C.c_int), ("tstart", C.c_double), ("tstop", C.c_double), ("tstep", C.c_double),
+                ("tmax", C.c_double), ("uic", C.c_int), ("dc_src_dev", C.c_int), ("dc_start", C.c_double),
+                ("dc_stop", C.c_double), ("dc_inc", C.c_double)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libtspice_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("tspice_oracle.cpp", "engine.hpp", "sparse13.hpp", "gomath.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libtspice_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_circuit_new.restype = C.c_void_p
+        L.orc_circuit_new.argtypes = [C.c_int, C.c_int]
+        L.orc_circuit_free.argtypes = [C.c_void_p]
+        L.orc_circuit_add.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                      C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_int]
+        L.orc_n_columns.argtypes = [C.c_void_p, C.c_int]
+        L.orc_structure.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_run.argtypes = [C.c_void_p, C.POINTER(OrcJob), C.c_int64, C.c_int, C.POINTER(C.c_int),
+                              C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_int64, C.POINTER(C.c_double),
+                              C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.orc_go_sin.restype = C.c_double
+        L.orc_go_sin.argtypes = [C.c_double]
+        L.orc_format_value_factor.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _arr(ctype, seq):
+    return (ctype * max(1, len(seq)))(*seq)
+
+
+class OracleCircuit:
+    """A parsed netlist handed to the CPU oracle.  Mirrors the reference's call sequence
+    netlist.Parse -> AssignNodeBranchMaps -> CreateMatrix -> SetupDevices (cmd/spice/main.go:364-401)."""
+
+    def __init__(self, text: str):
+        self.netlist = nlmod.parse(text)
+        self.plan = nlmod.build_plan(self.netlist)
+        L = lib()
+        self.h = L.orc_circuit_new(self.plan.n_nodes, self.plan.n_branches)
+        for r in self.plan.devices:
+            L.orc_circuit_add(self.h, r.kind, r.name.encode(), _arr(C.c_int, r.nodes), len(r.nodes), r.branch,
+                              _arr(C.c_double, r.p), len(r.p), _arr(C.c_int, r.ip), len(r.ip))
+
+    def __del__(self):
+        try:
+            lib().orc_circuit_free(self.h)
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return self.plan.n_nodes + self.plan.n_branches
+
+    def dev_index(self, name: str) -> int:
+        for i, r in enumerate(self.plan.devices):
+            if r.name == name:
+                return i
+        raise KeyError(name)
+
+    def signals(self, analysis=None):
+        return nlmod.signal_names(self.plan, self.netlist.analysis if analysis is None else analysis)
+
+    def structure(self):
+        n = self.n
+        e2i = (C.c_int * (n + 1))(); pr = (C.c_int * (n + 1))(); pc = (C.c_int * (n + 1))()
+        rc = lib().orc_structure(self.h, e2i, pr, pc)
+        return dict(rc=rc, ext2int=list(e2i)[1:], pivot_row=list(pr)[1:], pivot_col=list(pc)[1:])
+
+    def run(self, n_inst=1, overrides=None, analysis=None, tran=None, dc=None, threads=1, cap_rows=None,
+            want_wave=True, want_stats=False):
+        """overrides: {(device_name_or_index, param_index): array[n_inst]}.
+        Returns dict(wave [n_inst, cap, ncol], n_rows, status, counters, stats, signals)."""
+        nl = self.netlist
+        an = nl.analysis if analysis is None else analysis
+        job = OrcJob()
+        job.analysis = an
+        if an == nlmod.AN_TRAN:
+            t = dict(nl.tran)
+            if tran:
+                t.update(tran)
+            job.tstart, job.tstop, job.tstep, job.tmax, job.uic = t["tstart"], t["tstop"], t["tstep"], t["tmax"], int(t["uic"])
+        elif an == nlmod.AN_DC:
+            d = dict(nl.dc)
+            if dc:
+                d.update(dc)
+            job.dc_src_dev = self.dev_index(d["source"])
+            job.dc_start, job.dc_stop, job.dc_inc = d["start"], d["stop"], d["inc"]
+        overrides = overrides or {}
+        keys = list(overrides.keys())
+        ov_dev = [self.dev_index(k[0]) if isinstance(k[0], str) else int(k[0]) for k in keys]
+        ov_par = [int(k[1]) for k in keys]
+        vals = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(overrides[k], dtype=np.float64), (n_inst,))
+                                              for k in keys]) if keys else np.zeros((0, n_inst)))
+        ncol = lib().orc_n_columns(self.h, an)
+        if cap_rows is None:
+            cap_rows = 1 if an == nlmod.AN_OP else (int(round((job.dc_stop - job.dc_start) / job.dc_inc)) + 3
+                                                     if an == nlmod.AN_DC else 65536)
+        wave = np.full((n_inst, cap_rows, ncol), np.nan) if want_wave else None
+        stats = np.zeros((n_inst, 4, ncol)) if want_stats else None
+        n_rows = np.zeros(n_inst, dtype=np.int64)
+        status = np.zeros(n_inst, dtype=np.int32)
+        counters = np.zeros((n_inst, 6), dtype=np.int64)
+        dp = C.POINTER(C.c_double)
+        rc = lib().orc_run(self.h, C.byref(job), n_inst, len(keys), _arr(C.c_int, ov_dev), _arr(C.c_int, ov_par),
+                           vals.ctypes.data_as(dp), threads, cap_rows,
+                           wave.ctypes.data_as(dp) if wave is not None else None,
+                           n_rows.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(C.POINTER(C.c_int32)),
+                           counters.ctypes.data_as(C.POINTER(C.c_int64)),
+                           stats.ctypes.data_as(dp) if stats is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"orc_run failed rc={rc}")
+        return dict(wave=wave, n_rows=n_rows, status=status, counters=counters, stats=stats,
+                    signals=self.signals(an), ncol=ncol)
+
+
+def go_sin(x: float) -> float:
+    return lib().orc_go_sin(x)
+
+
+def format_value_factor(v: float) -> str:
+    buf = C.create_string_buffer(64)
+    lib().orc_format_value_factor(v, buf, 64)
+    return buf.value.decode()
