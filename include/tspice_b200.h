@@ -1,0 +1,204 @@
+/* tspice_b200.h — C ABI of the B200-native batched circuit-simulation engine.
+ *
+ * Drop-in boundary for ONE hot path of edp1096/toy-spice: many independent instances of one
+ * parsed netlist (parameter sweep / Monte Carlo) solved at once for operating point, DC sweep
+ * and transient analysis.  Netlist parsing and MNA node numbering stay on the host (the
+ * reference's own pkg/netlist + pkg/circuit); this library takes the already-numbered device
+ * table and replaces, for the whole batch, what the reference does per circuit in
+ *
+ *   pkg/analysis/op.go:171-233    OperatingPoint.Execute  (+ doNRiter :25-88, initial
+ *                                 estimate :90-111, Gmin stepping :192-214, source stepping :113-169)
+ *   pkg/analysis/dc.go:88-187     DCSweep.singleSweep / doNRiter
+ *   pkg/analysis/tran.go:57-250   Transient.Setup / Execute / doNRiter / calculateTruncError
+ *   pkg/analysis/anlysis.go:46-85 CheckConvergence / StoreTimeResult
+ *   pkg/circuit/circuit.go:165-313 Stamp / LoadState / Update / GetSolution / UpdateNonlinearVoltages
+ *   pkg/device/<kind>.go          every Stamp / UpdateVoltages / LoadState / UpdateState / CalculateLTE
+ *   pkg/matrix/circuit.go:57-166  Clear / AddElement / AddRHS / LoadGmin / Solve / Solution
+ *   github.com/edp1096/sparse     Factor / Solve with the pivot order of the first factorization
+ *
+ * Conventions
+ *   - every function returns TSB_OK (0) or a negative TSB_E_* code; tsb_last_error() gives text.
+ *   - per-instance failures (no convergence, singular matrix, NaN) are DATA (status array),
+ *     never a call failure.  No C++ exception crosses this boundary.
+ *   - handles are opaque and owned by the library; every create has a destroy.
+ *   - buffers passed in/out are caller-owned HOST memory unless the name says `_dev`.
+ *   - indices: nodes and branches are 1-based MNA unknown numbers, 0 = ground
+ *     (pkg/matrix/device.go:3-8); devices are numbered 0.. in tsb_plan_add_device call order,
+ *     which must be netlist order (mutual couplings are stamped last, circuit.go:126-152).
+ *   - one context drives one GPU (one process per GPU; shard instances across ranks).
+ */
+#ifndef TSPICE_B200_H
+#define TSPICE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tsb_ctx tsb_ctx;
+typedef struct tsb_plan tsb_plan;
+typedef struct tsb_batch tsb_batch;
+
+enum {
+    TSB_OK = 0,
+    TSB_E_INVALID = -1,     /* bad argument / wrong state */
+    TSB_E_PARSE = -2,       /* netlist front-end error (mirrors netlist.Parse errors) */
+    TSB_E_CUDA = -3,        /* CUDA driver/runtime error, or no GPU / driver library */
+    TSB_E_COMPILE = -4,     /* kernel specialisation failed (NVRTC) */
+    TSB_E_UNSUPPORTED = -5, /* e.g. AC analysis, > 2 sweep sources */
+    TSB_E_NOMEM = -6
+};
+
+/* Device kinds (pkg/netlist/parser.go:752-915 CreateDevice). */
+enum {
+    TSB_R = 0,     /* p: [R]                                              resistor.go  */
+    TSB_C = 1,     /* p: [C]                                              capacitor.go */
+    TSB_L = 2,     /* p: [L]                      branch required         inductor.go  */
+    TSB_V = 3,     /* p: waveform (below), ip: [src type]  branch required vsource.go  */
+    TSB_I = 4,     /* p: waveform (below), ip: [src type]                 isource.go   */
+    TSB_D = 5,     /* p: [is, n, tt]                                      diode.go     */
+    TSB_Q = 6,     /* p: [ies, ics, alphaf, ikf, ikr, vaf, var, nf, nr], ip: [pnp]   bjt.go */
+    TSB_M = 7,     /* p: [vto,kp,gamma,phi,lambda,w,l,tox,cgso,cgdo,cgbo,cbd,cbs,cj,cjsw,as,ad,ps,pd,
+                          mj,pb,uo,ucrit,uexp,vmax,theta,eta,kappa,delta], ip: [level, pmos]  mosfet.go */
+    TSB_K = 8,     /* p: [k], ip: device indices of the coupled inductors  mutual.go   */
+    TSB_LCORE = 9  /* p: [turns, area, len]       branch required         magnetic.go  */
+};
+
+/* Source waveforms (pkg/device/device.go:58-62).  p layout:
+ *   DC    [value]                  SIN   [offset, amplitude, freq, phase_deg]
+ *   PULSE [v1, v2, td, tr, tf, pw, per]   PWL [t0, v0, t1, v1, ...] (not sweepable) */
+enum { TSB_SRC_DC = 0, TSB_SRC_SIN = 1, TSB_SRC_PULSE = 2, TSB_SRC_PWL = 3 };
+
+/* Analysis kinds (pkg/analysis/anlysis.go:11-16). */
+enum { TSB_AN_OP = 0, TSB_AN_TRAN = 1, TSB_AN_AC = 2, TSB_AN_DC = 3 };
+
+/* Per-instance status (tsb_result_status). */
+enum {
+    TSB_ST_OK = 0,
+    TSB_ST_OP_FAILED = 1,    /* "source stepping failed" / "final solution failed"   op.go:216-229 */
+    TSB_ST_TRAN_FAILED = 2,  /* "failed to converge at t=%g"                         tran.go:119  */
+    TSB_ST_DC_FAILED = 3,    /* "convergence error at %s=%g"                         dc.go:128    */
+    TSB_ST_OVERFLOW = 4      /* more stored rows than the waveform capacity; rows beyond it dropped */
+};
+
+/* Convergence constants, defaults = NewBaseAnalysis (anlysis.go:35-44) and NewTransient (tran.go:51). */
+typedef struct tsb_opts {
+    int max_iter;       /* 100   */
+    double abstol;      /* 1e-12 */
+    double reltol;      /* 1e-6  */
+    double gmin;        /* 1e-12 (only recorded in ckt.Status; the solves use 0) */
+    double trtol;       /* 7.0   */
+    int strict_fp;      /* 1: compile kernels with --fmad=false (reference rounding, no FMA contraction) */
+    int block_size;     /* 0: default (128) */
+    int reuse_lu;       /* reserved (0) */
+} tsb_opts;
+
+/* Output selection for tsb_run_tran / tsb_run_dc. */
+enum {
+    TSB_OUT_WAVE = 1,   /* every stored row: wave[row][column][instance]          */
+    TSB_OUT_STATS = 2   /* min / max / sum / last per column over the stored rows */
+};
+
+void tsb_default_opts(tsb_opts* o);
+const char* tsb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int tsb_ctx_create(int device_ordinal, tsb_ctx** out);
+void tsb_ctx_destroy(tsb_ctx* ctx);
+const char* tsb_last_error(tsb_ctx* ctx);
+/* Launch on an existing CUDA stream (cudaStream_t / CUstream as an integer); 0 = the context's own. */
+int tsb_ctx_set_stream(tsb_ctx* ctx, uint64_t stream);
+/* Directory of the specialised-kernel cache (cubin files).  Default: $TSB_KCACHE or <lib dir>/../_kcache. */
+int tsb_ctx_set_cache_dir(tsb_ctx* ctx, const char* dir);
+/* FP64 DFMA-chain microbenchmark on this GPU: TFLOP/s (the FP64 roof used by bench.py). */
+int tsb_ctx_measure_fp64_peak(tsb_ctx* ctx, double* tflops);
+int tsb_ctx_sm_count(tsb_ctx* ctx, int* sms);
+
+/* ---- plan: one numbered netlist -------------------------------------------------------------
+ * Replaces circuit.NewWithComplex + CreateMatrix + SetupDevices (circuit.go:31-163) for the batch.
+ * `ctx` may be NULL for host-only use (structure queries, code generation at build time). */
+int tsb_plan_create(tsb_ctx* ctx, int n_nodes, int n_branches, tsb_plan** out);
+/* Host front-end convenience: C++ restatement of netlist.Parse + AssignNodeBranchMaps + CreateDevice
+ * (parser.go:75-915, circuit.go:48-71) for hosts that do not bring the reference's Go parser. */
+int tsb_plan_from_netlist(tsb_ctx* ctx, const char* text, tsb_plan** out);
+int tsb_plan_add_device(tsb_plan* plan, int kind, const char* name, const int* nodes, int n_nodes, int branch,
+                        const double* p, int n_p, const int* ip, int n_ip);
+/* Freezes the plan: Translate order, stamped pattern, nominal first-factor pivot order
+ * (the reference's symbolic pass), fill pattern. */
+int tsb_plan_finalize(tsb_plan* plan);
+void tsb_plan_destroy(tsb_plan* plan);
+const char* tsb_plan_error(tsb_plan* plan);
+
+int tsb_plan_size(const tsb_plan* plan, int* n_nodes, int* n_branches);
+int tsb_plan_num_devices(const tsb_plan* plan);
+int tsb_plan_device_info(const tsb_plan* plan, int dev, int* kind, const char** name, int nodes[4], int* branch,
+                         int* n_p, int* n_ip);
+int tsb_plan_device_params(const tsb_plan* plan, int dev, double* p, int cap_p, int* ip, int cap_ip);
+int tsb_plan_find_device(const tsb_plan* plan, const char* name);            /* index or -1 */
+int tsb_plan_node_name(const tsb_plan* plan, int node, const char** name);   /* from_netlist plans only */
+/* What the netlist's dot-cards asked for (from_netlist plans). */
+int tsb_plan_analysis(const tsb_plan* plan, int* analysis, double tran[4] /*tstart,tstop,tstep,tmax*/, int* uic,
+                      int* dc_src_dev, double dc[3] /*start,stop,inc*/);
+/* Structure (finalized plans).  All index arrays are 1-based with n+1 entries ([0] unused).
+ *   ext2int    Sparse `Translate` numbering of the main matrix (first-touch order)
+ *   pivot_row / pivot_col   external row / column of the pivot chosen at each elimination step */
+int tsb_plan_structure(const tsb_plan* plan, int* ext2int, int* pivot_row, int* pivot_col);
+/* Stamped pattern in first-touch order: rows[k], cols[k]; mode 0 = OP-mode stamps, 1 = + transient-only. */
+int tsb_plan_pattern(const tsb_plan* plan, int mode, int* rows, int* cols, int cap, int* nnz);
+/* Column names of a result row for `analysis` (TIME | SWEEP1, V(node..), I(branch..), I(R..)). */
+int tsb_plan_num_columns(const tsb_plan* plan, int analysis);
+int tsb_plan_column_name(const tsb_plan* plan, int analysis, int col, char* buf, int cap);
+
+/* ---- batch: N instances of a plan -----------------------------------------------------------*/
+int tsb_batch_create(tsb_plan* plan, int64_t n_inst, tsb_batch** out);
+void tsb_batch_destroy(tsb_batch* batch);
+/* Per-instance parameter values for (dev, param): n_inst doubles, host memory (copied H2D). */
+int tsb_batch_set_param(tsb_batch* batch, int dev, int param, const double* values);
+/* Same, values already resident in HBM (device pointer, n_inst doubles; borrowed until the batch
+ * is destroyed or the parameter is set again). */
+int tsb_batch_set_param_dev(tsb_batch* batch, int dev, int param, uint64_t dev_ptr);
+/* One value for all instances (replaces the netlist value). */
+int tsb_batch_set_param_uniform(tsb_batch* batch, int dev, int param, double value);
+
+/* Analyses — the batch equivalents of analysis.NewOP / NewTransient / NewDCSweep + Setup + Execute. */
+int tsb_run_op(tsb_batch* batch, const tsb_opts* opts);
+int tsb_run_tran(tsb_batch* batch, double tstart, double tstop, double tstep, double tmax, int uic,
+                 int out_flags, int64_t wave_cap_rows, const tsb_opts* opts);
+int tsb_run_dc(tsb_batch* batch, int src_dev, double start, double stop, double inc, int out_flags,
+               const tsb_opts* opts);
+/* Block until the last run has finished (runs are asynchronous on the context's stream). */
+int tsb_batch_sync(tsb_batch* batch);
+
+/* ---- results of the last run -----------------------------------------------------------------
+ * Layout in HBM (structure of arrays, instance is the fastest index so warps store coalesced):
+ *   wave     [cap_rows][n_columns][n_inst]    stats [4: min,max,sum,last][n_columns][n_inst]
+ *   rows     [n_inst] int64                   status [n_inst] int32
+ *   counters [6][n_inst] int64: accepted steps, rejected steps, transient solves, OP solves,
+ *            OP path (0 direct, 1 Gmin stepping, 2 source stepping), failure time/value (double bits) */
+int tsb_result_dims(const tsb_batch* batch, int64_t* n_inst, int* n_columns, int64_t* cap_rows);
+int tsb_result_dev_ptrs(const tsb_batch* batch, uint64_t* wave, uint64_t* stats, uint64_t* rows, uint64_t* status,
+                        uint64_t* counters);
+int tsb_result_rows(tsb_batch* batch, int64_t* rows /*[n_inst]*/);
+int tsb_result_status(tsb_batch* batch, int32_t* status /*[n_inst]*/);
+int tsb_result_counters(tsb_batch* batch, int64_t* counters /*[6][n_inst]*/);
+/* Waveform of one instance, row-major [rows][n_columns]; returns the row count in *n_rows. */
+int tsb_result_waveform(tsb_batch* batch, int64_t inst, double* out, int64_t cap_rows, int64_t* n_rows);
+/* Whole wave / stats arrays in the device layout above. */
+int tsb_result_wave_all(tsb_batch* batch, double* out, int64_t n_doubles);
+int tsb_result_stats_all(tsb_batch* batch, double* out /*[4][n_columns][n_inst]*/);
+/* Batch totals computed on the GPU: sum over instances of accepted steps, rejected, transient solves, OP solves. */
+int tsb_result_totals(tsb_batch* batch, int64_t totals[4]);
+
+/* ---- introspection / build-time support -------------------------------------------------------*/
+/* CUDA source of the kernels specialised for this batch configuration (which parameters vary). */
+int tsb_batch_kernel_source(tsb_batch* batch, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed);
+/* Cache key (hex) of that source + compile options; the cubin is looked up as <cache_dir>/<key>.cubin. */
+int tsb_batch_kernel_key(tsb_batch* batch, const tsb_opts* opts, char* buf, int cap);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+int64_t tsb_ctx_launch_count(const tsb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPICE_B200_H */

@@ -1,0 +1,109 @@
+"""Shared helpers for the parity tests: run one workload deck through the product (GPU, C-ABI) and
+through the CPU oracle on the same seeded parameter draws, and compare.
+
+Tolerance contract (BASELINE.json north_star / SURVEY.md §8c): node numbering and stamped pattern
+exact; voltages and currents |gpu - ref| <= 1e-9*|ref| + 1e-12 at identical time points."""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T = importlib.import_module("toy-spice_b200")
+from oracle import netlist as onl  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+RELTOL, ABSTOL = 1e-9, 1e-12
+
+
+def log_uniform(rng, lo, hi, n):
+    return np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+
+
+def draws(name: str, ckt, n: int, seed: int | None = None):
+    """Parameter draws of SURVEY.md §8(d) (toy-spice_b200/workloads.py)."""
+    from importlib import import_module
+    W = import_module("toy-spice_b200.workloads")
+    return W.sweep_draws(ckt.devices(), n, W.sweep_seed(name) if seed is None else seed)
+
+
+def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, analysis=None, tran=None):
+    """Through the reference-shaped API: Circuit -> analysis.Setup(batch) -> Execute."""
+    ckt = T.Circuit.from_netlist(text, ctx)
+    batch = ckt.batch(n)
+    for (dev, par), vals in overrides.items():
+        batch.set_param(dev, par, vals)
+    card = ckt.analysis_card()
+    if tran:
+        card.update(tran)
+    an_kind = card["analysis"] if analysis is None else analysis
+    if an_kind == T.AN_OP:
+        an = T.NewOP()
+    elif an_kind == T.AN_TRAN:
+        an = T.NewTransient(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"])
+        an.out = out
+        an.cap_rows = cap_rows
+    else:
+        an = T.NewDCSweep([ckt.devices()[card["dc_src_dev"]]["name"]], [card["dc_start"]], [card["dc_stop"]], [card["dc_inc"]])
+        an.out = out
+    if opts is not None:
+        an.opts = opts
+    an.Setup(batch)
+    an.Execute()
+    return ckt, batch, an
+
+
+def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None):
+    oc = O.OracleCircuit(text)
+    res = oc.run(n, overrides=overrides, threads=threads, cap_rows=cap_rows, want_stats=want_stats, analysis=analysis, tran=tran)
+    return oc, res
+
+
+def compare_waves(batch, ores, n, label=""):
+    """Instance-by-instance comparison at identical stored rows.  Returns a report dict."""
+    rows_g = batch.rows()
+    st_g = batch.status()
+    cnt_g = batch.counters()
+    ncol = ores["ncol"]
+    rep = dict(n=n, row_mismatch=0, status_mismatch=0, max_rel=0.0, max_abs=0.0, worst=None, nan_mismatch=0,
+               compared_points=0, counter_mismatch=0)
+    wall = batch.wave_all() if n > 64 else None
+    for i in range(n):
+        nr_o = int(ores["n_rows"][i])
+        if int(st_g[i]) != int(ores["status"][i]):
+            rep["status_mismatch"] += 1
+            continue
+        if int(rows_g[i]) != nr_o:
+            rep["row_mismatch"] += 1
+            continue
+        if not np.array_equal(cnt_g[:4, i], ores["counters"][i, :4]):
+            rep["counter_mismatch"] += 1
+        wg = wall[:nr_o, :, i] if wall is not None else batch.waveform(i)
+        wo = ores["wave"][i, :nr_o, :ncol]
+        nan_g, nan_o = np.isnan(wg), np.isnan(wo)
+        if not np.array_equal(nan_g, nan_o):
+            rep["nan_mismatch"] += 1
+            continue
+        ok = ~nan_o & np.isfinite(wo) & np.isfinite(wg)
+        err = np.abs(wg[ok] - wo[ok])
+        tol = RELTOL * np.abs(wo[ok]) + ABSTOL
+        rep["compared_points"] += int(ok.sum())
+        if err.size:
+            ratio = err / tol
+            j = int(np.argmax(ratio))
+            if ratio[j] > rep["max_rel"]:
+                rep["max_rel"] = float(ratio[j])
+                rep["max_abs"] = float(err[j])
+                rep["worst"] = (i, float(wg[ok][j]), float(wo[ok][j]))
+    return rep
+
+
+def report_ok(rep) -> bool:
+    return (rep["row_mismatch"] == 0 and rep["status_mismatch"] == 0 and rep["nan_mismatch"] == 0
+            and rep["max_rel"] <= 1.0)

@@ -1,0 +1,558 @@
+"""ctypes binding of libtspice_b200.so (include/tspice_b200.h) + a host-side mirror of the
+reference's analysis API for the batched path.
+
+The mirror keeps the reference's names and call sequence so that tests read like reference usage
+(cmd/spice/main.go:364-449, cmd/examples/rr/main.go:14-54):
+
+    ckt = Circuit.from_netlist(text)              # netlist.Parse + AssignNodeBranchMaps + CreateMatrix + SetupDevices
+    tr = NewTransient(tstart, tstop, tstep, tmax, uic)     # analysis.NewTransient        tran.go:29
+    tr.Setup(ckt); tr.Execute(); tr.GetResults()  # analysis.Analysis interface   anlysis.go:18-22
+
+with one addition — the batch axis: `ckt.batch(n)` + `set_param(...)` give every instance its own
+parameter draw, and `GetResults(inst)` / `waveforms()` / `stats()` read per-instance results.
+Errors follow the reference: Go `error` returns become `TsbError` (same message text where the
+reference has one), Go panics (`inconsistent parameter lengths`, dc.go:21-23) become ValueError.
+
+There is no CPU fallback anywhere in this module: without the CUDA library / a GPU every analysis
+raises TsbError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+AN_OP, AN_TRAN, AN_AC, AN_DC = 0, 1, 2, 3
+OUT_WAVE, OUT_STATS = 1, 2
+K_R, K_C, K_L, K_V, K_I, K_D, K_Q, K_M, K_K, K_LCORE = range(10)
+ST_OK, ST_OP_FAILED, ST_TRAN_FAILED, ST_DC_FAILED, ST_OVERFLOW = range(5)
+
+# every symbol include/tspice_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tsb_default_opts", "tsb_version", "tsb_ctx_create", "tsb_ctx_destroy", "tsb_last_error", "tsb_ctx_set_stream",
+    "tsb_ctx_set_cache_dir", "tsb_ctx_measure_fp64_peak", "tsb_ctx_sm_count", "tsb_plan_create",
+    "tsb_plan_from_netlist", "tsb_plan_add_device", "tsb_plan_finalize", "tsb_plan_destroy", "tsb_plan_error",
+    "tsb_plan_size", "tsb_plan_num_devices", "tsb_plan_device_info", "tsb_plan_device_params",
+    "tsb_plan_find_device", "tsb_plan_node_name", "tsb_plan_analysis", "tsb_plan_structure", "tsb_plan_pattern",
+    "tsb_plan_num_columns", "tsb_plan_column_name", "tsb_batch_create", "tsb_batch_destroy", "tsb_batch_set_param",
+    "tsb_batch_set_param_dev", "tsb_batch_set_param_uniform", "tsb_run_op", "tsb_run_tran", "tsb_run_dc",
+    "tsb_batch_sync", "tsb_result_dims", "tsb_result_dev_ptrs", "tsb_result_rows", "tsb_result_status",
+    "tsb_result_counters", "tsb_result_waveform", "tsb_result_wave_all", "tsb_result_stats_all",
+    "tsb_result_totals", "tsb_batch_kernel_source", "tsb_batch_kernel_key", "tsb_ctx_launch_count",
+]
+
+
+class TsbError(RuntimeError):
+    pass
+
+
+class Opts(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("abstol", C.c_double), ("reltol", C.c_double), ("gmin", C.c_double),
+                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("reuse_lu", C.c_int)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libtspice_b200.so")
+
+
+def lib():
+    """Loads the CUDA extension.  Fails loudly if it has not been built (__graft_entry__.build())."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise TsbError(f"{path} is missing: run __graft_entry__.build() (make -C toy-spice_b200/csrc)")
+        L = C.CDLL(path)
+        vp, i32, i64, dbl, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint64
+        P = C.POINTER
+        sig = {
+            "tsb_default_opts": (None, [P(Opts)]),
+            "tsb_version": (C.c_char_p, []),
+            "tsb_ctx_create": (i32, [i32, P(vp)]),
+            "tsb_ctx_destroy": (None, [vp]),
+            "tsb_last_error": (C.c_char_p, [vp]),
+            "tsb_ctx_set_stream": (i32, [vp, u64]),
+            "tsb_ctx_set_cache_dir": (i32, [vp, C.c_char_p]),
+            "tsb_ctx_measure_fp64_peak": (i32, [vp, P(dbl)]),
+            "tsb_ctx_sm_count": (i32, [vp, P(i32)]),
+            "tsb_ctx_launch_count": (i64, [vp]),
+            "tsb_plan_create": (i32, [vp, i32, i32, P(vp)]),
+            "tsb_plan_from_netlist": (i32, [vp, C.c_char_p, P(vp)]),
+            "tsb_plan_add_device": (i32, [vp, i32, C.c_char_p, P(i32), i32, i32, P(dbl), i32, P(i32), i32]),
+            "tsb_plan_finalize": (i32, [vp]),
+            "tsb_plan_destroy": (None, [vp]),
+            "tsb_plan_error": (C.c_char_p, [vp]),
+            "tsb_plan_size": (i32, [vp, P(i32), P(i32)]),
+            "tsb_plan_num_devices": (i32, [vp]),
+            "tsb_plan_device_info": (i32, [vp, i32, P(i32), P(C.c_char_p), P(i32), P(i32), P(i32), P(i32)]),
+            "tsb_plan_device_params": (i32, [vp, i32, P(dbl), i32, P(i32), i32]),
+            "tsb_plan_find_device": (i32, [vp, C.c_char_p]),
+            "tsb_plan_node_name": (i32, [vp, i32, P(C.c_char_p)]),
+            "tsb_plan_analysis": (i32, [vp, P(i32), P(dbl), P(i32), P(i32), P(dbl)]),
+            "tsb_plan_structure": (i32, [vp, P(i32), P(i32), P(i32)]),
+            "tsb_plan_pattern": (i32, [vp, i32, P(i32), P(i32), i32, P(i32)]),
+            "tsb_plan_num_columns": (i32, [vp, i32]),
+            "tsb_plan_column_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
+            "tsb_batch_create": (i32, [vp, i64, P(vp)]),
+            "tsb_batch_destroy": (None, [vp]),
+            "tsb_batch_set_param": (i32, [vp, i32, i32, P(dbl)]),
+            "tsb_batch_set_param_dev": (i32, [vp, i32, i32, u64]),
+            "tsb_batch_set_param_uniform": (i32, [vp, i32, i32, dbl]),
+            "tsb_run_op": (i32, [vp, P(Opts)]),
+            "tsb_run_tran": (i32, [vp, dbl, dbl, dbl, dbl, i32, i32, i64, P(Opts)]),
+            "tsb_run_dc": (i32, [vp, i32, dbl, dbl, dbl, i32, P(Opts)]),
+            "tsb_batch_sync": (i32, [vp]),
+            "tsb_result_dims": (i32, [vp, P(i64), P(i32), P(i64)]),
+            "tsb_result_dev_ptrs": (i32, [vp, P(u64), P(u64), P(u64), P(u64), P(u64)]),
+            "tsb_result_rows": (i32, [vp, P(i64)]),
+            "tsb_result_status": (i32, [vp, P(C.c_int32)]),
+            "tsb_result_counters": (i32, [vp, P(i64)]),
+            "tsb_result_waveform": (i32, [vp, i64, P(dbl), i64, P(i64)]),
+            "tsb_result_wave_all": (i32, [vp, P(dbl), i64]),
+            "tsb_result_stats_all": (i32, [vp, P(dbl)]),
+            "tsb_result_totals": (i32, [vp, P(i64)]),
+            "tsb_batch_kernel_source": (i32, [vp, P(Opts), C.c_char_p, i64, P(i64)]),
+            "tsb_batch_kernel_key": (i32, [vp, P(Opts), C.c_char_p, i32]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def default_opts(**kw) -> Opts:
+    o = Opts()
+    lib().tsb_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Context:
+    """One GPU (one process per GPU).  `tsb_ctx_create`."""
+
+    def __init__(self, device: int = 0):
+        self.h = C.c_void_p()
+        rc = lib().tsb_ctx_create(device, C.byref(self.h))
+        if rc != 0:
+            raise TsbError(f"tsb_ctx_create({device}) failed ({rc}): {lib().tsb_last_error(None).decode()}")
+        self.device = device
+
+    def _check(self, rc: int, what: str = ""):
+        if rc < 0:
+            raise TsbError(f"{what} failed ({rc}): {lib().tsb_last_error(self.h).decode()}")
+        return rc
+
+    def set_stream(self, stream: int):
+        self._check(lib().tsb_ctx_set_stream(self.h, stream), "set_stream")
+
+    def set_cache_dir(self, d: str):
+        self._check(lib().tsb_ctx_set_cache_dir(self.h, d.encode()), "set_cache_dir")
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(lib().tsb_ctx_measure_fp64_peak(self.h, C.byref(v)), "measure_fp64_peak")
+        return v.value
+
+    @property
+    def sm_count(self) -> int:
+        v = C.c_int()
+        self._check(lib().tsb_ctx_sm_count(self.h, C.byref(v)))
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        return lib().tsb_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().tsb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Circuit:
+    """The numbered netlist (reference: *circuit.Circuit after SetupDevices).  ctx may be None for
+    host-only use (structure queries, kernel source generation)."""
+
+    def __init__(self, ctx: Context | None, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    # -- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_netlist(cls, text: str, ctx: Context | None = None) -> "Circuit":
+        h = C.c_void_p()
+        rc = lib().tsb_plan_from_netlist(ctx.h if ctx else None, text.encode(), C.byref(h))
+        if rc != 0:
+            raise TsbError(f"netlist error ({rc}): {lib().tsb_last_error(ctx.h if ctx else None).decode()}")
+        return cls(ctx, h)
+
+    @classmethod
+    def from_devices(cls, n_nodes: int, n_branches: int, devices, ctx: Context | None = None) -> "Circuit":
+        """devices: iterable of (kind, name, nodes, branch, p, ip) — what a host with the reference's own
+        parser would pass after AssignNodeBranchMaps."""
+        h = C.c_void_p()
+        rc = lib().tsb_plan_create(ctx.h if ctx else None, n_nodes, n_branches, C.byref(h))
+        if rc != 0:
+            raise TsbError("tsb_plan_create failed")
+        for kind, name, nodes, branch, p, ip in devices:
+            rc = lib().tsb_plan_add_device(h, kind, name.encode(), (C.c_int * max(1, len(nodes)))(*nodes), len(nodes), branch,
+                                           (C.c_double * max(1, len(p)))(*p), len(p), (C.c_int * max(1, len(ip)))(*ip), len(ip))
+            if rc < 0:
+                raise TsbError(f"tsb_plan_add_device({name}) failed")
+        rc = lib().tsb_plan_finalize(h)
+        if rc != 0:
+            msg = lib().tsb_plan_error(h).decode()
+            lib().tsb_plan_destroy(h)
+            raise TsbError(f"tsb_plan_finalize failed ({rc}): {msg}")
+        return cls(ctx, h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().tsb_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- reference-style accessors (circuit.go:226-240) ----------------------------------------
+    def size(self):
+        a, b = C.c_int(), C.c_int()
+        lib().tsb_plan_size(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    @property
+    def n(self) -> int:
+        a, b = self.size()
+        return a + b
+
+    def GetNodeMap(self) -> dict:
+        nn, _ = self.size()
+        out = {}
+        for i in range(1, nn + 1):
+            s = C.c_char_p()
+            if lib().tsb_plan_node_name(self.h, i, C.byref(s)) == 0:
+                out[s.value.decode()] = i
+        return out
+
+    def devices(self):
+        out = []
+        for d in range(lib().tsb_plan_num_devices(self.h)):
+            kind, name, nodes, br, npar, nip = C.c_int(), C.c_char_p(), (C.c_int * 4)(), C.c_int(), C.c_int(), C.c_int()
+            nn = lib().tsb_plan_device_info(self.h, d, C.byref(kind), C.byref(name), nodes, C.byref(br), C.byref(npar), C.byref(nip))
+            p = (C.c_double * max(1, npar.value))()
+            ip = (C.c_int * max(1, nip.value))()
+            lib().tsb_plan_device_params(self.h, d, p, npar.value, ip, nip.value)
+            out.append(dict(kind=kind.value, name=name.value.decode(), nodes=list(nodes)[:nn], branch=br.value,
+                            p=list(p)[:npar.value], ip=list(ip)[:nip.value]))
+        return out
+
+    def GetBranchMap(self) -> dict:
+        return {d["name"]: d["branch"] for d in self.devices() if d["branch"] > 0}
+
+    def dev_index(self, name: str) -> int:
+        i = lib().tsb_plan_find_device(self.h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def analysis_card(self) -> dict:
+        an, uic, src = C.c_int(), C.c_int(), C.c_int()
+        tran = (C.c_double * 4)()
+        dc = (C.c_double * 3)()
+        lib().tsb_plan_analysis(self.h, C.byref(an), tran, C.byref(uic), C.byref(src), dc)
+        return dict(analysis=an.value, tstart=tran[0], tstop=tran[1], tstep=tran[2], tmax=tran[3], uic=bool(uic.value),
+                    dc_src_dev=src.value, dc_start=dc[0], dc_stop=dc[1], dc_inc=dc[2])
+
+    def structure(self) -> dict:
+        n = self.n
+        a, b, c = (C.c_int * (n + 1))(), (C.c_int * (n + 1))(), (C.c_int * (n + 1))()
+        if lib().tsb_plan_structure(self.h, a, b, c) != 0:
+            raise TsbError("plan not finalized")
+        return dict(ext2int=list(a)[1:], pivot_row=list(b)[1:], pivot_col=list(c)[1:])
+
+    def pattern(self, mode: int = 0):
+        nnz = C.c_int()
+        lib().tsb_plan_pattern(self.h, mode, None, None, 0, C.byref(nnz))
+        r, c = (C.c_int * max(1, nnz.value))(), (C.c_int * max(1, nnz.value))()
+        lib().tsb_plan_pattern(self.h, mode, r, c, nnz.value, C.byref(nnz))
+        return list(zip(list(r)[:nnz.value], list(c)[:nnz.value]))
+
+    def columns(self, analysis: int):
+        n = lib().tsb_plan_num_columns(self.h, analysis)
+        buf = C.create_string_buffer(128)
+        out = []
+        for k in range(n):
+            lib().tsb_plan_column_name(self.h, analysis, k, buf, 128)
+            out.append(buf.value.decode())
+        return out
+
+    def batch(self, n_inst: int) -> "Batch":
+        return Batch(self, n_inst)
+
+
+class Batch:
+    """N instances of one circuit; per-instance parameters in HBM as one array per swept parameter."""
+
+    def __init__(self, ckt: Circuit, n_inst: int):
+        self.ckt = ckt
+        self.n_inst = int(n_inst)
+        self.h = C.c_void_p()
+        rc = lib().tsb_batch_create(ckt.h, self.n_inst, C.byref(self.h))
+        if rc != 0:
+            raise TsbError(f"tsb_batch_create failed ({rc})")
+        self._keep = []
+
+    def _err(self) -> str:
+        return lib().tsb_last_error(self.ckt.ctx.h if self.ckt.ctx else None).decode()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise TsbError(f"{what} failed ({rc}): {self._err()}")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().tsb_batch_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _dev(self, dev) -> int:
+        return self.ckt.dev_index(dev) if isinstance(dev, str) else int(dev)
+
+    def set_param(self, dev, param: int, values):
+        """values: host array [n_inst] (copied H2D), a scalar (uniform), or a CUDA torch tensor (borrowed)."""
+        d = self._dev(dev)
+        if np.isscalar(values):
+            self._check(lib().tsb_batch_set_param_uniform(self.h, d, param, float(values)), "set_param_uniform")
+            return
+        if hasattr(values, "is_cuda") and values.is_cuda:
+            import torch
+            assert values.dtype == torch.float64 and values.is_contiguous() and values.numel() == self.n_inst
+            self._keep.append(values)
+            self._check(lib().tsb_batch_set_param_dev(self.h, d, param, values.data_ptr()), "set_param_dev")
+            return
+        if hasattr(values, "numpy"):
+            values = values.numpy()
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.shape != (self.n_inst,):
+            raise ValueError("values must have shape [n_inst]")
+        self._keep.append(v)
+        self._check(lib().tsb_batch_set_param(self.h, d, param, v.ctypes.data_as(C.POINTER(C.c_double))), "set_param")
+
+    # -- kernel introspection -------------------------------------------------------------------
+    def kernel_source(self, opts: Opts | None = None) -> str:
+        need = C.c_int64()
+        o = C.byref(opts) if opts is not None else None
+        lib().tsb_batch_kernel_source(self.h, o, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        lib().tsb_batch_kernel_source(self.h, o, buf, need.value, C.byref(need))
+        return buf.value.decode()
+
+    def kernel_key(self, opts: Opts | None = None) -> str:
+        buf = C.create_string_buffer(64)
+        lib().tsb_batch_kernel_key(self.h, C.byref(opts) if opts is not None else None, buf, 64)
+        return buf.value.decode()
+
+    # -- runs -----------------------------------------------------------------------------------
+    def run_op(self, opts: Opts | None = None):
+        self._check(lib().tsb_run_op(self.h, C.byref(opts) if opts is not None else None), "tsb_run_op")
+
+    def run_tran(self, tstart, tstop, tstep, tmax=0.0, uic=False, out=OUT_WAVE, cap_rows=0, opts: Opts | None = None):
+        self._check(lib().tsb_run_tran(self.h, tstart, tstop, tstep, tmax, int(uic), out, cap_rows,
+                                       C.byref(opts) if opts is not None else None), "tsb_run_tran")
+
+    def run_dc(self, src, start, stop, inc, out=OUT_WAVE, opts: Opts | None = None):
+        self._check(lib().tsb_run_dc(self.h, self._dev(src), start, stop, inc, out,
+                                     C.byref(opts) if opts is not None else None), "tsb_run_dc")
+
+    def sync(self):
+        self._check(lib().tsb_batch_sync(self.h), "tsb_batch_sync")
+
+    # -- results --------------------------------------------------------------------------------
+    def dims(self):
+        n, c, r = C.c_int64(), C.c_int(), C.c_int64()
+        lib().tsb_result_dims(self.h, C.byref(n), C.byref(c), C.byref(r))
+        return n.value, c.value, r.value
+
+    def rows(self) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int64)
+        self._check(lib().tsb_result_rows(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_rows")
+        return out
+
+    def status(self) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int32)
+        self._check(lib().tsb_result_status(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))), "result_status")
+        return out
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros((6, self.n_inst), dtype=np.int64)
+        self._check(lib().tsb_result_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_counters")
+        return out
+
+    def totals(self) -> np.ndarray:
+        out = np.zeros(4, dtype=np.int64)
+        self._check(lib().tsb_result_totals(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_totals")
+        return out
+
+    def waveform(self, inst: int) -> np.ndarray:
+        _, ncol, cap = self.dims()
+        out = np.zeros((max(1, cap), ncol))
+        nr = C.c_int64()
+        self._check(lib().tsb_result_waveform(self.h, inst, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(nr)), "result_waveform")
+        return out[: nr.value]
+
+    def wave_all(self) -> np.ndarray:
+        """[cap_rows, ncol, n_inst] exactly as laid out in HBM."""
+        n, ncol, cap = self.dims()
+        out = np.zeros((cap, ncol, n))
+        self._check(lib().tsb_result_wave_all(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size), "result_wave_all")
+        return out
+
+    def stats_all(self) -> np.ndarray:
+        n, ncol, _ = self.dims()
+        out = np.zeros((4, ncol, n))
+        self._check(lib().tsb_result_stats_all(self.h, out.ctypes.data_as(C.POINTER(C.c_double))), "result_stats_all")
+        return out
+
+    def dev_ptrs(self) -> dict:
+        v = [C.c_uint64() for _ in range(5)]
+        lib().tsb_result_dev_ptrs(self.h, *[C.byref(x) for x in v])
+        return dict(zip(("wave", "stats", "rows", "status", "counters"), [x.value for x in v]))
+
+
+# ---------------------------------------------------------------------------------------------
+# Mirror of pkg/analysis: Analysis{Setup, Execute, GetResults} over a Batch.
+class _BaseAnalysis:
+    """BaseAnalysis (anlysis.go:24-44).  Tolerances live in `self.opts` with the reference's defaults."""
+
+    def __init__(self):
+        self.opts = default_opts()
+        self.Circuit = None
+        self.batch = None
+
+    def Setup(self, ckt, batch: Batch | None = None):
+        """ckt: Circuit (batch of 1, nominal values) or a Batch."""
+        if isinstance(ckt, Batch):
+            self.batch, self.Circuit = ckt, ckt.ckt
+        else:
+            self.Circuit = ckt
+            self.batch = batch if batch is not None else ckt.batch(1)
+        if self.Circuit.ctx is None:
+            raise TsbError("circuit not set on a GPU context")      # tran.go:78-80 "circuit not set"
+        return None
+
+    def _columns(self):
+        return self.Circuit.columns(self._analysis)
+
+    def GetResults(self, inst: int = 0) -> dict:
+        """map[string][]float64 of one instance (anlysis.go:113-115)."""
+        w = self.batch.waveform(inst)
+        return {name: w[:, k].copy() for k, name in enumerate(self._columns())}
+
+    def status(self):
+        return self.batch.status()
+
+    def _raise_first_failure(self):
+        pass
+
+
+class OperatingPoint(_BaseAnalysis):
+    _analysis = AN_OP
+
+    def Execute(self):
+        if self.batch is None:
+            raise TsbError("circuit not set")
+        self.batch.run_op(self.opts)
+        self.batch.sync()
+        return None
+
+
+class Transient(_BaseAnalysis):
+    _analysis = AN_TRAN
+
+    def __init__(self, tStart, tStop, tStep, tMax, uic):
+        super().__init__()
+        self.startTime, self.stopTime, self.timeStep, self.maxStep, self.useUIC = tStart, tStop, tStep, tMax, bool(uic)
+        self.out = OUT_WAVE
+        self.cap_rows = 0
+
+    def Execute(self):
+        if self.batch is None:
+            raise TsbError("circuit not set")                         # tran.go:78-80
+        cap = self.cap_rows
+        if (self.out & OUT_WAVE) and cap <= 0:
+            # accepted steps are >= minStep apart except after rejections: 50*300 + slack rows always suffice
+            # for the bundled decks only when dedup applies; default to a generous bound and report overflow.
+            cap = 16384
+        self.batch.run_tran(self.startTime, self.stopTime, self.timeStep, self.maxStep, self.useUIC, self.out, cap, self.opts)
+        self.batch.sync()
+        return None
+
+
+class DCSweep(_BaseAnalysis):
+    _analysis = AN_DC
+
+    def __init__(self, sources, starts, stops, increments):
+        super().__init__()
+        if not (len(sources) == len(starts) == len(stops) == len(increments)):
+            raise ValueError("inconsistent parameter lengths")          # dc.go:21-23 (panic)
+        self.sourceNames, self.startVals, self.stopVals, self.increments = list(sources), list(starts), list(stops), list(increments)
+        self.out = OUT_WAVE
+
+    def Setup(self, ckt, batch=None):
+        super().Setup(ckt, batch)
+        for name in self.sourceNames:
+            try:
+                d = self.Circuit.dev_index(name)
+            except KeyError:
+                raise TsbError(f"source {name} not found")               # dc.go:64-66
+            if self.Circuit.devices()[d]["kind"] != K_V:
+                raise TsbError(f"source {name} not found")
+        return None
+
+    def Execute(self):
+        if self.batch is None:
+            raise TsbError("circuit not set")
+        if len(self.sourceNames) != 1:
+            raise TsbError(f"unsupported number of sweep sources: {len(self.sourceNames)}")   # dc.go:86 (nested: not batched yet)
+        self.batch.run_dc(self.sourceNames[0], self.startVals[0], self.stopVals[0], self.increments[0], self.out, self.opts)
+        self.batch.sync()
+        return None
+
+
+def NewOP():
+    return OperatingPoint()
+
+
+def NewTransient(tStart, tStop, tStep, tMax, uic):
+    return Transient(tStart, tStop, tStep, tMax, uic)
+
+
+def NewDCSweep(sources, starts, stops, numSteps):
+    return DCSweep(sources, starts, stops, numSteps)
+
+
+def analysis_from_card(ckt: Circuit):
+    """What cmd/spice/main.go:403-436 builds from the netlist's dot-cards."""
+    card = ckt.analysis_card()
+    if card["analysis"] == AN_OP:
+        return NewOP()
+    if card["analysis"] == AN_TRAN:
+        return NewTransient(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"])
+    if card["analysis"] == AN_DC:
+        name = ckt.devices()[card["dc_src_dev"]]["name"]
+        return NewDCSweep([name], [card["dc_start"]], [card["dc_stop"]], [card["dc_inc"]])
+    raise TsbError("Unsupported analysis type")

@@ -1,0 +1,381 @@
+// codegen.cpp — emits the netlist-specialised CUDA translation unit for one plan.
+//
+// Why specialise: every instance of a batch shares the netlist, so the stamp pattern, the pivot
+// order and the fill pattern are compile-time facts.  The generated `struct Ckt` holds all per-
+// instance data in arrays that are only ever indexed by literals — after inlining, ptxas keeps
+// parameters, device state, the matrix and the solution vectors in registers, and the LU is a
+// straight line of DFMA / DMUL / reciprocal instructions with no index arithmetic, no shared
+// memory and no shuffles (one circuit per thread; the matrices are 1x1 .. ~12x12).
+//
+// What the generated code restates (per Newton iteration):
+//   mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin); mat.Solve()      op.go:46-65, tran.go:172-190
+// with the per-device stamp arithmetic delegated to device/models.cuh and the analysis drivers
+// to device/skeleton.cuh (both embedded verbatim so the unit compiles under NVRTC and nvcc alike).
+#include <cstdio>
+#include <sstream>
+#include "tsb_internal.hpp"
+
+namespace tsb {
+
+static const char* k_models_src =
+#include "models_src.inc"
+    ;
+static const char* k_skeleton_src =
+#include "skeleton_src.inc"
+    ;
+
+namespace {
+
+std::string dlit(double v) {
+    char buf[64];
+    if (v == (long long)v && v > -1e15 && v < 1e15) snprintf(buf, sizeof buf, "%lld.0", (long long)v);
+    else snprintf(buf, sizeof buf, "%.17g", v);
+    return buf;
+}
+
+struct Emitter {
+    std::ostringstream os;
+    int ind = 0;
+    void line(const std::string& s) { for (int i = 0; i < ind; ++i) os << "    "; os << s << "\n"; }
+};
+
+const char* kind_name(int k) {
+    static const char* n[] = {"R", "C", "L", "V", "I", "D", "Q", "M", "K", "LCORE"};
+    return (k >= 0 && k < 10) ? n[k] : "?";
+}
+
+// o[] evaluation of one device inside a stamp routine
+void emit_eval(Emitter& e, const Plan& pl, int di, const std::string& ov) {
+    const Dev& d = pl.devs[di];
+    std::string P = "P + " + std::to_string(d.p_off), S = "S + " + std::to_string(d.s_off);
+    int no = device_num_outputs(d);
+    if (no > 0) e.line("double " + ov + "[" + std::to_string(no) + "];");
+    switch (d.kind) {
+    case TSB_R: e.line(ov + "[0] = D[" + std::to_string(d.d_off) + "];"); break;
+    case TSB_C: e.line("tsb_cap_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
+    case TSB_L: e.line("tsb_ind_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
+    case TSB_LCORE: e.line("tsb_lcore_eval(D[" + std::to_string(d.d_off) + "], e, " + ov + ");"); break;
+    case TSB_D: e.line("tsb_dio_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
+    case TSB_Q: e.line("tsb_bjt_eval(" + P + ", " + S + ", " + std::to_string(d.ip.empty() ? 0 : d.ip[0]) + ", " + ov + ");"); break;
+    case TSB_M:
+        e.line("tsb_mos_eval(" + P + ", " + S + ", " + std::to_string(d.ip.size() > 0 ? d.ip[0] : 1) + ", " +
+               std::to_string(d.ip.size() > 1 ? d.ip[1] : 0) + ", e, " + ov + ");");
+        break;
+    case TSB_K: {
+        int m = (int)d.ip.size(), q = 0;
+        auto cur = [&](int idx) {
+            const Dev& l = pl.devs[idx];
+            return l.kind == TSB_LCORE ? std::string("0.0") : "S[" + std::to_string(l.s_off) + "]";
+        };
+        for (int i = 0; i < m; ++i)
+            for (int j = i + 1; j < m; ++j, ++q)
+                e.line("tsb_mut_eval(D[" + std::to_string(d.d_off + q) + "], " + cur(d.ip[i]) + ", " + cur(d.ip[j]) + ", e, " + ov +
+                       " + " + std::to_string(3 * q) + ");");
+        break;
+    }
+    default: break;
+    }
+}
+
+// Emits the stamps of the listed devices into A[] (indexed through `lu.index`) and b[].
+void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only) {
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (linear_only && d.nonlinear()) continue;
+        if (op_only && d.kind == TSB_K) continue;
+        e.line("{   // " + std::string(kind_name(d.kind)) + " " + d.name);
+        ++e.ind;
+        std::string ov = "o";
+        emit_eval(e, pl, di, ov);
+        for (const StampEntry& s : pl.stamps[di]) {
+            if (op_only && s.tran_only) continue;
+            std::string val;
+            if (s.out == -1) val = dlit(s.cval);
+            else if (s.out == -2) val = "SV[" + std::to_string(d.src_slot) + "]";
+            else val = ov + "[" + std::to_string(s.out) + "]";
+            std::string tgt;
+            if (s.col == 0) tgt = "b[" + std::to_string(s.row) + "]";
+            else {
+                auto it = lu.index.find({s.row, s.col});
+                if (it == lu.index.end()) continue;     // cannot happen: pattern built from these entries
+                tgt = "A[" + std::to_string(it->second) + "]";
+            }
+            e.line(tgt + (s.sign < 0 ? " -= " : " += ") + val + ";");
+        }
+        --e.ind;
+        e.line("}");
+    }
+}
+
+// Factor + solve in the frozen order.  Same operation order per element as Sparse 1.3's
+// spFactor/spSolve (u = a*(1/pivot); a_ij -= u_kj*l_ik for k ascending; forward with reciprocal
+// pivots; back-substitution in ascending column order), so --fmad=false reproduces its rounding.
+void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string& xout) {
+    const int n = lu.n;
+    if (load_gmin) {
+        e.line("if (gmin != 0.0) {   // LoadGmin: added to the pivot positions (Diags[i] after reordering, SURVEY Q17)");
+        ++e.ind;
+        for (int k = 1; k <= n; ++k) e.line("A[" + std::to_string(lu.steps[k].piv) + "] += gmin;");
+        --e.ind;
+        e.line("}");
+    }
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        std::string piv = "A[" + std::to_string(st.piv) + "]";
+        e.line("// step " + std::to_string(k) + ": pivot (" + std::to_string(lu.prow[k]) + "," + std::to_string(lu.pcol[k]) + ")");
+        e.line("if (" + piv + " == 0.0) return false;");
+        e.line(piv + " = 1.0 / " + piv + ";");
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            std::string u = "A[" + std::to_string(st.urow[ui]) + "]";
+            e.line(u + " *= " + piv + ";");
+            for (size_t li = 0; li < st.lcol.size(); ++li)
+                e.line("A[" + std::to_string(st.target[ui][li]) + "] -= " + u + " * A[" + std::to_string(st.lcol[li]) + "];");
+        }
+    }
+    e.line("double c[" + std::to_string(n + 1) + "];");
+    for (int k = 1; k <= n; ++k) e.line("c[" + std::to_string(k) + "] = b[" + std::to_string(lu.prow[k]) + "];");
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        std::string ck = "c[" + std::to_string(k) + "]";
+        if (lu.dense) { e.line("if (" + ck + " != 0.0) {"); ++e.ind; }
+        e.line(ck + " *= A[" + std::to_string(st.piv) + "];");
+        for (size_t li = 0; li < st.lcol.size(); ++li)
+            e.line("c[" + std::to_string(st.lrow_step[li]) + "] -= " + ck + " * A[" + std::to_string(st.lcol[li]) + "];");
+        if (lu.dense) { --e.ind; e.line("}"); }
+    }
+    for (int k = n; k >= 1; --k) {
+        const LuProgram::Step& st = lu.steps[k];
+        for (size_t ui = 0; ui < st.urow.size(); ++ui)
+            e.line("c[" + std::to_string(k) + "] -= A[" + std::to_string(st.urow[ui]) + "] * c[" + std::to_string(st.ucol_step[ui]) + "];");
+    }
+    for (int k = 1; k <= n; ++k) e.line(xout + "[" + std::to_string(lu.pcol[k]) + "] = c[" + std::to_string(k) + "];");
+}
+
+}  // namespace
+
+std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
+    Emitter e;
+    const int n = pl.n();
+    const int ncol_tran = pl.num_columns(TSB_AN_TRAN);
+    e.line("// Generated by tspice_b200 codegen for netlist \"" + pl.title + "\": n=" + std::to_string(n) + ", " +
+           std::to_string(pl.devs.size()) + " devices, " + std::to_string(pl.lu_main.pos.size()) + " matrix entries incl. fill" +
+           (pl.lu_main.dense ? " (dense)" : "") + ".");
+    e.line("#define TSB_BLOCK " + std::to_string(cfg.block_size));
+    e.os << k_models_src << "\n" << k_skeleton_src << "\n";
+
+    e.line("struct Ckt {");
+    ++e.ind;
+    e.line("static constexpr int N = " + std::to_string(n) + ";");
+    e.line("static constexpr int NCOL_MAX = " + std::to_string(ncol_tran) + ";");
+    e.line("static constexpr bool HAS_NL = " + std::string(pl.has_nonlinear ? "true" : "false") + ";");
+    e.line("double P[" + std::to_string(std::max(1, pl.n_params)) + "];      // parameters");
+    e.line("double S[" + std::to_string(std::max(1, pl.n_state)) + "];      // device state carried between solves");
+    e.line("double D[" + std::to_string(std::max(1, pl.n_derived)) + "];      // per-instance constants derived from P (1/R, L0, M)");
+    e.line("double SV[" + std::to_string(std::max(1, pl.n_src)) + "];     // source values of the current solve context");
+    e.line("double x[" + std::to_string(n + 1) + "], xo[" + std::to_string(n + 1) + "];   // mat.Solution() and oldSolution (index 0 = ground)");
+    e.line("const double* U_;");
+    e.line("");
+
+    // ---- load -----------------------------------------------------------------------------
+    e.line("__device__ __forceinline__ void load(const TsbArgs& a, long long inst) {");
+    ++e.ind;
+    e.line("U_ = a.U;");
+    for (const Dev& d : pl.devs) {
+        if ((d.kind == TSB_V || d.kind == TSB_I) && d.src_type() == TSB_SRC_PWL) continue;   // PWL tables stay in global memory
+        for (size_t j = 0; j < d.p.size(); ++j) {
+            int k = d.p_off + (int)j;
+            if (cfg.varying[k])
+                e.line("P[" + std::to_string(k) + "] = __ldcs(a.pv[" + std::to_string(cfg.var_slot[k]) + "] + inst);   // " + d.name + " p" + std::to_string(j));
+            else
+                e.line("P[" + std::to_string(k) + "] = a.U[" + std::to_string(k) + "];");
+        }
+    }
+    for (int i = 0; i < std::max(1, pl.n_state); ++i) e.line("S[" + std::to_string(i) + "] = 0.0;");
+    for (int i = 0; i <= n; ++i) e.line("x[" + std::to_string(i) + "] = 0.0; xo[" + std::to_string(i) + "] = 0.0;");
+    for (int i = 0; i < std::max(1, pl.n_src); ++i) e.line("SV[" + std::to_string(i) + "] = 0.0;");
+    e.line("D[0] = 0.0;");
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        std::string P = "P + " + std::to_string(d.p_off);
+        if (d.kind == TSB_R) e.line("D[" + std::to_string(d.d_off) + "] = tsb_res_g(" + P + ");");
+        else if (d.kind == TSB_LCORE) e.line("D[" + std::to_string(d.d_off) + "] = tsb_lcore_L0(" + P + ");");
+        else if (d.kind == TSB_M) e.line("tsb_mos_init_state(" + P + ", S + " + std::to_string(d.s_off) + ");");
+        else if (d.kind == TSB_K) {
+            int m = (int)d.ip.size(), q = 0;
+            auto val = [&](int idx) {
+                const Dev& l = pl.devs[idx];
+                return l.kind == TSB_LCORE ? "D[" + std::to_string(l.d_off) + "]" : "P[" + std::to_string(l.p_off) + "]";
+            };
+            for (int i = 0; i < m; ++i)
+                for (int j = i + 1; j < m; ++j, ++q)
+                    e.line("D[" + std::to_string(d.d_off + q) + "] = tsb_mut_M(P[" + std::to_string(d.p_off) + "], " + val(d.ip[i]) + ", " + val(d.ip[j]) + ");");
+        }
+    }
+    --e.ind;
+    e.line("}");
+
+    // ---- init: side effects of SetupDevices' initial stamp (circuit.go:154-156) on device state
+    e.line("__device__ __forceinline__ void init() {");
+    ++e.ind;
+    if (pl.has_nonlinear) {
+        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = 0.0; e.gmin = 0.0;");
+        for (int di : pl.stamp_order) {
+            if (!pl.devs[di].nonlinear()) continue;
+            e.line("{");
+            ++e.ind;
+            emit_eval(e, pl, di, "o");
+            e.line("(void)o;");
+            --e.ind;
+            e.line("}");
+        }
+    }
+    --e.ind;
+    e.line("}");
+
+    // ---- sources ----------------------------------------------------------------------------
+    e.line("// VoltageSource.GetVoltage / CurrentSource.GetCurrent at Status.Time; `fac` = source-stepping factor");
+    e.line("__device__ __forceinline__ void eval_sources(double t, double fac) {");
+    ++e.ind;
+    for (const Dev& d : pl.devs) {
+        if (d.src_slot < 0) continue;
+        std::string sv = "SV[" + std::to_string(d.src_slot) + "]";
+        std::string P = "P + " + std::to_string(d.p_off);
+        // source stepping scales VoltageSource.dcValue only (op.go:118-124)
+        std::string fac = d.kind == TSB_V ? "fac" : "1.0";
+        switch (d.src_type()) {
+        case TSB_SRC_DC: e.line(sv + " = P[" + std::to_string(d.p_off) + "] * " + fac + ";"); break;
+        case TSB_SRC_SIN: e.line(sv + " = tsb_src_sin(" + P + ", t, " + fac + ");"); break;
+        case TSB_SRC_PULSE: e.line(sv + " = tsb_src_pulse(" + P + ", t);"); break;
+        case TSB_SRC_PWL: e.line(sv + " = tsb_src_pwl(U_ + " + std::to_string(d.p_off) + ", " + std::to_string(d.p.size() / 2) + ", t);"); break;
+        }
+    }
+    e.line("(void)t; (void)fac;");
+    --e.ind;
+    e.line("}");
+
+    // ---- DC sweep source override --------------------------------------------------------------
+    e.line("__device__ __forceinline__ void set_dc(double v) {");
+    ++e.ind;
+    if (cfg.dc_param >= 0) e.line("P[" + std::to_string(cfg.dc_param) + "] = v;   // VoltageSource.SetValue (vsource.go:241-244)");
+    e.line("(void)v;");
+    --e.ind;
+    e.line("}");
+
+    // ---- nonlinear voltage update ----------------------------------------------------------------
+    e.line("__device__ __forceinline__ void update_nl(const double* v) {   // circuit.UpdateNonlinearVoltages");
+    ++e.ind;
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (!d.nonlinear()) continue;
+        std::string S = "S + " + std::to_string(d.s_off);
+        auto v = [&](int k) { return "v[" + std::to_string(d.nodes[k]) + "]"; };
+        if (d.kind == TSB_D) e.line("S[" + std::to_string(d.s_off) + "] = " + v(0) + " - " + v(1) + ";");
+        else if (d.kind == TSB_Q) e.line("tsb_bjt_update(" + S + ", " + std::to_string(d.ip.empty() ? 0 : d.ip[0]) + ", " + v(0) + ", " + v(1) + ", " + v(2) + ");");
+        else e.line("tsb_mos_update(" + S + ", " + std::to_string(d.ip.size() > 1 ? d.ip[1] : 0) + ", " + v(0) + ", " + v(1) + ", " + v(2) + ", " + v(3) + ");");
+    }
+    e.line("(void)v;");
+    --e.ind;
+    e.line("}");
+
+    // ---- initial estimate -----------------------------------------------------------------------
+    e.line("// OperatingPoint.calculateInitialEstimate (op.go:90-111): separate sparse matrix, linear devices only");
+    e.line("__device__ __forceinline__ bool init_estimate(double status_dt, double* out) {");
+    ++e.ind;
+    if (pl.init_struct_singular) {
+        e.line("(void)status_dt; (void)out;");
+        e.line("return false;   // structurally singular without the nonlinear devices -> nil estimate");
+    } else {
+        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = status_dt; e.gmin = 0.0;");
+        e.line("double A[" + std::to_string(pl.lu_init.pos.size()) + "];");
+        e.line("double b[" + std::to_string(n + 1) + "];");
+        for (size_t k = 0; k < pl.lu_init.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;");
+        for (int i = 0; i <= n; ++i) e.line("b[" + std::to_string(i) + "] = 0.0;");
+        emit_stamps(e, pl, pl.lu_init, true, true);
+        e.line("double xt[" + std::to_string(n + 1) + "];");
+        emit_lu(e, pl.lu_init, false, "xt");
+        for (int i = 1; i <= n; ++i) e.line("out[" + std::to_string(i) + "] = xt[" + std::to_string(i) + "];");
+        e.line("return true;");
+    }
+    --e.ind;
+    e.line("}");
+
+    // ---- Newton body ----------------------------------------------------------------------------
+    e.line("// mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin); mat.Solve()  ->  x");
+    e.line("__device__ __forceinline__ bool assemble_solve(int mode, double time, double dt, double gmin) {");
+    ++e.ind;
+    e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin;");
+    e.line("double A[" + std::to_string(pl.lu_main.pos.size()) + "];");
+    e.line("double b[" + std::to_string(n + 1) + "];");
+    for (size_t k = 0; k < pl.lu_main.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;   // (" + std::to_string(pl.lu_main.pos[k].first) + "," + std::to_string(pl.lu_main.pos[k].second) + ")");
+    for (int i = 0; i <= n; ++i) e.line("b[" + std::to_string(i) + "] = 0.0;");
+    emit_stamps(e, pl, pl.lu_main, false, false);
+    e.line("double xt[" + std::to_string(n + 1) + "];");
+    emit_lu(e, pl.lu_main, true, "xt");
+    for (int i = 1; i <= n; ++i) e.line("x[" + std::to_string(i) + "] = xt[" + std::to_string(i) + "];");
+    e.line("return true;");
+    --e.ind;
+    e.line("}");
+
+    // ---- time-dependent device state -------------------------------------------------------------
+    auto vd_expr = [&](const Dev& d) {
+        return "(x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "])";
+    };
+    e.line("__device__ __forceinline__ void load_state(double dt) {   // circuit.LoadState (circuit.go:192-201)");
+    ++e.ind;
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (d.kind == TSB_L) e.line("tsb_ind_load(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ", dt);");
+    }
+    e.line("(void)dt;");
+    --e.ind;
+    e.line("}");
+    e.line("__device__ __forceinline__ void update_state() {   // circuit.Update (circuit.go:203-224)");
+    ++e.ind;
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (d.kind == TSB_C) e.line("tsb_cap_update(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ");");
+        if (d.kind == TSB_L) e.line("tsb_ind_update(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ");");
+    }
+    --e.ind;
+    e.line("}");
+    e.line("__device__ __forceinline__ double lte(double dt) {   // Transient.calculateTruncError (tran.go:239-250)");
+    ++e.ind;
+    e.line("double m = 0.0, l;");
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (d.kind == TSB_C) e.line("l = tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt); if (l > m) m = l;");
+        if (d.kind == TSB_L) e.line("l = tsb_ind_lte(S + " + std::to_string(d.s_off) + ", dt); if (l > m) m = l;");
+    }
+    e.line("(void)dt; (void)l;");
+    e.line("return m;");
+    --e.ind;
+    e.line("}");
+
+    // ---- signals -----------------------------------------------------------------------------------
+    e.line("__device__ __forceinline__ void signals(double* out) const {   // circuit.GetSolution (circuit.go:242-273)");
+    ++e.ind;
+    {
+        int k = 0;
+        for (int i = 1; i <= pl.n_nodes; ++i) e.line("out[" + std::to_string(k++) + "] = x[" + std::to_string(i) + "];");
+        for (int b = pl.n_nodes + 1; b <= n; ++b) e.line("out[" + std::to_string(k++) + "] = -x[" + std::to_string(b) + "];");
+        for (const Dev& d : pl.devs)
+            if (d.kind == TSB_R)
+                e.line("out[" + std::to_string(k++) + "] = (x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "]) / P[" + std::to_string(d.p_off) + "];   // I(" + d.name + ")");
+    }
+    --e.ind;
+    e.line("}");
+    --e.ind;
+    e.line("};");
+    e.line("");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_optran(TsbArgs a) {");
+    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_inst; inst += (long long)gridDim.x * blockDim.x)");
+    e.line("        tsb_run_optran_instance<Ckt>(a, inst);");
+    e.line("}");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
+    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_inst; inst += (long long)gridDim.x * blockDim.x)");
+    e.line("        tsb_run_dc_instance<Ckt>(a, inst);");
+    e.line("}");
+    return e.os.str();
+}
+
+}  // namespace tsb

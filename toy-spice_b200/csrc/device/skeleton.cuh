@@ -1,0 +1,364 @@
+// skeleton.cuh — per-thread analysis drivers of the batched engine (hand-written, generic).
+//
+// One GPU thread owns one circuit instance for the whole analysis: parameters, device state,
+// solution vectors and the MNA matrix live in registers; nothing is exchanged between threads.
+// The drivers are templated on a generated struct `Ckt` (codegen.cpp) that provides the
+// netlist-specific straight-line code (stamps, LU in the frozen pivot order, state updates).
+//
+// The drivers are written as ONE loop around ONE Newton-iteration body: every trip through
+// the loop performs exactly one "stamp + factor + solve + convergence test" for every live lane,
+// whatever phase that lane is in (operating point, Gmin stepping, source stepping, transient
+// step k, a rejected step being retried).  Lanes of a warp therefore never wait for each other
+// at step boundaries — a lane that needs 5 Newton iterations and its neighbour that needs 2 both
+// do useful work on every trip; only lanes that have finished idle until the warp's slowest lane is done.
+//
+// Reference behaviour reproduced (statement by statement; see SURVEY.md §3.6 for the quirks):
+//   OperatingPoint.Execute / doNRiter / calculateInitialEstimate / performSourceStepping   op.go:25-233
+//   Transient.Setup / Execute / doNRiter / calculateTruncError                            tran.go:57-250
+//   DCSweep.singleSweep / doNRiter, BaseAnalysis.CheckConvergence / StoreTimeResult       dc.go:88-187, anlysis.go:46-85
+#ifndef TSB_SKELETON_CUH
+#define TSB_SKELETON_CUH
+
+#define TSB_MAX_VARYING 64
+
+struct TsbArgs {
+    long long n_inst;
+    const double* pv[TSB_MAX_VARYING];   // per varying parameter: [n_inst] doubles (SoA, instance fastest)
+    const double* U;           // [n_params]       uniform parameter values (+ PWL tables)
+    int analysis;              // 0 OP, 1 TRAN, 3 DC
+    int uic;
+    double tstart, tstop, tstep, maxstep, minstep;   // after NewTransient's clamping (tran.go:29-37)
+    int max_iter;
+    double abstol, reltol, trtol;
+    int out_flags;             // 1 wave, 2 stats
+    long long cap_rows;
+    double* wave;              // [cap_rows][ncol][n_inst]
+    double* stats;             // [4][ncol][n_inst]
+    long long* rows;           // [n_inst]
+    int* status;               // [n_inst]
+    long long* counters;       // [6][n_inst]
+    double* scratch;           // [N+1][n_inst]  "currentSolution" of the OP fallbacks
+    const double* sweep;       // [n_sweep] DC sweep values
+    int n_sweep;
+};
+
+#define TSB_ST_OK 0
+#define TSB_ST_OP_FAILED 1
+#define TSB_ST_TRAN_FAILED 2
+#define TSB_ST_DC_FAILED 3
+#define TSB_ST_OVERFLOW 4
+#define TSB_AN_OP 0
+#define TSB_AN_TRAN 1
+#define TSB_AN_DC 3
+#define TSB_OUT_WAVE 1
+#define TSB_OUT_STATS 2
+
+extern __shared__ double tsb_smem[];
+
+// op.go:67-77 / tran.go:192-207: |new-old| <= reltol*max(|new|,|old|) + abstol for i = 1..n.
+// Written as "no element exceeds" so that NaN passes, as in the reference.
+template <int N>
+__device__ __forceinline__ bool tsb_converged(const double* x, const double* xo, double reltol, double abstol) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 1; i <= N; ++i) {
+        double diff = fabs(x[i] - xo[i]);
+        double tol = reltol * fmax(fabs(x[i]), fabs(xo[i])) + abstol;
+        if (diff > tol) ok = false;
+    }
+    return ok;
+}
+// anlysis.go:46-59 (DC sweep): |d| > abstol && |d| > reltol*|new| -> not converged.
+template <int N>
+__device__ __forceinline__ bool tsb_converged_dc(const double* x, const double* xo, double reltol, double abstol) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 1; i <= N; ++i) {
+        double diff = fabs(x[i] - xo[i]);
+        if (diff > abstol && diff > reltol * fabs(x[i])) ok = false;
+    }
+    return ok;
+}
+
+// Result sink of one instance: waveform rows to HBM (instance-fastest layout, so a warp whose
+// lanes are at the same row index writes 256 contiguous bytes per column) and running
+// min / max / sum / last per column in shared memory.
+template <int NCOL>
+struct TsbSink {
+    const TsbArgs& a;
+    long long inst;
+    long long n_rows;
+    bool overflow;
+    double* sm;                 // this thread's first stats word; stride blockDim.x between words
+    __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false) {
+        sm = tsb_smem + threadIdx.x;
+        if (a.out_flags & TSB_OUT_STATS) {
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                sm[(0 * NCOL + j) * blockDim.x] = __longlong_as_double(0x7ff0000000000000LL);    // +inf
+                sm[(1 * NCOL + j) * blockDim.x] = __longlong_as_double(0xfff0000000000000LL);    // -inf
+                sm[(2 * NCOL + j) * blockDim.x] = 0.0;
+                sm[(3 * NCOL + j) * blockDim.x] = 0.0;
+            }
+        }
+    }
+    __device__ __forceinline__ void push(const double* row) {
+        if (a.out_flags & TSB_OUT_WAVE) {
+            if (n_rows < a.cap_rows) {
+                double* w = a.wave + (n_rows * NCOL) * a.n_inst + inst;
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) __stcs(w + j * a.n_inst, row[j]);     // streaming store: written once, never re-read
+            } else overflow = true;
+        }
+        if (a.out_flags & TSB_OUT_STATS) {
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                double v = row[j];
+                double* s = sm + j * blockDim.x;
+                s[0] = fmin(s[0], v);
+                s[(1 * NCOL) * blockDim.x] = fmax(s[(1 * NCOL) * blockDim.x], v);
+                s[(2 * NCOL) * blockDim.x] += v;
+                s[(3 * NCOL) * blockDim.x] = v;
+            }
+        }
+        ++n_rows;
+    }
+    __device__ __forceinline__ void finish() {
+        if (a.out_flags & TSB_OUT_STATS) {
+#pragma unroll
+            for (int k = 0; k < 4 * NCOL; ++k) a.stats[(long long)k * a.n_inst + inst] = sm[k * blockDim.x];
+        }
+        a.rows[inst] = n_rows;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Operating point + transient (analysis == TSB_AN_OP stops after the first operating point).
+template <class Ckt>
+__device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long long inst) {
+    constexpr int N = Ckt::N;
+    Ckt c;
+    c.load(a, inst);
+    c.init();
+    TsbSink<Ckt::NCOL_MAX> sink(a, inst);   // NCOL_MAX = transient column count (>= OP column count)
+
+    long long n_acc = 0, n_rej = 0, n_sol_tran = 0, n_sol_op = 0;
+    int op_path = 0, status = TSB_ST_OK;
+    double fail_at = 0.0;
+
+    enum { PH_OP_START, PH_TRAN_BEGIN, PH_NR, PH_DONE };
+    enum { C_MAIN, C_GMIN, C_GFINAL, C_SRC, C_SFINAL, C_TRAN };
+    int phase = (a.analysis == TSB_AN_TRAN && a.uic) ? PH_TRAN_BEGIN : PH_OP_START;
+    int op_pass = 0, cont = C_MAIN, iter = 0, mode = TSB_MODE_OP, gstep = 0;
+    double gmin = 0.0, sfac = 0.0, status_dt = 0.0;
+    double time = 0.0, dt = a.minstep, next_time = 0.0;
+    bool have_last = false;
+    double last_time = 0.0;
+    long long last_key = 0;
+    if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
+
+    while (phase != PH_DONE) {
+        if (phase == PH_OP_START) {
+            // OperatingPoint.Execute(): linear-only initial estimate from a separate sparse matrix
+            c.eval_sources(0.0, 1.0);
+            bool ok = c.init_estimate(status_dt, c.xo);
+            ++n_sol_op;
+            if (!ok) {
+#pragma unroll
+                for (int i = 1; i <= N; ++i) c.xo[i] = 0.0;
+            }
+            gmin = 0.0; cont = C_MAIN; iter = 0; mode = TSB_MODE_OP; phase = PH_NR;
+        } else if (phase == PH_TRAN_BEGIN) {
+            // top of the `for tr.time < tr.stopTime` loop (tran.go:96-111)
+            next_time = time + dt;
+            if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+            c.eval_sources(time, 1.0);          // sources are evaluated at the START of the step
+            iter = 0; mode = TSB_MODE_TRAN; gmin = 0.0; cont = C_TRAN; phase = PH_NR;
+        }
+
+        // ---------------- one Newton iteration (op.go:45-86, tran.go:172-213) -------------------
+        if (Ckt::HAS_NL && (mode == TSB_MODE_OP || iter > 0)) c.update_nl(c.xo);
+        const bool is_tran = mode == TSB_MODE_TRAN;
+        bool solved = c.assemble_solve(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, gmin);
+        if (is_tran) ++n_sol_tran; else ++n_sol_op;
+        bool conv = false, fail = !solved;
+        if (solved) {
+            if (iter > 0) conv = tsb_converged<N>(c.x, c.xo, a.reltol, a.abstol);
+            if (!conv) {
+#pragma unroll
+                for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+                if (++iter >= a.max_iter) fail = true;
+            }
+        }
+        if (!conv && !fail) continue;
+
+        // ---------------- the Newton loop returned: decide what runs next -----------------------
+        bool op_done = false, op_failed = false;
+        switch (cont) {
+        case C_MAIN:
+            if (conv) { op_done = true; break; }
+            // Gmin stepping (op.go:192-205): gmin = n*1e-3*10^10, 11 solves dividing by 10
+            op_path = max(op_path, 1);
+            gmin = ((double)N * 0.001) * 1e10;
+            gstep = 0;
+#pragma unroll
+            for (int i = 1; i <= N; ++i) { a.scratch[(long long)i * a.n_inst + inst] = c.x[i]; c.xo[i] = c.x[i]; }
+            iter = 0; cont = C_GMIN;
+            break;
+        case C_GMIN:
+            if (conv) {
+#pragma unroll
+                for (int i = 1; i <= N; ++i) { a.scratch[(long long)i * a.n_inst + inst] = c.x[i]; c.xo[i] = c.x[i]; }
+                gmin /= 10;
+                if (++gstep <= 10) { iter = 0; break; }
+            } else {
+#pragma unroll
+                for (int i = 1; i <= N; ++i) c.xo[i] = a.scratch[(long long)i * a.n_inst + inst];
+            }
+            gmin = 0.0; iter = 0; cont = C_GFINAL;
+            break;
+        case C_GFINAL:
+            if (conv) { op_done = true; break; }
+            // performSourceStepping (op.go:113-169): V-source DC values * 0.1 .. ~1.0
+            op_path = max(op_path, 2);
+            c.eval_sources(0.0, 0.1);
+            {
+                bool ok = c.init_estimate(0.0, c.xo);
+                ++n_sol_op;
+                if (!ok) {
+#pragma unroll
+                    for (int i = 1; i <= N; ++i) c.xo[i] = 0.0;
+                }
+            }
+            sfac = 0.1; gmin = 0.0; iter = 0; cont = C_SRC;
+            break;
+        case C_SRC:
+            if (!conv) { c.eval_sources(0.0, 1.0); op_failed = true; break; }
+#pragma unroll
+            for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+            sfac += 0.1;
+            if (sfac <= 1.0) { c.eval_sources(0.0, sfac); iter = 0; }
+            else { c.eval_sources(0.0, 1.0); iter = 0; cont = C_SFINAL; }
+            break;
+        case C_SFINAL:
+            if (conv) op_done = true; else op_failed = true;
+            break;
+        case C_TRAN:
+            if (fail) {
+                // tran.go:113-120
+                if (dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; }
+                else { status = TSB_ST_TRAN_FAILED; fail_at = time; phase = PH_DONE; }
+                break;
+            }
+            {
+                double lte = c.lte(dt);                           // tran.go:122, 239-250
+                if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; break; }
+                c.load_state(dt);                                 // tran.go:137-138
+                c.update_state();
+                time = next_time;
+                ++n_acc;
+                if (time >= a.tstart) {                           // StoreTimeResult, anlysis.go:61-85
+                    long long key = tsb_time_key(time);
+                    if (!have_last || !(time == last_time || key == last_key)) {
+                        double row[Ckt::NCOL_MAX];
+                        row[0] = time;
+                        c.signals(row + 1);
+                        sink.push(row);
+                        have_last = true; last_time = time; last_key = key;
+                    }
+                }
+                if (time < a.tstop && dt < a.maxstep) {           // tran.go:145-151
+                    if (lte < a.trtol / 100) dt = fmin(dt * 2, a.maxstep);
+                    else dt = fmin(dt * 1.1, a.maxstep);
+                }
+                phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
+            }
+            break;
+        }
+        if (op_failed) { status = TSB_ST_OP_FAILED; phase = PH_DONE; }
+        if (op_done) {
+            if (a.analysis == TSB_AN_OP) {
+                // storeResults (op.go:235-248): V(node) = x[i], I(dev) = x[branch] (not negated)
+                double row[Ckt::NCOL_MAX];
+#pragma unroll
+                for (int i = 1; i <= N; ++i) row[i - 1] = c.x[i];
+                // an OP row has N columns; the sink is dimensioned for the transient layout, so
+                // write it directly
+                if (a.out_flags & TSB_OUT_WAVE) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) a.wave[(long long)i * a.n_inst + inst] = row[i];
+                }
+                sink.n_rows = 1;
+                phase = PH_DONE;
+            } else if (op_pass == 0) {
+                // Transient.Setup ran the first OP; SetTimeStep(tStep) leaks into the status the second
+                // OP's initial estimate sees; Transient.Execute then runs the OP again.
+                op_pass = 1; status_dt = a.tstep; phase = PH_OP_START;
+            } else {
+                time = 0.0; dt = a.minstep;                        // tran.go:93
+                phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
+            }
+        }
+    }
+
+    if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
+    if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish();
+    a.status[inst] = status;
+    a.counters[0 * a.n_inst + inst] = n_acc;
+    a.counters[1 * a.n_inst + inst] = n_rej;
+    a.counters[2 * a.n_inst + inst] = n_sol_tran;
+    a.counters[3 * a.n_inst + inst] = n_sol_op;
+    a.counters[4 * a.n_inst + inst] = op_path;
+    a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DC sweep (dc.go:88-187): per sweep value one "wasted" stamp, then Newton with state continuation.
+template <class Ckt>
+__device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long inst) {
+    constexpr int N = Ckt::N;
+    Ckt c;
+    c.load(a, inst);
+    c.init();
+    TsbSink<Ckt::NCOL_MAX> sink(a, inst);
+    long long n_sol = 0;
+    int status = TSB_ST_OK;
+    double fail_at = 0.0;
+    int k = 0;
+    int iter = -1;                 // -1: the stamp before doNRiter whose solution is never used (dc.go:119-125)
+    if (a.n_sweep > 0) { c.set_dc(a.sweep[0]); c.eval_sources(0.0, 1.0); }
+    while (k < a.n_sweep) {
+        if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
+        bool solved = c.assemble_solve(TSB_MODE_OP, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
+        if (iter < 0) { iter = 0; continue; }
+        ++n_sol;
+        bool conv = false, fail = !solved;
+        if (solved) {
+            if (iter > 0) conv = tsb_converged_dc<N>(c.x, c.xo, a.reltol, a.abstol);
+            if (!conv) {
+#pragma unroll
+                for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+                if (++iter >= a.max_iter) fail = true;
+            }
+        }
+        if (!conv && !fail) continue;
+        if (fail) { status = TSB_ST_DC_FAILED; fail_at = a.sweep[k]; break; }
+        double row[Ckt::NCOL_MAX];
+        row[0] = a.sweep[k];
+        c.signals(row + 1);
+        sink.push(row);
+        ++k;
+        if (k < a.n_sweep) { c.set_dc(a.sweep[k]); c.eval_sources(0.0, 1.0); iter = -1; }
+    }
+    if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
+    sink.finish();
+    a.status[inst] = status;
+    a.counters[0 * a.n_inst + inst] = 0;
+    a.counters[1 * a.n_inst + inst] = 0;
+    a.counters[2 * a.n_inst + inst] = 0;
+    a.counters[3 * a.n_inst + inst] = n_sol;
+    a.counters[4 * a.n_inst + inst] = 0;
+    a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+}
+
+#endif  // TSB_SKELETON_CUH

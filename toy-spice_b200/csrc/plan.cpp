@@ -1,0 +1,416 @@
+// plan.cpp — freezes a numbered device table into everything the GPU kernels are specialised on.
+//
+//   stamp order            circuit.go:83-152 (netlist order, mutual couplings last)
+//   stamp call sequence    the ordered AddElement/AddRHS calls of every device Stamp() (pkg/device/*.go)
+//   Translate numbering    first-touch order of the setup stamp + SetupElements (circuit.go:154-160,
+//                          matrix/circuit.go:57-63) — what Sparse's ext->int map looks like
+//   pivot order            the reference's first Factor() happens in iteration 0 of the first
+//                          operating point (op.go:25-88) on the OP-mode matrix; replayed here for the
+//                          NOMINAL instance with MarkowitzLU (hostlu.hpp) and then frozen for the batch
+//   elimination program    symbolic LU over the stamped pattern (OP + transient entries) in that order
+#include <algorithm>
+#include <cstring>
+#include <set>
+#include "tsb_internal.hpp"
+#include "hostlu.hpp"
+#include "device/models.cuh"
+
+namespace tsb {
+
+int device_num_outputs(const Dev& d) {
+    switch (d.kind) {
+    case TSB_R: return 1;
+    case TSB_C: case TSB_L: case TSB_D: case TSB_LCORE: return 2;
+    case TSB_Q: return 10;
+    case TSB_M: return 22;
+    case TSB_K: { int m = (int)d.ip.size(); return 3 * (m * (m - 1) / 2); }
+    default: return 0;
+    }
+}
+
+static int state_size(int kind) {
+    switch (kind) {
+    case TSB_C: case TSB_L: return 4;
+    case TSB_D: return 1;
+    case TSB_Q: return 3;
+    case TSB_M: return 9;
+    default: return 0;
+    }
+}
+
+static const int OUT_CONST = -1, OUT_SRC = -2;
+
+// The ordered AddElement / AddRHS calls of one device.  Entries whose row or column is ground are
+// skipped exactly where the reference's `if n != 0` guards skip them.
+void device_stamp_entries(const Plan& plan, int di, std::vector<StampEntry>& out) {
+    const Dev& d = plan.devs[di];
+    auto el = [&](int r, int c, int o, double sign, bool tran = false) {
+        if (r != 0 && c != 0) out.push_back(StampEntry{r, c, o, sign, 0.0, tran});
+    };
+    auto elc = [&](int r, int c, double v) {
+        if (r != 0 && c != 0) out.push_back(StampEntry{r, c, OUT_CONST, 1.0, v, false});
+    };
+    auto rhs = [&](int r, int o, double sign, bool tran = false) {
+        if (r != 0) out.push_back(StampEntry{r, 0, o, sign, 0.0, tran});
+    };
+    const int* n = d.nodes;
+    const int b = d.branch;
+    switch (d.kind) {
+    case TSB_R:       // resistor.go:60-71
+        el(n[0], n[0], 0, +1); el(n[0], n[1], 0, -1); el(n[1], n[0], 0, -1); el(n[1], n[1], 0, +1);
+        break;
+    case TSB_C:       // capacitor.go:72-105
+        el(n[0], n[0], 0, +1); el(n[0], n[1], 0, -1); rhs(n[0], 1, +1);
+        el(n[1], n[1], 0, +1); el(n[1], n[0], 0, -1); rhs(n[1], 1, -1);
+        break;
+    case TSB_L: case TSB_LCORE:   // inductor.go:58-76, magnetic.go:206-250
+        elc(n[0], b, -1.0); elc(b, n[0], -1.0); elc(n[1], b, 1.0); elc(b, n[1], 1.0);
+        el(b, b, 0, +1); rhs(b, 1, +1);
+        break;
+    case TSB_V:       // vsource.go:139-151
+        elc(b, n[0], 1.0); elc(n[0], b, 1.0); elc(b, n[1], -1.0); elc(n[1], b, -1.0);
+        rhs(b, OUT_SRC, +1);
+        break;
+    case TSB_I:       // isource.go:138-145
+        rhs(n[0], OUT_SRC, +1); rhs(n[1], OUT_SRC, -1);
+        break;
+    case TSB_D:       // diode.go:208-224
+        el(n[0], n[0], 0, +1); el(n[0], n[1], 0, -1); rhs(n[0], 1, -1);
+        el(n[1], n[0], 0, -1); el(n[1], n[1], 0, +1); rhs(n[1], 1, +1);
+        break;
+    case TSB_Q: {     // bjt.go:344-372 (collector, base, emitter)
+        int nc = n[0], nb = n[1], ne = n[2];
+        el(nc, nc, 0, +1); el(nc, nb, 1, +1); el(nc, ne, 2, +1); rhs(nc, 3, +1);
+        el(nb, nb, 4, +1); el(nb, nc, 5, +1); rhs(nb, 6, +1);
+        el(ne, ne, 7, +1); el(ne, nb, 8, +1); rhs(ne, 9, +1);
+        break;
+    }
+    case TSB_M: {     // mosfet.go:701-783 (drain, gate, source, bulk)
+        int nd = n[0], ng = n[1], ns = n[2], nb = n[3];
+        el(nd, nd, 0, +1); el(nd, ng, 1, +1); el(nd, ns, 2, +1); el(nd, nb, 3, +1); rhs(nd, 4, +1);
+        el(ns, ns, 5, +1); el(ns, nd, 6, +1); el(ns, ng, 7, +1); el(ns, nb, 8, +1); rhs(ns, 9, +1);
+        if (ng != 0) {
+            if (nd != 0) { el(ng, nd, 10, +1, true); el(nd, ng, 10, +1, true); rhs(ng, 11, +1, true); rhs(nd, 11, -1, true); }
+            if (ns != 0) { el(ng, ns, 12, +1, true); el(ns, ng, 12, +1, true); rhs(ng, 13, +1, true); rhs(ns, 13, -1, true); }
+            if (nb != 0) { el(ng, nb, 14, +1, true); el(nb, ng, 14, +1, true); rhs(ng, 15, +1, true); rhs(nb, 15, -1, true); }
+            el(ng, ng, 16, +1, true);
+        }
+        if (nb != 0) {
+            if (ns != 0) { el(nb, ns, 17, +1, true); el(ns, nb, 17, +1, true); rhs(nb, 18, +1, true); rhs(ns, 18, -1, true); }
+            if (nd != 0) { el(nb, nd, 19, +1, true); el(nd, nb, 19, +1, true); rhs(nb, 20, +1, true); rhs(nd, 20, -1, true); }
+            el(nb, nb, 21, +1, true);
+        }
+        break;
+    }
+    case TSB_K: {     // mutual.go:104-116
+        int m = (int)d.ip.size(), q = 0;
+        for (int i = 0; i < m; ++i)
+            for (int j = i + 1; j < m; ++j, ++q) {
+                int bi = plan.devs[d.ip[i]].branch, bj = plan.devs[d.ip[j]].branch;
+                el(bi, bj, 3 * q, +1, true); el(bj, bi, 3 * q, +1, true);
+                rhs(bi, 3 * q + 1, +1, true); rhs(bj, 3 * q + 2, +1, true);
+            }
+        break;
+    }
+    }
+}
+
+int Plan::num_columns(int an) const {
+    if (an == TSB_AN_OP) return n_nodes + n_branches;
+    int nr = 0;
+    for (const Dev& d : devs) if (d.kind == TSB_R) ++nr;
+    return 1 + n_nodes + n_branches + nr;
+}
+
+std::string Plan::column_name(int an, int col) const {
+    int k = col;
+    if (an != TSB_AN_OP) {
+        if (k == 0) return an == TSB_AN_TRAN ? "TIME" : "SWEEP1";
+        --k;
+    }
+    if (k < n_nodes) {
+        if ((int)node_names.size() > k + 1) return "V(" + node_names[k + 1] + ")";
+        return "V(" + std::to_string(k + 1) + ")";
+    }
+    k -= n_nodes;
+    if (k < n_branches) {
+        for (const Dev& d : devs) if (d.branch == n_nodes + 1 + k) return "I(" + d.name + ")";
+        return "I(b" + std::to_string(k + 1) + ")";
+    }
+    k -= n_branches;
+    for (const Dev& d : devs) if (d.kind == TSB_R) { if (k == 0) return "I(" + d.name + ")"; --k; }
+    return "?";
+}
+
+namespace {
+
+// ---- host evaluation of the NOMINAL instance (symbolic pass only) ---------------------------
+struct Nominal {
+    const Plan& pl;
+    std::vector<double> P, S, D, SV;
+    explicit Nominal(const Plan& p) : pl(p), P(p.nominal), S(p.n_state, 0.0), D(std::max(1, p.n_derived), 0.0), SV(std::max(1, p.n_src), 0.0) {}
+
+    void derive() {
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (d.kind == TSB_R) D[d.d_off] = tsb_res_g(&P[d.p_off]);
+            else if (d.kind == TSB_LCORE) D[d.d_off] = tsb_lcore_L0(&P[d.p_off]);
+            else if (d.kind == TSB_M) tsb_mos_init_state(&P[d.p_off], &S[d.s_off]);
+            else if (d.kind == TSB_K) {
+                int m = (int)d.ip.size(), q = 0;
+                for (int i = 0; i < m; ++i)
+                    for (int j = i + 1; j < m; ++j, ++q)
+                        D[d.d_off + q] = tsb_mut_M(P[d.p_off], ind_value(d.ip[i]), ind_value(d.ip[j]));
+            }
+        }
+    }
+    double ind_value(int di) const {
+        const Dev& d = pl.devs[di];
+        return d.kind == TSB_LCORE ? D[d.d_off] : P[d.p_off];
+    }
+    double ind_current(int di) const {
+        const Dev& d = pl.devs[di];
+        return d.kind == TSB_LCORE ? 0.0 : S[d.s_off];
+    }
+    void sources(double t, double fac) {
+        for (const Dev& d : pl.devs) {
+            if (d.src_slot < 0) continue;
+            const double* p = &P[d.p_off];
+            double v = 0;
+            switch (d.src_type()) {
+            case TSB_SRC_DC: v = p[0] * fac; break;
+            case TSB_SRC_SIN: v = tsb_src_sin(p, t, fac); break;
+            case TSB_SRC_PULSE: v = tsb_src_pulse(p, t); break;
+            case TSB_SRC_PWL: v = tsb_src_pwl(p, (int)d.p.size() / 2, t); break;
+            }
+            SV[d.src_slot] = v;
+        }
+    }
+    void eval(int di, const TsbEnv& e, double* o) {
+        const Dev& d = pl.devs[di];
+        const double* p = d.p.empty() ? nullptr : &P[d.p_off];
+        double* s = d.n_state ? &S[d.s_off] : nullptr;
+        switch (d.kind) {
+        case TSB_R: o[0] = D[d.d_off]; break;
+        case TSB_C: tsb_cap_eval(p, s, e, o); break;
+        case TSB_L: tsb_ind_eval(p, s, e, o); break;
+        case TSB_LCORE: tsb_lcore_eval(D[d.d_off], e, o); break;
+        case TSB_D: tsb_dio_eval(p, s, e, o); break;
+        case TSB_Q: tsb_bjt_eval(p, s, d.ip.empty() ? 0 : d.ip[0], o); break;
+        case TSB_M: tsb_mos_eval(p, s, d.ip.size() > 0 ? d.ip[0] : 1, d.ip.size() > 1 ? d.ip[1] : 0, e, o); break;
+        case TSB_K: {
+            int m = (int)d.ip.size(), q = 0;
+            for (int i = 0; i < m; ++i)
+                for (int j = i + 1; j < m; ++j, ++q)
+                    tsb_mut_eval(D[d.d_off + q], ind_current(d.ip[i]), ind_current(d.ip[j]), e, o + 3 * q);
+            break;
+        }
+        default: break;
+        }
+    }
+    void update_nl(const std::vector<double>& x) {
+        for (const Dev& d : pl.devs) {
+            if (!d.nonlinear()) continue;
+            double* s = &S[d.s_off];
+            if (d.kind == TSB_D) s[0] = x[d.nodes[0]] - x[d.nodes[1]];
+            else if (d.kind == TSB_Q) tsb_bjt_update(s, d.ip.empty() ? 0 : d.ip[0], x[d.nodes[0]], x[d.nodes[1]], x[d.nodes[2]]);
+            else tsb_mos_update(s, d.ip.size() > 1 ? d.ip[1] : 0, x[d.nodes[0]], x[d.nodes[1]], x[d.nodes[2]], x[d.nodes[3]]);
+        }
+    }
+    // Stamp into a MarkowitzLU + rhs; `linear_only` = calculateInitialEstimate (op.go:90-111).
+    void stamp(MarkowitzLU& m, std::vector<double>& b, const TsbEnv& e, bool linear_only, bool op_calls_only) {
+        double o[64];
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (linear_only && d.nonlinear()) continue;
+            std::vector<double> big;
+            double* op = o;
+            int no = device_num_outputs(d);
+            if (no > 64) { big.resize(no); op = big.data(); }
+            eval(di, e, op);
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (op_calls_only && s.tran_only) continue;
+                double v = s.out == OUT_CONST ? s.cval : (s.out == OUT_SRC ? SV[d.src_slot] : op[s.out]);
+                if (s.col == 0) {
+                    if (d.kind == TSB_C || d.kind == TSB_LCORE) { if (e.mode != TSB_MODE_TRAN) continue; }   // no AddRHS in OP mode
+                    b[s.row] += s.sign * v;
+                } else m.add(s.row, s.col, s.sign * v);
+            }
+        }
+    }
+};
+
+void build_lu_program(int n, const std::vector<std::pair<int, int>>& pattern, const PivotOrder& ord, bool dense, LuProgram& lu) {
+    lu = LuProgram();
+    lu.n = n; lu.prow = ord.prow; lu.pcol = ord.pcol; lu.dense = dense;
+    auto add = [&](int r, int c) {
+        auto key = std::make_pair(r, c);
+        auto it = lu.index.find(key);
+        if (it != lu.index.end()) return it->second;
+        int k = (int)lu.pos.size();
+        lu.pos.push_back(key); lu.index[key] = k;
+        return k;
+    };
+    if (dense) { for (int r = 1; r <= n; ++r) for (int c = 1; c <= n; ++c) add(r, c); }
+    else for (auto& rc : pattern) add(rc.first, rc.second);
+    std::vector<int> rstep(n + 1, 0), cstep(n + 1, 0);
+    for (int k = 1; k <= n; ++k) { rstep[ord.prow[k]] = k; cstep[ord.pcol[k]] = k; }
+    lu.steps.assign(n + 1, LuProgram::Step());
+    for (int k = 1; k <= n; ++k) {
+        LuProgram::Step& st = lu.steps[k];
+        int pr = ord.prow[k], pc = ord.pcol[k];
+        st.piv = add(pr, pc);
+        std::vector<std::pair<int, int>> us, ls;      // (step of col/row, ext index)
+        for (int c = 1; c <= n; ++c) if (cstep[c] > k && lu.index.count({pr, c})) us.push_back({cstep[c], c});
+        for (int r = 1; r <= n; ++r) if (rstep[r] > k && lu.index.count({r, pc})) ls.push_back({rstep[r], r});
+        std::sort(us.begin(), us.end()); std::sort(ls.begin(), ls.end());
+        for (auto& u : us) { st.urow.push_back(lu.index[{pr, u.second}]); st.ucol_step.push_back(u.first); }
+        for (auto& l : ls) { st.lcol.push_back(lu.index[{l.second, pc}]); st.lrow_step.push_back(l.first); }
+        st.target.assign(us.size(), std::vector<int>(ls.size(), -1));
+        for (size_t ui = 0; ui < us.size(); ++ui)
+            for (size_t li = 0; li < ls.size(); ++li)
+                st.target[ui][li] = add(ls[li].second, us[ui].second);     // creates fill-in
+    }
+}
+
+}  // namespace
+
+int plan_finalize(Plan& pl) {
+    pl.error.clear();
+    const int n = pl.n();
+    if (n <= 0) { pl.error = "empty circuit"; return TSB_E_INVALID; }
+    // validate + stamp order
+    pl.stamp_order.clear();
+    for (size_t i = 0; i < pl.devs.size(); ++i) if (pl.devs[i].kind != TSB_K) pl.stamp_order.push_back((int)i);
+    for (size_t i = 0; i < pl.devs.size(); ++i) if (pl.devs[i].kind == TSB_K) pl.stamp_order.push_back((int)i);
+    static const int need_nodes[10] = {2, 2, 2, 2, 2, 2, 3, 4, 0, 2};
+    static const int need_p[10] = {1, 1, 1, 1, 1, 3, 9, 29, 1, 3};
+    pl.n_params = pl.n_state = pl.n_src = pl.n_derived = 0;
+    pl.has_nonlinear = pl.has_time_dependent = pl.has_bjt = false;
+    pl.nominal.clear();
+    for (Dev& d : pl.devs) {
+        if (d.kind < 0 || d.kind > 9) { pl.error = "bad device kind on " + d.name; return TSB_E_INVALID; }
+        // the reference panics on a wrong node count (diode.go:45-47, bjt.go:69-71, mosfet.go:126-128)
+        if (d.n_nodes != need_nodes[d.kind]) { pl.error = "device " + d.name + ": wrong number of nodes"; return TSB_E_INVALID; }
+        if ((int)d.p.size() < need_p[d.kind]) { pl.error = "device " + d.name + ": too few parameters"; return TSB_E_INVALID; }
+        for (int i = 0; i < d.n_nodes; ++i)
+            if (d.nodes[i] < 0 || d.nodes[i] > pl.n_nodes) { pl.error = "device " + d.name + ": node index out of range"; return TSB_E_INVALID; }
+        bool needs_branch = d.kind == TSB_L || d.kind == TSB_V || d.kind == TSB_LCORE;
+        if (needs_branch && (d.branch <= pl.n_nodes || d.branch > n)) { pl.error = "device " + d.name + ": branch index out of range"; return TSB_E_INVALID; }
+        if (d.kind == TSB_V || d.kind == TSB_I) {
+            int st = d.src_type();
+            size_t need = st == TSB_SRC_DC ? 1 : st == TSB_SRC_SIN ? 4 : st == TSB_SRC_PULSE ? 7 : 4;
+            if (st < 0 || st > 3 || d.p.size() < need || (st == TSB_SRC_PWL && d.p.size() % 2)) { pl.error = "device " + d.name + ": bad source waveform"; return TSB_E_INVALID; }
+            d.src_slot = pl.n_src++;
+        } else d.src_slot = -1;
+        if (d.kind == TSB_K) {
+            if (d.ip.size() < 2) { pl.error = "mutual coupling " + d.name + " requires at least two inductors"; return TSB_E_INVALID; }
+            for (int idx : d.ip)
+                if (idx < 0 || idx >= (int)pl.devs.size() || (pl.devs[idx].kind != TSB_L && pl.devs[idx].kind != TSB_LCORE)) {
+                    pl.error = "mutual coupling " + d.name + ": not an inductor"; return TSB_E_INVALID;
+                }
+        }
+        d.p_off = pl.n_params; pl.n_params += (int)d.p.size();
+        pl.nominal.insert(pl.nominal.end(), d.p.begin(), d.p.end());
+        d.n_state = state_size(d.kind); d.s_off = pl.n_state; pl.n_state += d.n_state;
+        d.d_off = -1;
+        if (d.kind == TSB_R || d.kind == TSB_LCORE) { d.d_off = pl.n_derived; pl.n_derived += 1; }
+        if (d.kind == TSB_K) { int m = (int)d.ip.size(); d.d_off = pl.n_derived; pl.n_derived += m * (m - 1) / 2; }
+        if (d.nonlinear()) pl.has_nonlinear = true;
+        if (d.time_dependent()) pl.has_time_dependent = true;
+        if (d.kind == TSB_Q) pl.has_bjt = true;
+    }
+    pl.stamps.assign(pl.devs.size(), {});
+    for (size_t i = 0; i < pl.devs.size(); ++i) device_stamp_entries(pl, (int)i, pl.stamps[i]);
+
+    // stamped patterns in first-touch order
+    pl.pattern_op.clear(); pl.pattern_tran_extra.clear();
+    {
+        std::set<std::pair<int, int>> seen;
+        for (int di : pl.stamp_order)
+            for (const StampEntry& s : pl.stamps[di])
+                if (s.col != 0 && !s.tran_only && seen.insert({s.row, s.col}).second) pl.pattern_op.push_back({s.row, s.col});
+        for (int di : pl.stamp_order)
+            for (const StampEntry& s : pl.stamps[di])
+                if (s.col != 0 && s.tran_only && seen.insert({s.row, s.col}).second) pl.pattern_tran_extra.push_back({s.row, s.col});
+    }
+
+    // ---- replay the reference's first operating point for the nominal instance ----------------
+    Nominal nom(pl);
+    nom.derive();
+    TsbEnv env{TSB_MODE_OP, 0.0, 0.0, 0.0};
+    {   // SetupDevices' initial stamp (circuit.go:154-156): only its side effects on device state matter
+        double o[64]; std::vector<double> big;
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (!d.nonlinear()) continue;
+            int no = device_num_outputs(d);
+            double* op = o; if (no > 64) { big.resize(no); op = big.data(); }
+            nom.eval(di, env, op);
+        }
+    }
+    nom.sources(0.0, 1.0);
+    // calculateInitialEstimate: fresh sparse matrix, linear devices only
+    std::vector<double> x0(n + 1, 0.0);
+    {
+        MarkowitzLU mi(n);
+        std::vector<double> b(n + 1, 0.0);
+        nom.stamp(mi, b, env, true, true);
+        std::vector<std::pair<int, int>> pat;
+        {
+            std::set<std::pair<int, int>> seen;
+            for (int di : pl.stamp_order) {
+                if (pl.devs[di].nonlinear()) continue;
+                for (const StampEntry& s : pl.stamps[di])
+                    if (s.col != 0 && !s.tran_only && seen.insert({s.row, s.col}).second) pat.push_back({s.row, s.col});
+            }
+        }
+        pl.order_init = PivotOrder();
+        pl.order_init.n = n;
+        pl.order_init.ext2int.assign(n + 1, 0);
+        pl.order_init.prow.assign(n + 1, 0); pl.order_init.pcol.assign(n + 1, 0);
+        bool ok = mi.assigned() == n && mi.order_and_factor();
+        pl.order_init.singular = !ok;
+        pl.init_struct_singular = !ok;
+        if (ok) {
+            for (int i = 1; i <= n; ++i) { pl.order_init.ext2int[i] = mi.ext2int(i); pl.order_init.prow[i] = mi.pivot_row(i); pl.order_init.pcol[i] = mi.pivot_col(i); }
+            mi.solve(b, x0);
+            nom.update_nl(x0);
+            build_lu_program(n, pat, pl.order_init, false, pl.lu_init);
+        }
+    }
+    // iteration 0 of OperatingPoint.doNRiter: UpdateNonlinearVoltages(x0), Stamp, Solve -> first Factor()
+    {
+        nom.update_nl(x0);
+        MarkowitzLU mm(n);
+        // Translate numbering = setup-stamp call order, then SetupElements touches every (i, j)
+        for (int di : pl.stamp_order)
+            for (const StampEntry& s : pl.stamps[di])
+                if (s.col != 0 && !s.tran_only) mm.create(s.row, s.col);
+        for (int i = 1; i <= n; ++i) for (int j = 1; j <= n; ++j) mm.create(i, j);
+        std::vector<double> b(n + 1, 0.0);
+        nom.stamp(mm, b, env, false, true);
+        pl.order_main = PivotOrder();
+        pl.order_main.n = n;
+        pl.order_main.ext2int.assign(n + 1, 0);
+        pl.order_main.prow.assign(n + 1, 0); pl.order_main.pcol.assign(n + 1, 0);
+        for (int i = 1; i <= n; ++i) pl.order_main.ext2int[i] = mm.ext2int(i);
+        if (!mm.order_and_factor()) {
+            pl.order_main.singular = true;
+            pl.error = "matrix is singular at the nominal operating point (no pivot order)";
+            return TSB_E_INVALID;
+        }
+        for (int i = 1; i <= n; ++i) { pl.order_main.prow[i] = mm.pivot_row(i); pl.order_main.pcol[i] = mm.pivot_col(i); }
+    }
+    {
+        std::vector<std::pair<int, int>> pat = pl.pattern_op;
+        pat.insert(pat.end(), pl.pattern_tran_extra.begin(), pl.pattern_tran_extra.end());
+        // BJT circuits run dense so that Inf/NaN propagate through the solve exactly as they do
+        // through the reference's structurally dense matrix.
+        build_lu_program(n, pat, pl.order_main, pl.has_bjt, pl.lu_main);
+    }
+    pl.finalized = true;
+    return TSB_OK;
+}
+
+}  // namespace tsb

@@ -1,0 +1,717 @@
+// runtime.cpp — the C ABI (include/tspice_b200.h): contexts, plans, batches, runs, results.
+//
+// GPU plumbing: CUDA runtime API for memory / streams / launches; the netlist-specialised kernels
+// are loaded as cubins (cudaLibraryLoadData) either from the in-tree kernel cache (built by
+// __graft_entry__.build() with nvcc) or, on a miss, compiled with NVRTC (dlopen'ed lazily, so the
+// library loads and exports its symbols on machines without a GPU or without NVRTC).
+// There is NO CPU execution path for batches: if CUDA is unavailable every run_* call fails loudly.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include "tsb_internal.hpp"
+
+namespace tsb {
+cudaError_t launch_fp64_peak(double* scratch, int blocks, int iters, cudaStream_t s);
+cudaError_t launch_totals(const long long* counters, long long n_inst, unsigned long long* totals, int sms, cudaStream_t s);
+cudaError_t launch_fill_i64(long long* p, long long n, long long v, int sms, cudaStream_t s);
+}
+
+using namespace tsb;
+
+// Mirror of the device-side TsbArgs (device/skeleton.cuh) — keep in sync.
+#define TSB_MAX_VARYING 64
+struct TsbArgsHost {
+    long long n_inst;
+    const double* pv[TSB_MAX_VARYING];
+    const double* U;
+    int analysis;
+    int uic;
+    double tstart, tstop, tstep, maxstep, minstep;
+    int max_iter;
+    double abstol, reltol, trtol;
+    int out_flags;
+    long long cap_rows;
+    double* wave;
+    double* stats;
+    long long* rows;
+    int* status;
+    long long* counters;
+    double* scratch;
+    const double* sweep;
+    int n_sweep;
+};
+
+struct KernelModule {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t optran = nullptr, dc = nullptr;
+};
+
+struct tsb_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    std::string cache_dir;
+    std::map<std::string, KernelModule> modules;      // key -> loaded module
+    int64_t launches = 0;
+};
+
+struct tsb_plan {
+    Plan p;
+    tsb_ctx* ctx = nullptr;
+    std::string err;
+};
+
+struct tsb_batch {
+    tsb_plan* plan = nullptr;
+    tsb_ctx* ctx = nullptr;
+    int64_t n_inst = 0;
+    std::vector<double> uniform;                       // flat parameter space
+    std::vector<char> varying;
+    std::vector<int> var_slot;
+    std::vector<double*> slot_ptr;                     // device pointer per slot
+    std::vector<char> slot_owned;
+    double* d_uniform = nullptr;
+    // results of the last run
+    int analysis = -1, ncol = 0, out_flags = 0;
+    int64_t cap_rows = 0;
+    double *d_wave = nullptr, *d_stats = nullptr, *d_scratch = nullptr, *d_sweep = nullptr;
+    long long *d_rows = nullptr, *d_counters = nullptr;
+    int* d_status = nullptr;
+    unsigned long long* d_totals = nullptr;
+    size_t wave_bytes = 0, stats_bytes = 0;
+};
+
+namespace {
+
+std::string g_global_err;
+
+int fail(tsb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_global_err = msg;
+    return code;
+}
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(ctx, TSB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+std::string lib_dir() {
+    Dl_info info;
+    if (dladdr((void*)&lib_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.rfind('/');
+        return s == std::string::npos ? "." : p.substr(0, s);
+    }
+    return ".";
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+    return h;
+}
+std::string source_key(const std::string& src, const std::string& opts) {
+    char buf[40];
+    uint64_t a = fnv1a(opts, fnv1a(src, 14695981039346656037ULL));
+    uint64_t b = fnv1a(src, fnv1a(opts, 0x9e3779b97f4a7c15ULL));
+    snprintf(buf, sizeof buf, "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+    return buf;
+}
+
+// ---- NVRTC (lazy) -----------------------------------------------------------------------------
+struct Nvrtc {
+    void* h = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (h) break; }
+        if (!h) { err = "NVRTC not found (libnvrtc.so.12) and no cached cubin for this kernel"; return false; }
+#define SYM(f) *(void**)(&f) = dlsym(h, "nvrtc" #f); if (!f) { err = "nvrtc" #f " missing"; return false; }
+        SYM(CreateProgram) SYM(CompileProgram) SYM(GetCUBINSize) SYM(GetCUBIN) SYM(GetProgramLogSize) SYM(GetProgramLog) SYM(DestroyProgram)
+#undef SYM
+        return true;
+    }
+};
+Nvrtc g_nvrtc;
+std::mutex g_nvrtc_mu;
+
+std::string compile_options_string(const tsb_opts& o) {
+    std::string s = "--gpu-architecture=sm_100a --std=c++17 -lineinfo";
+    s += o.strict_fp ? " --fmad=false" : " --fmad=true";
+    return s;
+}
+
+bool nvrtc_compile(const std::string& src, const std::string& name, const tsb_opts& o, std::vector<char>& cubin, std::string& err) {
+    std::lock_guard<std::mutex> lk(g_nvrtc_mu);
+    if (!g_nvrtc.load(err)) return false;
+    void* prog = nullptr;
+    if (g_nvrtc.CreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != 0) { err = "nvrtcCreateProgram failed"; return false; }
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", o.strict_fp ? "--fmad=false" : "--fmad=true"};
+    int rc = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+    if (rc != 0) {
+        size_t n = 0; g_nvrtc.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0'); if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+        err = "NVRTC compile failed:\n" + log.substr(0, 4000);
+        g_nvrtc.DestroyProgram(&prog);
+        return false;
+    }
+    size_t n = 0; g_nvrtc.GetCUBINSize(prog, &n);
+    cubin.resize(n);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
+    return n > 0;
+}
+
+CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
+    CodegenConfig cfg;
+    cfg.varying = b->varying; cfg.var_slot = b->var_slot; cfg.n_var = (int)b->slot_ptr.size();
+    cfg.block_size = o.block_size > 0 ? o.block_size : 128;
+    cfg.dc_param = dc_param;
+    return cfg;
+}
+
+int get_module(tsb_batch* b, const tsb_opts& o, int dc_param, KernelModule** out) {
+    tsb_ctx* ctx = b->ctx;
+    std::string src = generate_source(b->plan->p, make_config(b, o, dc_param));
+    std::string key = source_key(src, compile_options_string(o));
+    auto it = ctx->modules.find(key);
+    if (it != ctx->modules.end()) { *out = &it->second; return TSB_OK; }
+    std::vector<char> cubin;
+    std::string path = ctx->cache_dir + "/" + key + ".cubin";
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (f) cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    if (cubin.empty()) {
+        std::string err;
+        std::string srcname = ctx->cache_dir + "/" + key + ".cu";
+        mkdir(ctx->cache_dir.c_str(), 0755);
+        { std::ofstream f(srcname); f << src; }
+        if (!nvrtc_compile(src, srcname, o, cubin, err)) return fail(ctx, TSB_E_COMPILE, err);
+        std::ofstream f(path, std::ios::binary);
+        f.write(cubin.data(), (std::streamsize)cubin.size());
+    }
+    KernelModule m;
+    CU(ctx, cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    CU(ctx, cudaLibraryGetKernel(&m.optran, m.lib, "tsb_optran"));
+    CU(ctx, cudaLibraryGetKernel(&m.dc, m.lib, "tsb_dc"));
+    ctx->modules[key] = m;
+    *out = &ctx->modules[key];
+    return TSB_OK;
+}
+
+void free_results(tsb_batch* b) {
+    cudaFree(b->d_wave); cudaFree(b->d_stats); cudaFree(b->d_rows); cudaFree(b->d_status);
+    cudaFree(b->d_counters); cudaFree(b->d_scratch); cudaFree(b->d_sweep); cudaFree(b->d_totals);
+    b->d_wave = b->d_stats = b->d_scratch = b->d_sweep = nullptr;
+    b->d_rows = b->d_counters = nullptr; b->d_status = nullptr; b->d_totals = nullptr;
+    b->wave_bytes = b->stats_bytes = 0;
+}
+
+int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, int n_sweep) {
+    tsb_ctx* ctx = b->ctx;
+    const Plan& p = b->plan->p;
+    const int64_t N = b->n_inst;
+    int ncol = p.num_columns(analysis);
+    size_t wave_bytes = (out_flags & TSB_OUT_WAVE) ? (size_t)cap_rows * ncol * N * sizeof(double) : 0;
+    size_t stats_bytes = (out_flags & TSB_OUT_STATS) ? (size_t)4 * ncol * N * sizeof(double) : 0;
+    if (wave_bytes != b->wave_bytes) {
+        cudaFree(b->d_wave); b->d_wave = nullptr; b->wave_bytes = 0;
+        if (wave_bytes) { CU(ctx, cudaMalloc(&b->d_wave, wave_bytes)); b->wave_bytes = wave_bytes; }
+    }
+    if (stats_bytes != b->stats_bytes) {
+        cudaFree(b->d_stats); b->d_stats = nullptr; b->stats_bytes = 0;
+        if (stats_bytes) { CU(ctx, cudaMalloc(&b->d_stats, stats_bytes)); b->stats_bytes = stats_bytes; }
+    }
+    if (!b->d_rows) CU(ctx, cudaMalloc(&b->d_rows, N * sizeof(long long)));
+    if (!b->d_status) CU(ctx, cudaMalloc(&b->d_status, N * sizeof(int)));
+    if (!b->d_counters) CU(ctx, cudaMalloc(&b->d_counters, 6 * N * sizeof(long long)));
+    if (!b->d_scratch) CU(ctx, cudaMalloc(&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
+    if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 4 * sizeof(unsigned long long)));
+    if (n_sweep > 0) { cudaFree(b->d_sweep); b->d_sweep = nullptr; CU(ctx, cudaMalloc(&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
+    b->analysis = analysis; b->ncol = ncol; b->out_flags = out_flags; b->cap_rows = cap_rows;
+    return TSB_OK;
+}
+
+int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args) {
+    tsb_ctx* ctx = b->ctx;
+    int block = o.block_size > 0 ? o.block_size : 128;
+    size_t smem = (args.out_flags & TSB_OUT_STATS) ? (size_t)4 * b->plan->p.num_columns(TSB_AN_TRAN) * block * sizeof(double) : 0;
+    if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (b->n_inst + block - 1) / block;
+    if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+    if (blocks < 1) blocks = 1;
+    void* kargs[] = {&args};
+    CU(ctx, cudaLaunchKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
+    ++ctx->launches;
+    return TSB_OK;
+}
+
+int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
+    tsb_ctx* ctx = b->ctx;
+    memset(&a, 0, sizeof a);
+    a.n_inst = b->n_inst;
+    if (b->slot_ptr.size() > TSB_MAX_VARYING) return fail(ctx, TSB_E_UNSUPPORTED, "too many per-instance parameters (max 64)");
+    for (size_t s = 0; s < b->slot_ptr.size(); ++s) a.pv[s] = b->slot_ptr[s];
+    size_t ub = b->uniform.size() * sizeof(double);
+    if (!b->d_uniform) CU(ctx, cudaMalloc(&b->d_uniform, ub ? ub : 8));
+    if (ub) CU(ctx, cudaMemcpyAsync(b->d_uniform, b->uniform.data(), ub, cudaMemcpyHostToDevice, ctx->stream));
+    a.U = b->d_uniform;
+    a.max_iter = o.max_iter; a.abstol = o.abstol; a.reltol = o.reltol; a.trtol = o.trtol;
+    a.wave = b->d_wave; a.stats = b->d_stats; a.rows = b->d_rows; a.status = b->d_status;
+    a.counters = b->d_counters; a.scratch = b->d_scratch;
+    a.out_flags = b->out_flags; a.cap_rows = b->cap_rows;
+    return TSB_OK;
+}
+
+tsb_opts resolve(const tsb_opts* o) {
+    tsb_opts r; tsb_default_opts(&r);
+    if (o) {
+        r = *o;
+        if (r.max_iter <= 0) r.max_iter = 100;
+        if (r.block_size <= 0) r.block_size = 128;
+    }
+    const char* env = getenv("TSB_STRICT_FP");
+    if (env && *env && *env != '0') r.strict_fp = 1;
+    return r;
+}
+
+int check_batch(tsb_batch* b) {
+    if (!b || !b->plan) return TSB_E_INVALID;
+    if (!b->ctx) return fail(nullptr, TSB_E_CUDA, "batch has no GPU context (host-only plan): analyses run on the GPU only");
+    return TSB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+void tsb_default_opts(tsb_opts* o) {
+    if (!o) return;
+    o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
+    o->strict_fp = 0; o->block_size = 128; o->reuse_lu = 0;
+}
+const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
+
+int tsb_ctx_create(int device_ordinal, tsb_ctx** out) {
+    if (!out) return TSB_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, TSB_E_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device_ordinal < 0 || device_ordinal >= count) return fail(nullptr, TSB_E_INVALID, "device ordinal out of range");
+    std::unique_ptr<tsb_ctx> ctx(new tsb_ctx);
+    ctx->device = device_ordinal;
+    CU(nullptr, cudaSetDevice(device_ordinal));
+    CU(nullptr, cudaFree(0));
+    CU(nullptr, cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device_ordinal));
+    CU(nullptr, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    const char* env = getenv("TSB_KCACHE");
+    ctx->cache_dir = env && *env ? env : lib_dir() + "/_kcache";
+    *out = ctx.release();
+    return TSB_OK;
+}
+void tsb_ctx_destroy(tsb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->modules) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+const char* tsb_last_error(tsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
+int tsb_ctx_set_stream(tsb_ctx* ctx, uint64_t stream) {
+    if (!ctx) return TSB_E_INVALID;
+    ctx->stream = stream ? (cudaStream_t)(uintptr_t)stream : ctx->own_stream;
+    return TSB_OK;
+}
+int tsb_ctx_set_cache_dir(tsb_ctx* ctx, const char* dir) {
+    if (!ctx || !dir) return TSB_E_INVALID;
+    ctx->cache_dir = dir;
+    return TSB_OK;
+}
+int tsb_ctx_sm_count(tsb_ctx* ctx, int* sms) { if (!ctx || !sms) return TSB_E_INVALID; *sms = ctx->sms; return TSB_OK; }
+int64_t tsb_ctx_launch_count(const tsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tsb_ctx_measure_fp64_peak(tsb_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return TSB_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sms * 8, iters = 4096;
+    double* scratch = nullptr;
+    CU(ctx, cudaMalloc(&scratch, (size_t)blocks * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(ctx, cudaEventRecord(e0, ctx->stream));
+        CU(ctx, launch_fp64_peak(scratch, blocks, iters, ctx->stream));
+        ++ctx->launches;
+        CU(ctx, cudaEventRecord(e1, ctx->stream));
+        CU(ctx, cudaEventSynchronize(e1));
+        float ms = 0; CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * iters * 256.0 * blocks;     // 64 DFMA per iteration per thread
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch);
+    *tflops = best;
+    return TSB_OK;
+}
+
+// ---- plan -------------------------------------------------------------------------------------
+int tsb_plan_create(tsb_ctx* ctx, int n_nodes, int n_branches, tsb_plan** out) {
+    if (!out || n_nodes < 0 || n_branches < 0) return TSB_E_INVALID;
+    tsb_plan* p = new tsb_plan; p->ctx = ctx; p->p.ctx = ctx;
+    p->p.n_nodes = n_nodes; p->p.n_branches = n_branches;
+    *out = p;
+    return TSB_OK;
+}
+int tsb_plan_from_netlist(tsb_ctx* ctx, const char* text, tsb_plan** out) {
+    if (!out || !text) return TSB_E_INVALID;
+    *out = nullptr;
+    std::unique_ptr<tsb_plan> p(new tsb_plan); p->ctx = ctx; p->p.ctx = ctx;
+    std::string err;
+    int rc = plan_from_netlist(text, p->p, err);
+    if (rc != TSB_OK) return fail(ctx, rc, err);
+    rc = plan_finalize(p->p);
+    if (rc != TSB_OK) return fail(ctx, rc, p->p.error);
+    *out = p.release();
+    return TSB_OK;
+}
+int tsb_plan_add_device(tsb_plan* plan, int kind, const char* name, const int* nodes, int n_nodes, int branch,
+                        const double* p, int n_p, const int* ip, int n_ip) {
+    if (!plan || plan->p.finalized || n_nodes < 0 || n_nodes > 4 || n_p < 0 || n_ip < 0) return TSB_E_INVALID;
+    Dev d; d.kind = kind; d.name = name ? name : ""; d.n_nodes = n_nodes; d.branch = branch;
+    for (int i = 0; i < n_nodes; ++i) d.nodes[i] = nodes[i];
+    if (n_p) d.p.assign(p, p + n_p);
+    if (n_ip) d.ip.assign(ip, ip + n_ip);
+    plan->p.devs.push_back(d);
+    return (int)plan->p.devs.size() - 1;
+}
+int tsb_plan_finalize(tsb_plan* plan) {
+    if (!plan) return TSB_E_INVALID;
+    int rc = plan_finalize(plan->p);
+    if (rc != TSB_OK) { plan->err = plan->p.error; return fail(plan->ctx, rc, plan->p.error); }
+    return TSB_OK;
+}
+void tsb_plan_destroy(tsb_plan* plan) { delete plan; }
+const char* tsb_plan_error(tsb_plan* plan) { return plan ? plan->p.error.c_str() : ""; }
+
+int tsb_plan_size(const tsb_plan* plan, int* n_nodes, int* n_branches) {
+    if (!plan) return TSB_E_INVALID;
+    if (n_nodes) *n_nodes = plan->p.n_nodes;
+    if (n_branches) *n_branches = plan->p.n_branches;
+    return TSB_OK;
+}
+int tsb_plan_num_devices(const tsb_plan* plan) { return plan ? (int)plan->p.devs.size() : TSB_E_INVALID; }
+int tsb_plan_device_info(const tsb_plan* plan, int dev, int* kind, const char** name, int nodes[4], int* branch, int* n_p, int* n_ip) {
+    if (!plan || dev < 0 || dev >= (int)plan->p.devs.size()) return TSB_E_INVALID;
+    const Dev& d = plan->p.devs[dev];
+    if (kind) *kind = d.kind;
+    if (name) *name = d.name.c_str();
+    if (nodes) for (int i = 0; i < 4; ++i) nodes[i] = i < d.n_nodes ? d.nodes[i] : 0;
+    if (branch) *branch = d.branch;
+    if (n_p) *n_p = (int)d.p.size();
+    if (n_ip) *n_ip = (int)d.ip.size();
+    return d.n_nodes;
+}
+int tsb_plan_device_params(const tsb_plan* plan, int dev, double* p, int cap_p, int* ip, int cap_ip) {
+    if (!plan || dev < 0 || dev >= (int)plan->p.devs.size()) return TSB_E_INVALID;
+    const Dev& d = plan->p.devs[dev];
+    for (int i = 0; i < cap_p && i < (int)d.p.size(); ++i) p[i] = d.p[i];
+    for (int i = 0; i < cap_ip && i < (int)d.ip.size(); ++i) ip[i] = d.ip[i];
+    return TSB_OK;
+}
+int tsb_plan_find_device(const tsb_plan* plan, const char* name) {
+    if (!plan || !name) return -1;
+    for (size_t i = 0; i < plan->p.devs.size(); ++i) if (plan->p.devs[i].name == name) return (int)i;
+    return -1;
+}
+int tsb_plan_node_name(const tsb_plan* plan, int node, const char** name) {
+    if (!plan || !name || node < 0 || node >= (int)plan->p.node_names.size()) return TSB_E_INVALID;
+    *name = plan->p.node_names[node].c_str();
+    return TSB_OK;
+}
+int tsb_plan_analysis(const tsb_plan* plan, int* analysis, double tran[4], int* uic, int* dc_src_dev, double dc[3]) {
+    if (!plan) return TSB_E_INVALID;
+    if (analysis) *analysis = plan->p.analysis;
+    if (tran) for (int i = 0; i < 4; ++i) tran[i] = plan->p.tran[i];
+    if (uic) *uic = plan->p.uic;
+    if (dc_src_dev) *dc_src_dev = plan->p.dc_src_dev;
+    if (dc) for (int i = 0; i < 3; ++i) dc[i] = plan->p.dc[i];
+    return TSB_OK;
+}
+int tsb_plan_structure(const tsb_plan* plan, int* ext2int, int* pivot_row, int* pivot_col) {
+    if (!plan || !plan->p.finalized) return TSB_E_INVALID;
+    int n = plan->p.n();
+    for (int i = 0; i <= n; ++i) {
+        if (ext2int) ext2int[i] = plan->p.order_main.ext2int[i];
+        if (pivot_row) pivot_row[i] = plan->p.order_main.prow[i];
+        if (pivot_col) pivot_col[i] = plan->p.order_main.pcol[i];
+    }
+    return TSB_OK;
+}
+int tsb_plan_pattern(const tsb_plan* plan, int mode, int* rows, int* cols, int cap, int* nnz) {
+    if (!plan || !plan->p.finalized) return TSB_E_INVALID;
+    std::vector<std::pair<int, int>> pat = plan->p.pattern_op;
+    if (mode == 1) pat.insert(pat.end(), plan->p.pattern_tran_extra.begin(), plan->p.pattern_tran_extra.end());
+    if (nnz) *nnz = (int)pat.size();
+    for (int i = 0; i < cap && i < (int)pat.size(); ++i) { if (rows) rows[i] = pat[i].first; if (cols) cols[i] = pat[i].second; }
+    return TSB_OK;
+}
+int tsb_plan_num_columns(const tsb_plan* plan, int analysis) { return plan ? plan->p.num_columns(analysis) : TSB_E_INVALID; }
+int tsb_plan_column_name(const tsb_plan* plan, int analysis, int col, char* buf, int cap) {
+    if (!plan || !buf || cap <= 0 || col < 0 || col >= plan->p.num_columns(analysis)) return TSB_E_INVALID;
+    snprintf(buf, cap, "%s", plan->p.column_name(analysis, col).c_str());
+    return TSB_OK;
+}
+
+// ---- batch ------------------------------------------------------------------------------------
+int tsb_batch_create(tsb_plan* plan, int64_t n_inst, tsb_batch** out) {
+    if (!plan || !out || n_inst <= 0) return TSB_E_INVALID;
+    if (!plan->p.finalized) return fail(plan->ctx, TSB_E_INVALID, "plan is not finalized");
+    tsb_batch* b = new tsb_batch;
+    b->plan = plan; b->ctx = plan->ctx; b->n_inst = n_inst;
+    b->uniform = plan->p.nominal;
+    b->varying.assign(plan->p.n_params, 0);
+    b->var_slot.assign(plan->p.n_params, -1);
+    *out = b;
+    return TSB_OK;
+}
+void tsb_batch_destroy(tsb_batch* b) {
+    if (!b) return;
+    if (b->ctx) {
+        cudaSetDevice(b->ctx->device);
+        for (size_t s = 0; s < b->slot_ptr.size(); ++s) if (b->slot_owned[s]) cudaFree(b->slot_ptr[s]);
+        cudaFree(b->d_uniform);
+        free_results(b);
+    }
+    delete b;
+}
+
+static int param_index(tsb_batch* b, int dev, int param, int* flat) {
+    if (!b) return TSB_E_INVALID;
+    const Plan& p = b->plan->p;
+    if (dev < 0 || dev >= (int)p.devs.size()) return fail(b->ctx, TSB_E_INVALID, "device index out of range");
+    const Dev& d = p.devs[dev];
+    if (param < 0 || param >= (int)d.p.size()) return fail(b->ctx, TSB_E_INVALID, "parameter index out of range for " + d.name);
+    if ((d.kind == TSB_V || d.kind == TSB_I) && d.src_type() == TSB_SRC_PWL)
+        return fail(b->ctx, TSB_E_UNSUPPORTED, "PWL tables are not sweepable");
+    *flat = d.p_off + param;
+    return TSB_OK;
+}
+static int claim_slot(tsb_batch* b, int flat) {
+    if (b->var_slot[flat] >= 0) return b->var_slot[flat];
+    b->varying[flat] = 1;
+    b->var_slot[flat] = (int)b->slot_ptr.size();
+    b->slot_ptr.push_back(nullptr);
+    b->slot_owned.push_back(0);
+    return b->var_slot[flat];
+}
+int tsb_batch_set_param(tsb_batch* b, int dev, int param, const double* values) {
+    int flat = 0, rc = param_index(b, dev, param, &flat);
+    if (rc != TSB_OK) return rc;
+    if (!values) return TSB_E_INVALID;
+    int slot = claim_slot(b, flat);
+    if (!b->ctx) return TSB_OK;      // host-only plan: only the "varies per instance" fact is recorded
+    tsb_ctx* ctx = b->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!b->slot_owned[slot]) {
+        double* p = nullptr;
+        CU(ctx, cudaMalloc(&p, (size_t)b->n_inst * sizeof(double)));
+        b->slot_ptr[slot] = p; b->slot_owned[slot] = 1;
+    }
+    CU(ctx, cudaMemcpyAsync(b->slot_ptr[slot], values, (size_t)b->n_inst * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return TSB_OK;
+}
+int tsb_batch_set_param_dev(tsb_batch* b, int dev, int param, uint64_t dev_ptr) {
+    int flat = 0, rc = param_index(b, dev, param, &flat);
+    if (rc != TSB_OK) return rc;
+    if (!dev_ptr) return TSB_E_INVALID;
+    int slot = claim_slot(b, flat);
+    if (b->slot_owned[slot]) { cudaFree(b->slot_ptr[slot]); b->slot_owned[slot] = 0; }
+    b->slot_ptr[slot] = (double*)(uintptr_t)dev_ptr;
+    return TSB_OK;
+}
+int tsb_batch_set_param_uniform(tsb_batch* b, int dev, int param, double value) {
+    int flat = 0, rc = param_index(b, dev, param, &flat);
+    if (rc != TSB_OK) return rc;
+    if (b->varying[flat]) return fail(b->ctx, TSB_E_INVALID, "parameter already set per instance");
+    b->uniform[flat] = value;
+    return TSB_OK;
+}
+
+// ---- analyses ----------------------------------------------------------------------------------
+int tsb_run_op(tsb_batch* b, const tsb_opts* opts) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    tsb_opts o = resolve(opts);
+    CU(ctx, cudaSetDevice(ctx->device));
+    KernelModule* m = nullptr;
+    if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
+    if ((rc = alloc_results(b, TSB_AN_OP, TSB_OUT_WAVE, 1, 0)) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
+    a.analysis = TSB_AN_OP;
+    return launch(b, o, m->optran, a);
+}
+
+int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double tmax, int uic, int out_flags,
+                 int64_t wave_cap_rows, const tsb_opts* opts) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    if (!(tstop > 0) || !(tstep > 0)) return fail(ctx, TSB_E_INVALID, "tstop and tstep must be positive");
+    if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
+    if ((out_flags & TSB_OUT_WAVE) && wave_cap_rows <= 0) return fail(ctx, TSB_E_INVALID, "wave_cap_rows must be positive");
+    tsb_opts o = resolve(opts);
+    CU(ctx, cudaSetDevice(ctx->device));
+    KernelModule* m = nullptr;
+    if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
+    if ((rc = alloc_results(b, TSB_AN_TRAN, out_flags, (out_flags & TSB_OUT_WAVE) ? wave_cap_rows : 0, 0)) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
+    // NewTransient (tran.go:29-55)
+    if (tstep > tstop / 300) tstep = tstop / 300;
+    double minstep = tstep / 50.0;
+    if (tmax == 0) tmax = tstep;
+    a.analysis = TSB_AN_TRAN; a.uic = uic;
+    a.tstart = tstart; a.tstop = tstop; a.tstep = tstep; a.maxstep = tmax; a.minstep = minstep;
+    return launch(b, o, m->optran, a);
+}
+
+int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    const Plan& p = b->plan->p;
+    if (src_dev < 0 || src_dev >= (int)p.devs.size() || p.devs[src_dev].kind != TSB_V)
+        return fail(ctx, TSB_E_INVALID, "source not found");                       // dc.go:47-68
+    if (!(inc > 0)) return fail(ctx, TSB_E_INVALID, "sweep increment must be positive");
+    if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
+    std::vector<double> sweep;
+    for (double v = start; v <= stop; v += inc) { sweep.push_back(v); if (sweep.size() > (1u << 24)) break; }   // dc.go:36-42
+    tsb_opts o = resolve(opts);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const Dev& sd = p.devs[src_dev];
+    int st = sd.src_type();
+    int dc_param = (st == TSB_SRC_DC || st == TSB_SRC_SIN) ? sd.p_off : -1;   // SetValue only reaches dcValue
+    if (dc_param >= 0 && b->varying[dc_param]) return fail(ctx, TSB_E_INVALID, "the swept source value is set per instance");
+    KernelModule* m = nullptr;
+    if ((rc = get_module(b, o, dc_param, &m)) != TSB_OK) return rc;
+    if ((rc = alloc_results(b, TSB_AN_DC, out_flags, (out_flags & TSB_OUT_WAVE) ? (int64_t)sweep.size() : 0, (int)sweep.size())) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
+    if (!sweep.empty()) CU(ctx, cudaMemcpyAsync(b->d_sweep, sweep.data(), sweep.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));     // `sweep` is a stack vector
+    a.analysis = TSB_AN_DC; a.sweep = b->d_sweep; a.n_sweep = (int)sweep.size();
+    return launch(b, o, m->dc, a);
+}
+
+int tsb_batch_sync(tsb_batch* b) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    return TSB_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------
+int tsb_result_dims(const tsb_batch* b, int64_t* n_inst, int* n_columns, int64_t* cap_rows) {
+    if (!b) return TSB_E_INVALID;
+    if (n_inst) *n_inst = b->n_inst;
+    if (n_columns) *n_columns = b->ncol;
+    if (cap_rows) *cap_rows = b->cap_rows;
+    return TSB_OK;
+}
+int tsb_result_dev_ptrs(const tsb_batch* b, uint64_t* wave, uint64_t* stats, uint64_t* rows, uint64_t* status, uint64_t* counters) {
+    if (!b) return TSB_E_INVALID;
+    if (wave) *wave = (uint64_t)(uintptr_t)b->d_wave;
+    if (stats) *stats = (uint64_t)(uintptr_t)b->d_stats;
+    if (rows) *rows = (uint64_t)(uintptr_t)b->d_rows;
+    if (status) *status = (uint64_t)(uintptr_t)b->d_status;
+    if (counters) *counters = (uint64_t)(uintptr_t)b->d_counters;
+    return TSB_OK;
+}
+static int d2h(tsb_batch* b, void* dst, const void* src, size_t bytes) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    if (!src) return fail(b->ctx, TSB_E_INVALID, "no such result for the last run");
+    CU(b->ctx, cudaSetDevice(b->ctx->device));
+    CU(b->ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    return TSB_OK;
+}
+int tsb_result_rows(tsb_batch* b, int64_t* rows) { return b && rows ? d2h(b, rows, b->d_rows, b->n_inst * sizeof(long long)) : TSB_E_INVALID; }
+int tsb_result_status(tsb_batch* b, int32_t* status) { return b && status ? d2h(b, status, b->d_status, b->n_inst * sizeof(int)) : TSB_E_INVALID; }
+int tsb_result_counters(tsb_batch* b, int64_t* counters) { return b && counters ? d2h(b, counters, b->d_counters, 6 * b->n_inst * sizeof(long long)) : TSB_E_INVALID; }
+int tsb_result_wave_all(tsb_batch* b, double* out, int64_t n_doubles) {
+    if (!b || !out) return TSB_E_INVALID;
+    if ((size_t)n_doubles * sizeof(double) < b->wave_bytes) return fail(b->ctx, TSB_E_INVALID, "output buffer too small");
+    return d2h(b, out, b->d_wave, b->wave_bytes);
+}
+int tsb_result_stats_all(tsb_batch* b, double* out) { return b && out ? d2h(b, out, b->d_stats, b->stats_bytes) : TSB_E_INVALID; }
+int tsb_result_waveform(tsb_batch* b, int64_t inst, double* out, int64_t cap_rows, int64_t* n_rows) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    if (!out || inst < 0 || inst >= b->n_inst) return TSB_E_INVALID;
+    if (!b->d_wave) return fail(ctx, TSB_E_INVALID, "the last run did not store waveforms");
+    CU(ctx, cudaSetDevice(ctx->device));
+    long long rows = 0;
+    CU(ctx, cudaMemcpyAsync(&rows, b->d_rows + inst, sizeof rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rows > b->cap_rows) rows = b->cap_rows;
+    if (n_rows) *n_rows = rows;
+    if (rows > cap_rows) rows = cap_rows;
+    if (rows <= 0) return TSB_OK;
+    // gather the strided column: wave[(r*ncol + j)*n_inst + inst] -> out[r*ncol + j]
+    CU(ctx, cudaMemcpy2DAsync(out, sizeof(double), b->d_wave + inst, (size_t)b->n_inst * sizeof(double), sizeof(double),
+                              (size_t)rows * b->ncol, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TSB_OK;
+}
+int tsb_result_totals(tsb_batch* b, int64_t totals[4]) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    if (!totals || !b->d_counters) return TSB_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(b->d_totals, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, launch_totals(b->d_counters, b->n_inst, b->d_totals, ctx->sms, ctx->stream));
+    ++ctx->launches;
+    unsigned long long h[4];
+    CU(ctx, cudaMemcpyAsync(h, b->d_totals, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) totals[k] = (int64_t)h[k];
+    return TSB_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------------
+int tsb_batch_kernel_source(tsb_batch* b, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed) {
+    if (!b) return TSB_E_INVALID;
+    tsb_opts o = resolve(opts);
+    std::string src = generate_source(b->plan->p, make_config(b, o, -1));
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", src.c_str()); }
+    return TSB_OK;
+}
+int tsb_batch_kernel_key(tsb_batch* b, const tsb_opts* opts, char* buf, int cap) {
+    if (!b || !buf || cap < 33) return TSB_E_INVALID;
+    tsb_opts o = resolve(opts);
+    std::string src = generate_source(b->plan->p, make_config(b, o, -1));
+    snprintf(buf, cap, "%s", source_key(src, compile_options_string(o)).c_str());
+    return TSB_OK;
+}
+
+}  // extern "C"

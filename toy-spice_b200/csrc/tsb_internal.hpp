@@ -1,0 +1,113 @@
+// tsb_internal.hpp — host-side data model of the batched engine (not part of the public ABI).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../../include/tspice_b200.h"
+
+namespace tsb {
+
+// ---- device table -------------------------------------------------------------------------
+struct Dev {
+    int kind = 0;
+    std::string name;
+    int nodes[4] = {0, 0, 0, 0};
+    int n_nodes = 0;
+    int branch = 0;
+    std::vector<double> p;     // nominal parameters (layout: include/tspice_b200.h)
+    std::vector<int> ip;
+    // assigned by finalize
+    int p_off = 0;             // offset of p[] in the flat parameter space
+    int s_off = 0, n_state = 0;
+    int src_slot = -1;         // V / I: index into the source-value array
+    int d_off = -1;            // derived-value slot(s)
+    bool nonlinear() const { return kind == TSB_D || kind == TSB_Q || kind == TSB_M; }
+    bool time_dependent() const { return kind == TSB_C || kind == TSB_L; }
+    int src_type() const { return ip.empty() ? TSB_SRC_DC : ip[0]; }
+};
+
+// One AddElement / AddRHS call of a device stamp: value = sign * o[out] (or a constant).
+struct StampEntry {
+    int row, col;      // external indices; col == 0 -> AddRHS(row)
+    int out;           // index into the device's stamp-value array o[]; -1 -> constant `cval`
+    double sign;       // +1 / -1
+    double cval;       // constant value when out < 0 (the +-1 incidence entries)
+    bool tran_only;    // emitted by the reference only when Mode == Transient (pattern bookkeeping)
+};
+
+struct PivotOrder {
+    int n = 0;
+    std::vector<int> ext2int;        // [n+1], Translate numbering
+    std::vector<int> prow, pcol;     // [n+1], external row/col of the pivot of step k
+    bool singular = false;
+};
+
+// Elimination program over a fixed pattern (symbolic factorisation result).
+struct LuProgram {
+    int n = 0;
+    std::vector<std::pair<int, int>> pos;          // entry k -> (ext row, ext col), pattern + fill
+    std::map<std::pair<int, int>, int> index;      // (ext row, ext col) -> k
+    std::vector<int> prow, pcol;                   // [n+1]
+    struct Step {
+        int piv;                                   // entry index of the pivot
+        std::vector<int> urow;                     // entries (prow[k], c) right of the pivot, in column-internal order
+        std::vector<int> lcol;                     // entries (r, pcol[k]) below the pivot, in row-internal order
+        std::vector<std::vector<int>> target;      // target[u][l] = entry (row of l, col of u)
+        std::vector<int> lrow_step;                // for each l: elimination step index of its row
+        std::vector<int> ucol_step;                // for each u: elimination step index of its column
+    };
+    std::vector<Step> steps;                       // [n+1], 1-based
+    bool dense = false;
+};
+
+struct Plan {
+    tsb_ctx* ctx = nullptr;
+    int n_nodes = 0, n_branches = 0;
+    std::vector<Dev> devs;                          // netlist order
+    std::vector<int> stamp_order;                   // device indices, K last (circuit.go:83-152)
+    std::vector<std::string> node_names;            // [n_nodes+1], from_netlist plans
+    std::string title;
+    // dot-card request (from_netlist plans)
+    int analysis = TSB_AN_OP;
+    double tran[4] = {0, 0, 0, 0};
+    int uic = 0;
+    int dc_src_dev = -1;
+    double dc[3] = {0, 0, 0};
+    std::string dc_src_name;
+    // finalize results
+    bool finalized = false;
+    int n_params = 0, n_state = 0, n_src = 0, n_derived = 0;
+    std::vector<double> nominal;                    // flat parameter space
+    std::vector<double> pwl_table;                  // concatenated PWL tables (uniform data)
+    std::vector<std::vector<StampEntry>> stamps;    // per device: ordered AddElement/AddRHS calls (OP + tran)
+    std::vector<std::pair<int, int>> pattern_op, pattern_tran_extra;   // first-touch order
+    PivotOrder order_main, order_init;
+    LuProgram lu_main, lu_init;
+    bool init_struct_singular = false;
+    bool has_nonlinear = false, has_time_dependent = false, has_bjt = false;
+    std::string error;
+
+    int n() const { return n_nodes + n_branches; }
+    int num_columns(int analysis_) const;
+    std::string column_name(int analysis_, int col) const;
+};
+
+// netlist.cpp
+int plan_from_netlist(const std::string& text, Plan& plan, std::string& err);
+// plan.cpp
+int plan_finalize(Plan& plan);
+void device_stamp_entries(const Plan& plan, int dev_index, std::vector<StampEntry>& out);
+int device_num_outputs(const Dev& d);
+// codegen.cpp
+struct CodegenConfig {
+    std::vector<char> varying;      // [n_params] 1 -> read per instance from the SoA parameter buffer
+    std::vector<int> var_slot;      // [n_params] slot in the SoA buffer or -1
+    int n_var = 0;
+    int block_size = 128;
+    int dc_param = -1;              // flat parameter index overwritten by the DC sweep value
+};
+std::string generate_source(const Plan& plan, const CodegenConfig& cfg);
+
+}  // namespace tsb

@@ -29,3 +29,46 @@ BUNDLED = {
     'vpulse': '* vpulse test circuit\nVpulse n1 0 PULSE(0 5 2ms 0.5ms 0.5ms 5ms 10ms)\nR1 n1 0 1k\n\n.tran 0.1ms 30ms',
     'vpwl': '* vpwl test circuit\nVpwl n1 0 PWL(0 0 2ms 0 2.5ms 3.3 5ms 3.3 5.5ms 0 10ms 0)\nR1 n1 0 1k\n\n.tran 0.1ms 15ms',
 }
+
+
+# Synthetic sweep definitions of SURVEY.md §8(d): which parameters of which device kinds vary per
+# instance, and how they are drawn around the netlist's nominal value.  Device kinds use the
+# numbering of include/tspice_b200.h.  Entries: kind -> [(param index, distribution, a, b)], with
+# "logu" = nominal * LogUniform[a, b], "u" = Uniform[a, b], "n" = Normal(a, b).
+SWEEP_SPEC = {
+    0: [(0, "logu", 0.5, 2.0)],                       # R
+    1: [(0, "logu", 0.5, 2.0)],                       # C
+    2: [(0, "logu", 0.5, 2.0)],                       # L
+    8: [(0, "u", 0.8, 0.99)],                         # K coupling coefficient
+    5: [(0, "logu", 0.1, 10.0), (1, "u", 1.0, 2.0)],  # D: Is, N
+    6: [(0, "logu", 0.1, 10.0), (2, "u", 0.97, 0.995), (5, "u", 50.0, 150.0)],   # Q: Ies, alphaF, Vaf
+    7: [(0, "n", 0.7, 0.05), (1, "logu", 0.8, 1.25), (4, "u", 0.0, 0.02)],       # M: VTO, KP, LAMBDA
+    9: [(1, "logu", 0.5, 2.0)],                       # core area
+}
+SWEEP_SEEDS = {"rc": 1234, "rlc": 1234, "rl": 1234, "rr": 1234, "diode": 2345, "bjt": 3456, "mosfet": 3456,
+               "transformer": 4567}
+
+
+def sweep_seed(name: str) -> int:
+    for k, v in SWEEP_SEEDS.items():
+        if name.startswith(k):
+            return v
+    return 999
+
+
+def sweep_draws(devices, n: int, seed: int):
+    """{(device name, param index): float64[n]} in device order (PCG64, instance-major per parameter)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for d in devices:
+        for (pi, dist, a, b) in SWEEP_SPEC.get(d["kind"], []):
+            nominal = d["p"][pi]
+            if dist == "logu":
+                v = nominal * np.exp(rng.uniform(np.log(a), np.log(b), n))
+            elif dist == "u":
+                v = rng.uniform(a, b, n)
+            else:
+                v = rng.normal(a, b, n)
+            out[(d["name"], pi)] = v
+    return out
