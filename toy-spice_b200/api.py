@@ -387,13 +387,13 @@ class Batch:
         lib().tsb_result_dims(self.h, C.byref(n), C.byref(c), C.byref(r))
         return n.value, c.value, r.value
 
-    def rows(self) -> np.ndarray:
-        out = np.zeros(self.n_inst, dtype=np.int64)
+    def rows(self, out=None) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int64) if out is None else out
         self._check(lib().tsb_result_rows(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_rows")
         return out
 
-    def status(self) -> np.ndarray:
-        out = np.zeros(self.n_inst, dtype=np.int32)
+    def status(self, out=None) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int32) if out is None else out
         self._check(lib().tsb_result_status(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))), "result_status")
         return out
 
@@ -421,9 +421,10 @@ class Batch:
         self._check(lib().tsb_result_wave_all(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size), "result_wave_all")
         return out
 
-    def stats_all(self) -> np.ndarray:
+    def stats_all(self, out=None) -> np.ndarray:
+        """[4: min, max, sum, last][ncol][n_inst]; `out` may be a (pinned) preallocated array."""
         n, ncol, _ = self.dims()
-        out = np.zeros((4, ncol, n))
+        out = np.zeros((4, ncol, n)) if out is None else out
         self._check(lib().tsb_result_stats_all(self.h, out.ctypes.data_as(C.POINTER(C.c_double))), "result_stats_all")
         return out
 
