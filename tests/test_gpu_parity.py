@@ -1,0 +1,215 @@
+"""GPU parity tests proper (run with `-m gpu` on the B200 box).  Everything goes through the C-ABI
+(ctypes -> libtspice_b200.so); the CPU oracle is only the checker.
+
+Bar: node numbering / pattern exact (tests/test_host.py); node voltages and branch currents within
+|gpu - ref| <= 1e-9*|ref| + 1e-12 at identical stored rows; row counts, per-instance status and NaN
+pattern identical.  Full-size runs (BASELINE.json sizes) are checked through size-independent
+properties (linearity, permutation equivariance, waveform <-> statistics consistency) plus an oracle
+comparison on a sub-sample."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import parity_util as PU
+
+T, O = PU.T, PU.O
+pytestmark = pytest.mark.gpu
+DECKS = [d for d in sorted(T.BUNDLED) if d != "bjt3"]
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz")
+
+
+def _parity(ctx, name, n, strict, cap=12288):
+    text = T.BUNDLED[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=cap, opts=T.default_opts(strict_fp=strict))
+    _, ores = PU.run_oracle(text, n, ov, cap_rows=cap)
+    return PU.compare_waves(batch, ores, n), batch, ores
+
+
+@pytest.mark.parametrize("strict", [0, 1], ids=["fma", "strict"])
+@pytest.mark.parametrize("name", DECKS)
+def test_deck_matches_oracle(ctx, name, strict):
+    """Every bundled deck (OP, DC sweep and transient cards), 48-instance SURVEY §8(d) sweep."""
+    rep, batch, ores = _parity(ctx, name, 48, strict)
+    assert PU.report_ok(rep), rep
+    assert rep["compared_points"] > 0 or name.startswith("bjt")     # bjt1 is all-NaN in the reference too
+    # accepted / rejected step counts are discrete decisions: identical except for documented near-threshold flips
+    assert rep["counter_mismatch"] <= 2, rep
+
+
+def test_golden_vectors(ctx):
+    g = np.load(GOLD)
+    for name in sorted({k.split("/")[0] for k in g.files}):
+        keys = [tuple(s.split("|")) for s in g[f"{name}/ov_keys"]]
+        ov = {(d, int(p)): g[f"{name}/ov_vals"][i].copy() for i, (d, p) in enumerate(keys)}
+        ckt, batch, an = PU.run_gpu(ctx, T.BUNDLED[name], 4, ov, cap_rows=12288)
+        assert np.array_equal(batch.rows(), g[f"{name}/n_rows"]), name
+        assert np.array_equal(batch.status(), g[f"{name}/status"]), name
+        for i in range(4):
+            w = batch.waveform(i)[g[f"{name}/rows_idx/{i}"]]
+            ref = g[f"{name}/wave/{i}"]
+            assert np.array_equal(np.isnan(w), np.isnan(ref)), (name, i)
+            ok = np.isfinite(ref)
+            assert np.all(np.abs(w[ok] - ref[ok]) <= PU.RELTOL * np.abs(ref[ok]) + PU.ABSTOL), (name, i)
+
+
+def test_rr_plumbing_batch_of_one(ctx):
+    """BASELINE.json configs[0]: rr.cir, batch = 1 — exact known answer through the reference-shaped API."""
+    ckt = T.Circuit.from_netlist(T.BUNDLED["rr"], ctx)
+    op = T.NewOP()
+    op.Setup(ckt)
+    op.Execute()
+    r = op.GetResults()
+    assert set(r) == {"V(1)", "V(2)", "I(Vin)"}
+    assert r["V(1)"][0] == 5.0 and r["V(2)"][0] == 2.5 and abs(r["I(Vin)"][0] + 2.5e-3) < 1e-18
+    tr = T.analysis_from_card(ckt)
+    tr.Setup(ckt)
+    tr.Execute()
+    res = tr.GetResults()
+    assert set(res) == {"TIME", "V(1)", "V(2)", "I(Vin)", "I(R1)", "I(R2)"}
+    assert len(res["TIME"]) == 38 and res["TIME"][-1] == 0.003
+    assert np.all(res["V(2)"] == 2.5) and np.allclose(res["I(R2)"], 2.5e-3, rtol=0, atol=1e-18)
+    assert int(tr.batch.counters()[0, 0]) == 38 and int(tr.batch.counters()[2, 0]) == 76
+
+
+def test_strict_mode_is_bitwise_for_rc(ctx):
+    """With --fmad=false and the same pivot order the GPU reproduces the oracle's rounding on rc.cir
+    except for the source term (CUDA sin vs the restated Go sin): V(2) agrees to a few ulp."""
+    rep, batch, ores = _parity(ctx, "rc", 32, 1, cap=320)
+    assert rep["row_mismatch"] == 0 and rep["max_abs"] < 5e-15
+
+
+def test_nvrtc_runtime_specialisation(ctx, built):
+    """An unseen netlist (not in the pre-built kernel cache) is specialised at run time with NVRTC."""
+    text = ("ladder\nV1 1 0 SIN(0 1 2k)\nR1 1 2 10\nC1 2 0 100n\nR2 2 3 22\nC2 3 0 47n\nR3 3 4 33\nC3 4 0 10n\n"
+            "R4 4 0 1k\n.tran 1u 1m\n")
+    with tempfile.TemporaryDirectory() as d:
+        c2 = built.Context(0)
+        c2.set_cache_dir(d)
+        n = 16
+        ov = PU.draws("ladder", T.Circuit.from_netlist(text), n, seed=77)
+        ckt, batch, an = PU.run_gpu(c2, text, n, ov, cap_rows=4096)
+        assert any(f.endswith(".cubin") for f in os.listdir(d))
+        _, ores = PU.run_oracle(text, n, ov, cap_rows=4096)
+        rep = PU.compare_waves(batch, ores, n)
+        assert PU.report_ok(rep), rep
+
+
+def test_waveform_overflow_is_reported_per_instance(ctx):
+    ov = {}
+    ckt, batch, an = PU.run_gpu(ctx, T.BUNDLED["rc"], 8, ov, cap_rows=100)
+    assert np.all(batch.status() == T.api.ST_OVERFLOW) and np.all(batch.rows() == 305)
+    assert batch.waveform(0).shape == (100, 5)
+
+
+def test_stats_equal_waveform_reduction(ctx):
+    n = 64
+    text = T.BUNDLED["rlc"]
+    ov = PU.draws("rlc", T.Circuit.from_netlist(text), n)
+    ckt, b1, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_WAVE | T.OUT_STATS, cap_rows=12288)
+    w = b1.wave_all()
+    s = b1.stats_all()
+    rows = b1.rows()
+    for i in range(0, n, 7):
+        wi = w[: rows[i], :, i]
+        assert np.array_equal(s[0, :, i], wi.min(axis=0)) and np.array_equal(s[1, :, i], wi.max(axis=0))
+        assert np.array_equal(s[3, :, i], wi[-1])
+        seq = np.zeros(wi.shape[1])
+        for r in range(wi.shape[0]):
+            seq = seq + wi[r]
+        assert np.array_equal(s[2, :, i], seq)         # same sequential summation order as the kernel
+
+
+def test_full_size_rc_properties(ctx):
+    """BASELINE.json configs[1] size (2^20 instances of rc.cir): size-independent properties + sub-sample vs oracle."""
+    n = 1 << 20
+    text = T.BUNDLED["rc"]
+    ckt0 = T.Circuit.from_netlist(text)
+    ov = PU.draws("rc", ckt0, n)
+    ckt, b, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS)
+    assert np.all(b.status() == 0) and np.all(b.rows() == 305)
+    tot = b.totals()
+    assert tot[0] == 305 * n and tot[1] == 0 and tot[2] == 610 * n
+    s = b.stats_all()
+    # V(1) is the source: its statistics cannot depend on R or C
+    assert np.all(s[:, 1, :] == s[:, 1, :1])
+    # permutation equivariance: permuting the parameter arrays permutes the results bit for bit
+    perm = np.random.default_rng(5).permutation(n)
+    ovp = {k: v[perm] for k, v in ov.items()}
+    _, bp, _ = PU.run_gpu(ctx, text, n, ovp, out=T.OUT_STATS)
+    assert np.array_equal(bp.stats_all(), s[:, :, perm])
+    # linearity: halving the source amplitude halves every signal exactly (power-of-two scaling is exact and
+    # keeps the step sequence: the capacitor LTE only shrinks)
+    ckt_h = T.Circuit.from_netlist(text, ctx)
+    bh = ckt_h.batch(n)
+    for (d, p), v in ov.items():
+        bh.set_param(d, p, v)
+    bh.set_param("vin", 1, 2.5)
+    card = ckt_h.analysis_card()
+    bh.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS)
+    bh.sync()
+    sh = bh.stats_all()
+    assert np.array_equal(sh[:, 1:, :], 0.5 * s[:, 1:, :]) and np.array_equal(sh[:, 0, :], s[:, 0, :])
+    # sub-sample against the oracle
+    idx = np.random.default_rng(6).choice(n, 256, replace=False)
+    _, ores = PU.run_oracle(text, 256, {k: v[idx] for k, v in ov.items()}, want_stats=True, cap_rows=320)
+    ref = ores["stats"].transpose(1, 2, 0)
+    got = s[:, :, idx]
+    assert np.all(np.abs(got - ref) <= 305 * (PU.RELTOL * np.abs(ref) + PU.ABSTOL))
+
+
+def test_full_size_rlc_subsample(ctx):
+    """2^20 instances of rlc.cir (20 795 accepted steps each), statistics output; 64-instance sub-sample vs oracle."""
+    n = 1 << 20
+    text = T.BUNDLED["rlc"]
+    ov = PU.draws("rlc", T.Circuit.from_netlist(text), n)
+    ckt, b, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS)
+    assert np.all(b.status() == 0)
+    tot = b.totals()
+    assert tot[0] == 20795 * n and tot[1] == 2861 * n and tot[2] == 47312 * n
+    idx = np.random.default_rng(7).choice(n, 64, replace=False)
+    _, ores = PU.run_oracle(text, 64, {k: v[idx] for k, v in ov.items()}, want_stats=True, want_wave=False)
+    s = b.stats_all()[:, :, idx]
+    ref = ores["stats"].transpose(1, 2, 0)
+    rows = b.rows()[idx]
+    assert np.array_equal(rows, ores["n_rows"])
+    for k in (0, 1, 3):                       # min, max, last
+        assert np.all(np.abs(s[k] - ref[k]) <= PU.RELTOL * np.abs(ref[k]) + PU.ABSTOL)
+    assert np.all(np.abs(s[2] - ref[2]) <= 1e-7 * np.abs(ref[2]) + 1e-9)     # sums of ~11 400 rows
+
+
+def test_uniform_override_and_device_pointers(ctx):
+    """set_param with a scalar (uniform), a host array, and a CUDA tensor (borrowed HBM pointer) agree."""
+    import torch
+    text = T.BUNDLED["rc"]
+    n = 64
+    r = np.linspace(50.0, 200.0, n)
+    c1 = T.Circuit.from_netlist(text, ctx)
+    b1 = c1.batch(n)
+    b1.set_param("r1", 0, r)
+    b1.set_param("c1", 0, 2e-6)
+    c2 = T.Circuit.from_netlist(text, ctx)
+    b2 = c2.batch(n)
+    b2.set_param("r1", 0, torch.from_numpy(r).cuda())
+    b2.set_param("c1", 0, torch.full((n,), 2e-6, dtype=torch.float64, device="cuda"))
+    for b in (b1, b2):
+        b.run_tran(0.0, 3e-3, 1e-5, 1e-5, out=T.OUT_WAVE, cap_rows=320)
+        b.sync()
+    assert np.array_equal(b1.wave_all(), b2.wave_all())
+    _, ores = PU.run_oracle(text, n, {("r1", 0): r, ("c1", 0): np.full(n, 2e-6)}, cap_rows=320)
+    assert PU.report_ok(PU.compare_waves(b1, ores, n))
+
+
+def test_newton_fallback_paths_match(ctx):
+    """diode1.cir needs Gmin stepping in the reference (op.go:192-214): path and result must agree."""
+    rep, batch, ores = _parity(ctx, "diode1", 32, 0)
+    assert PU.report_ok(rep)
+    assert np.array_equal(batch.counters()[4], ores["counters"][:, 4])       # 0 direct / 1 Gmin / 2 source stepping
+    assert batch.counters()[4].max() >= 1
+
+
+def test_fp64_peak_measurement(ctx):
+    tf = ctx.measure_fp64_peak()
+    assert 20.0 < tf < 60.0, tf        # B200 FP64 vector: ~37 TFLOP/s

@@ -157,7 +157,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     Emitter e;
     const int n = pl.n();
     const int ncol_tran = pl.num_columns(TSB_AN_TRAN);
-    e.line("// Generated by tspice_b200 codegen for netlist \"" + pl.title + "\": n=" + std::to_string(n) + ", " +
+    e.line("// Generated by tspice_b200 codegen: n=" + std::to_string(n) + ", " +
            std::to_string(pl.devs.size()) + " devices, " + std::to_string(pl.lu_main.pos.size()) + " matrix entries incl. fill" +
            (pl.lu_main.dense ? " (dense)" : "") + ".");
     e.line("#define TSB_BLOCK " + std::to_string(cfg.block_size));
