@@ -290,15 +290,11 @@ def main():
 
     totals = {d["name"]: d["b_res"].totals() for d in decks}
     acc_local = int(sum(t[0] for t in totals.values()))
-    solves_local = int(sum(t[2] + t[3] for t in totals.values()))
+    solves_local = int(sum(t[2] + t[3] for t in totals.values()))     # as the reference counts them
+    exec_local = int(sum(t[4] for t in totals.values()))              # factor+solve passes actually executed
     t_local = sum(ms_steps) * 1e-3
-    tt = torch.tensor([t_local, float(acc_local), float(solves_local)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_job, acc_job, solves_job = float(tmax[0]), float(tsum[1]), float(tsum[2])
-    else:
-        t_job, acc_job, solves_job = t_local, float(acc_local), float(solves_local)
+    S = importlib.import_module("toy-spice_b200.sharding")
+    t_job, (acc_job, solves_job, exec_job) = S.reduce_job(t_local, [acc_local, solves_local, exec_local], device=f"cuda:{local}")
     value = acc_job * args.steps / t_job if t_job > 0 else 0.0
 
     # ---- timed: end to end through the public API with host buffers -----------------------------
@@ -318,7 +314,7 @@ def main():
     # ---- roofline of the dominant launch (rlc transient) -----------------------------------------
     dom = decks[-1]
     dom_tot = totals[dom["name"]]
-    dom_solves = int(dom_tot[2] + dom_tot[3])
+    dom_solves = int(dom_tot[4])          # EXECUTED factor+solve passes (the redundant linear re-solve is not run, not counted)
     dom_flops = dom_solves * dom["flops"]["total"]
     dom_ms = float(np.mean(ms_dom))
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
@@ -326,7 +322,7 @@ def main():
         "bound": "fp64", "kernel": "tsb_optran (rlc.cir)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
         "peak_source": "DFMA-chain microbenchmark measured in this run (tsb_ctx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-        "flops_per_solve": dom["flops"], "solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
+        "flops_per_solve": dom["flops"], "executed_solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
         "algorithmic_hbm_bytes_per_launch": n * (8 * 3 + 4 * dom["ncol"] * 8 + 8 + 4 + 6 * 8),
     }
 
@@ -348,6 +344,7 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)", "strict_fp": args.strict_fp},
             "accepted_steps_per_step": acc_job, "newton_solves_per_step": solves_job,
             "newton_solves_per_sec": solves_job * args.steps / t_job if t_job > 0 else 0.0,
+            "executed_solves_per_step": exec_job,
             "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world},
             "gpu_launches": int(launches), "failed_instances": bad_status,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

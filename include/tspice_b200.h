@@ -89,9 +89,15 @@ typedef struct tsb_opts {
     double reltol;      /* 1e-6  */
     double gmin;        /* 1e-12 (only recorded in ckt.Status; the solves use 0) */
     double trtol;       /* 7.0   */
-    int strict_fp;      /* 1: compile kernels with --fmad=false (reference rounding, no FMA contraction) */
+    int strict_fp;      /* 1: reference rounding (no FMA contraction, IEEE division wherever the reference divides);
+                           0: fast build (FMA, one reciprocal of dt per step, reciprocal-seed pivots; each
+                              substituted operation within 1 ulp); -1 (default): 1 for circuits with mutual
+                              couplings (condition numbers ~1e7 make 1-ulp differences visible at 1e-9), else 0 */
     int block_size;     /* 0: default (128) */
-    int reuse_lu;       /* reserved (0) */
+    int skip_linear_resolve; /* 1 (default): circuits without nonlinear devices do not execute the reference's
+                           second Newton solve per step — it re-stamps identical values, returns identical bits and
+                           always passes the convergence test; counters still report it (reference-equivalent) */
+    int min_blocks;     /* __launch_bounds__ min resident blocks per SM for the specialised kernels (0: default) */
 } tsb_opts;
 
 /* Output selection for tsb_run_tran / tsb_run_dc. */
@@ -174,21 +180,23 @@ int tsb_batch_sync(tsb_batch* batch);
  * Layout in HBM (structure of arrays, instance is the fastest index so warps store coalesced):
  *   wave     [cap_rows][n_columns][n_inst]    stats [4: min,max,sum,last][n_columns][n_inst]
  *   rows     [n_inst] int64                   status [n_inst] int32
- *   counters [6][n_inst] int64: accepted steps, rejected steps, transient solves, OP solves,
- *            OP path (0 direct, 1 Gmin stepping, 2 source stepping), failure time/value (double bits) */
+ *   counters [8][n_inst] int64: 0 accepted steps, 1 rejected steps, 2 transient solves, 3 OP solves (2, 3: as the
+ *            reference would count them), 4 OP path (0 direct, 1 Gmin stepping, 2 source stepping),
+ *            5 failure time/value (double bits), 6 factor+solve passes actually executed, 7 reserved */
 int tsb_result_dims(const tsb_batch* batch, int64_t* n_inst, int* n_columns, int64_t* cap_rows);
 int tsb_result_dev_ptrs(const tsb_batch* batch, uint64_t* wave, uint64_t* stats, uint64_t* rows, uint64_t* status,
                         uint64_t* counters);
 int tsb_result_rows(tsb_batch* batch, int64_t* rows /*[n_inst]*/);
 int tsb_result_status(tsb_batch* batch, int32_t* status /*[n_inst]*/);
-int tsb_result_counters(tsb_batch* batch, int64_t* counters /*[6][n_inst]*/);
+int tsb_result_counters(tsb_batch* batch, int64_t* counters /*[8][n_inst]*/);
 /* Waveform of one instance, row-major [rows][n_columns]; returns the row count in *n_rows. */
 int tsb_result_waveform(tsb_batch* batch, int64_t inst, double* out, int64_t cap_rows, int64_t* n_rows);
 /* Whole wave / stats arrays in the device layout above. */
 int tsb_result_wave_all(tsb_batch* batch, double* out, int64_t n_doubles);
 int tsb_result_stats_all(tsb_batch* batch, double* out /*[4][n_columns][n_inst]*/);
-/* Batch totals computed on the GPU: sum over instances of accepted steps, rejected, transient solves, OP solves. */
-int tsb_result_totals(tsb_batch* batch, int64_t totals[4]);
+/* Batch totals computed on the GPU: sum over instances of accepted steps, rejected steps, transient solves,
+ * OP solves (reference-equivalent counts) and executed factor+solve passes. */
+int tsb_result_totals(tsb_batch* batch, int64_t totals[5]);
 
 /* ---- introspection / build-time support -------------------------------------------------------*/
 /* CUDA source of the kernels specialised for this batch configuration (which parameters vary). */

@@ -59,14 +59,16 @@ def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, anal
     return ckt, batch, an
 
 
-def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None):
+def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None, want_wave=True):
     oc = O.OracleCircuit(text)
-    res = oc.run(n, overrides=overrides, threads=threads, cap_rows=cap_rows, want_stats=want_stats, analysis=analysis, tran=tran)
+    res = oc.run(n, overrides=overrides, threads=threads, cap_rows=cap_rows, want_stats=want_stats, analysis=analysis, tran=tran,
+                 want_wave=want_wave)
     return oc, res
 
 
-def compare_waves(batch, ores, n, label=""):
-    """Instance-by-instance comparison at identical stored rows.  Returns a report dict."""
+def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
+    """Instance-by-instance comparison at identical stored rows.  Returns a report dict
+    (max_rel = worst |gpu - ref| / (reltol*|ref| + abstol); <= 1 means inside the tolerance)."""
     rows_g = batch.rows()
     st_g = batch.status()
     cnt_g = batch.counters()
@@ -92,7 +94,7 @@ def compare_waves(batch, ores, n, label=""):
             continue
         ok = ~nan_o & np.isfinite(wo) & np.isfinite(wg)
         err = np.abs(wg[ok] - wo[ok])
-        tol = RELTOL * np.abs(wo[ok]) + ABSTOL
+        tol = reltol * np.abs(wo[ok]) + abstol
         rep["compared_points"] += int(ok.sum())
         if err.size:
             ratio = err / tol

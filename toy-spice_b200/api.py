@@ -51,7 +51,7 @@ class TsbError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("abstol", C.c_double), ("reltol", C.c_double), ("gmin", C.c_double),
-                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("reuse_lu", C.c_int)]
+                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int)]
 
 
 def lib_path() -> str:
@@ -398,12 +398,12 @@ class Batch:
         return out
 
     def counters(self) -> np.ndarray:
-        out = np.zeros((6, self.n_inst), dtype=np.int64)
+        out = np.zeros((8, self.n_inst), dtype=np.int64)
         self._check(lib().tsb_result_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_counters")
         return out
 
     def totals(self) -> np.ndarray:
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(5, dtype=np.int64)
         self._check(lib().tsb_result_totals(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "result_totals")
         return out
 

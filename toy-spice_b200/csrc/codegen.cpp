@@ -124,7 +124,7 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
         std::string piv = "A[" + std::to_string(st.piv) + "]";
         e.line("// step " + std::to_string(k) + ": pivot (" + std::to_string(lu.prow[k]) + "," + std::to_string(lu.pcol[k]) + ")");
         e.line("if (" + piv + " == 0.0) return false;");
-        e.line(piv + " = 1.0 / " + piv + ";");
+        e.line(piv + " = " + std::string(lu.dense ? "1.0 / " + piv : "tsb_rcp(" + piv + ")") + ";");
         for (size_t ui = 0; ui < st.urow.size(); ++ui) {
             std::string u = "A[" + std::to_string(st.urow[ui]) + "]";
             e.line(u + " *= " + piv + ";");
@@ -161,6 +161,9 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
            std::to_string(pl.devs.size()) + " devices, " + std::to_string(pl.lu_main.pos.size()) + " matrix entries incl. fill" +
            (pl.lu_main.dense ? " (dense)" : "") + ".");
     e.line("#define TSB_BLOCK " + std::to_string(cfg.block_size));
+    if (cfg.fast_div) e.line("#define TSB_FAST_DIV 1");
+    e.line("#define TSB_MIN_BLOCKS " + std::to_string(cfg.min_blocks));
+    e.line("#define TSB_SKIP_LINEAR_RESOLVE " + std::to_string(cfg.skip_linear ? 1 : 0));
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
     e.line("struct Ckt {");
@@ -198,6 +201,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         const Dev& d = pl.devs[di];
         std::string P = "P + " + std::to_string(d.p_off);
         if (d.kind == TSB_R) e.line("D[" + std::to_string(d.d_off) + "] = tsb_res_g(" + P + ");");
+        else if (d.kind == TSB_L) e.line("tsb_ind_derive(" + P + ", D + " + std::to_string(d.d_off) + ");");
         else if (d.kind == TSB_LCORE) e.line("D[" + std::to_string(d.d_off) + "] = tsb_lcore_L0(" + P + ");");
         else if (d.kind == TSB_M) e.line("tsb_mos_init_state(" + P + ", S + " + std::to_string(d.s_off) + ");");
         else if (d.kind == TSB_K) {
@@ -218,7 +222,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("__device__ __forceinline__ void init() {");
     ++e.ind;
     if (pl.has_nonlinear) {
-        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = 0.0; e.gmin = 0.0;");
+        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = 0.0; e.gmin = 0.0; e.rdt = 0.0;");
         for (int di : pl.stamp_order) {
             if (!pl.devs[di].nonlinear()) continue;
             e.line("{");
@@ -285,7 +289,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         e.line("(void)status_dt; (void)out;");
         e.line("return false;   // structurally singular without the nonlinear devices -> nil estimate");
     } else {
-        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = status_dt; e.gmin = 0.0;");
+        e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = status_dt; e.gmin = 0.0; e.rdt = status_dt > 0 ? 1.0 / status_dt : 0.0;");
         e.line("double A[" + std::to_string(pl.lu_init.pos.size()) + "];");
         e.line("double b[" + std::to_string(n + 1) + "];");
         for (size_t k = 0; k < pl.lu_init.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;");
@@ -301,9 +305,9 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
 
     // ---- Newton body ----------------------------------------------------------------------------
     e.line("// mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin); mat.Solve()  ->  x");
-    e.line("__device__ __forceinline__ bool assemble_solve(int mode, double time, double dt, double gmin) {");
+    e.line("__device__ __forceinline__ bool assemble_solve(int mode, double time, double dt, double rdt, double gmin) {");
     ++e.ind;
-    e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin;");
+    e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin; e.rdt = rdt;");
     e.line("double A[" + std::to_string(pl.lu_main.pos.size()) + "];");
     e.line("double b[" + std::to_string(n + 1) + "];");
     for (size_t k = 0; k < pl.lu_main.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;   // (" + std::to_string(pl.lu_main.pos[k].first) + "," + std::to_string(pl.lu_main.pos[k].second) + ")");
@@ -324,7 +328,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     ++e.ind;
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
-        if (d.kind == TSB_L) e.line("tsb_ind_load(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ", dt);");
+        if (d.kind == TSB_L) e.line("tsb_ind_load(P + " + std::to_string(d.p_off) + ", D + " + std::to_string(d.d_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ", dt);");
     }
     e.line("(void)dt;");
     --e.ind;
@@ -334,19 +338,19 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
         if (d.kind == TSB_C) e.line("tsb_cap_update(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ");");
-        if (d.kind == TSB_L) e.line("tsb_ind_update(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ");");
+        if (d.kind == TSB_L) e.line("tsb_ind_update(D + " + std::to_string(d.d_off) + ", S + " + std::to_string(d.s_off) + ", " + vd_expr(d) + ");");
     }
     --e.ind;
     e.line("}");
-    e.line("__device__ __forceinline__ double lte(double dt) {   // Transient.calculateTruncError (tran.go:239-250)");
+    e.line("__device__ __forceinline__ double lte(double dt, double rdt) {   // Transient.calculateTruncError (tran.go:239-250)");
     ++e.ind;
     e.line("double m = 0.0, l;");
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
-        if (d.kind == TSB_C) e.line("l = tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt); if (l > m) m = l;");
-        if (d.kind == TSB_L) e.line("l = tsb_ind_lte(S + " + std::to_string(d.s_off) + ", dt); if (l > m) m = l;");
+        if (d.kind == TSB_C) e.line("l = tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt, rdt); if (l > m) m = l;");
+        if (d.kind == TSB_L) e.line("l = tsb_ind_lte(S + " + std::to_string(d.s_off) + ", dt, rdt); if (l > m) m = l;");
     }
-    e.line("(void)dt; (void)l;");
+    e.line("(void)dt; (void)rdt; (void)l;");
     e.line("return m;");
     --e.ind;
     e.line("}");
@@ -360,14 +364,15 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         for (int b = pl.n_nodes + 1; b <= n; ++b) e.line("out[" + std::to_string(k++) + "] = -x[" + std::to_string(b) + "];");
         for (const Dev& d : pl.devs)
             if (d.kind == TSB_R)
-                e.line("out[" + std::to_string(k++) + "] = (x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "]) / P[" + std::to_string(d.p_off) + "];   // I(" + d.name + ")");
+                e.line("out[" + std::to_string(k++) + "] = (x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "]) " +
+                       (cfg.fast_div ? "* D[" + std::to_string(d.d_off) + "]" : "/ P[" + std::to_string(d.p_off) + "]") + ";   // I(" + d.name + ")");
     }
     --e.ind;
     e.line("}");
     --e.ind;
     e.line("};");
     e.line("");
-    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_optran(TsbArgs a) {");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK, TSB_MIN_BLOCKS) tsb_optran(TsbArgs a) {");
     e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_inst; inst += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_optran_instance<Ckt>(a, inst);");
     e.line("}");

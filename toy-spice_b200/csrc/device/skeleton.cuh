@@ -40,6 +40,7 @@ struct TsbArgs {
     double* scratch;           // [N+1][n_inst]  "currentSolution" of the OP fallbacks
     const double* sweep;       // [n_sweep] DC sweep values
     int n_sweep;
+    int skip_linear_resolve;   // linear circuits: do not execute the second, bit-identical Newton solve
 };
 
 #define TSB_ST_OK 0
@@ -142,7 +143,8 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     c.init();
     TsbSink<Ckt::NCOL_MAX> sink(a, inst);   // NCOL_MAX = transient column count (>= OP column count)
 
-    long long n_acc = 0, n_rej = 0, n_sol_tran = 0, n_sol_op = 0;
+    long long n_acc = 0, n_rej = 0, n_sol_tran = 0, n_sol_op = 0;   // as the reference would count them
+    long long n_exec = 0;                                            // factor+solve passes actually executed
     int op_path = 0, status = TSB_ST_OK;
     double fail_at = 0.0;
 
@@ -151,7 +153,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     int phase = (a.analysis == TSB_AN_TRAN && a.uic) ? PH_TRAN_BEGIN : PH_OP_START;
     int op_pass = 0, cont = C_MAIN, iter = 0, mode = TSB_MODE_OP, gstep = 0;
     double gmin = 0.0, sfac = 0.0, status_dt = 0.0;
-    double time = 0.0, dt = a.minstep, next_time = 0.0;
+    double time = 0.0, dt = a.minstep, next_time = 0.0, rdt = 0.0;
     bool have_last = false;
     double last_time = 0.0;
     long long last_key = 0;
@@ -173,17 +175,25 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             next_time = time + dt;
             if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
             c.eval_sources(time, 1.0);          // sources are evaluated at the START of the step
+            rdt = 1.0 / dt;                     // the one division by the time step of this attempt
             iter = 0; mode = TSB_MODE_TRAN; gmin = 0.0; cont = C_TRAN; phase = PH_NR;
         }
 
         // ---------------- one Newton iteration (op.go:45-86, tran.go:172-213) -------------------
         if (Ckt::HAS_NL && (mode == TSB_MODE_OP || iter > 0)) c.update_nl(c.xo);
         const bool is_tran = mode == TSB_MODE_TRAN;
-        bool solved = c.assemble_solve(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, gmin);
+        bool solved = c.assemble_solve(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
         if (is_tran) ++n_sol_tran; else ++n_sol_op;
+        ++n_exec;
         bool conv = false, fail = !solved;
         if (solved) {
-            if (iter > 0) conv = tsb_converged<N>(c.x, c.xo, a.reltol, a.abstol);
+            if (!Ckt::HAS_NL && TSB_SKIP_LINEAR_RESOLVE) {
+                // A circuit without NonLinear devices re-stamps identical values in iteration 1, so the
+                // reference's second solve returns the very same bits and its test |x - x| <= tol passes
+                // (NaN / Inf included).  Skip executing it; count it as the reference would.
+                conv = true;
+                if (is_tran) ++n_sol_tran; else ++n_sol_op;
+            } else if (iter > 0) conv = tsb_converged<N>(c.x, c.xo, a.reltol, a.abstol);
             if (!conv) {
 #pragma unroll
                 for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
@@ -251,7 +261,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
                 break;
             }
             {
-                double lte = c.lte(dt);                           // tran.go:122, 239-250
+                double lte = c.lte(dt, rdt);                      // tran.go:122, 239-250
                 if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; break; }
                 c.load_state(dt);                                 // tran.go:137-138
                 c.update_state();
@@ -310,6 +320,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     a.counters[3 * a.n_inst + inst] = n_sol_op;
     a.counters[4 * a.n_inst + inst] = op_path;
     a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+    a.counters[6 * a.n_inst + inst] = n_exec;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,7 +340,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     if (a.n_sweep > 0) { c.set_dc(a.sweep[0]); c.eval_sources(0.0, 1.0); }
     while (k < a.n_sweep) {
         if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
-        bool solved = c.assemble_solve(TSB_MODE_OP, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
+        bool solved = c.assemble_solve(TSB_MODE_OP, 0.0, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
         if (iter < 0) { iter = 0; continue; }
         ++n_sol;
         bool conv = false, fail = !solved;
@@ -359,6 +370,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     a.counters[3 * a.n_inst + inst] = n_sol;
     a.counters[4 * a.n_inst + inst] = 0;
     a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+    a.counters[6 * a.n_inst + inst] = n_sol + a.n_sweep;      // + the discarded stamp pass per sweep value
 }
 
 #endif  // TSB_SKELETON_CUH

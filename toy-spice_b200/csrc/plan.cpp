@@ -154,6 +154,7 @@ struct Nominal {
         for (int di : pl.stamp_order) {
             const Dev& d = pl.devs[di];
             if (d.kind == TSB_R) D[d.d_off] = tsb_res_g(&P[d.p_off]);
+            else if (d.kind == TSB_L) tsb_ind_derive(&P[d.p_off], &D[d.d_off]);
             else if (d.kind == TSB_LCORE) D[d.d_off] = tsb_lcore_L0(&P[d.p_off]);
             else if (d.kind == TSB_M) tsb_mos_init_state(&P[d.p_off], &S[d.s_off]);
             else if (d.kind == TSB_K) {
@@ -286,7 +287,7 @@ int plan_finalize(Plan& pl) {
     static const int need_nodes[10] = {2, 2, 2, 2, 2, 2, 3, 4, 0, 2};
     static const int need_p[10] = {1, 1, 1, 1, 1, 3, 9, 29, 1, 3};
     pl.n_params = pl.n_state = pl.n_src = pl.n_derived = 0;
-    pl.has_nonlinear = pl.has_time_dependent = pl.has_bjt = false;
+    pl.has_nonlinear = pl.has_time_dependent = pl.has_bjt = pl.has_mutual = false;
     pl.nominal.clear();
     for (Dev& d : pl.devs) {
         if (d.kind < 0 || d.kind > 9) { pl.error = "bad device kind on " + d.name; return TSB_E_INVALID; }
@@ -315,10 +316,12 @@ int plan_finalize(Plan& pl) {
         d.n_state = state_size(d.kind); d.s_off = pl.n_state; pl.n_state += d.n_state;
         d.d_off = -1;
         if (d.kind == TSB_R || d.kind == TSB_LCORE) { d.d_off = pl.n_derived; pl.n_derived += 1; }
+        if (d.kind == TSB_L) { d.d_off = pl.n_derived; pl.n_derived += 3; }
         if (d.kind == TSB_K) { int m = (int)d.ip.size(); d.d_off = pl.n_derived; pl.n_derived += m * (m - 1) / 2; }
         if (d.nonlinear()) pl.has_nonlinear = true;
         if (d.time_dependent()) pl.has_time_dependent = true;
         if (d.kind == TSB_Q) pl.has_bjt = true;
+        if (d.kind == TSB_K) pl.has_mutual = true;
     }
     pl.stamps.assign(pl.devs.size(), {});
     for (size_t i = 0; i < pl.devs.size(); ++i) device_stamp_entries(pl, (int)i, pl.stamps[i]);
@@ -338,7 +341,7 @@ int plan_finalize(Plan& pl) {
     // ---- replay the reference's first operating point for the nominal instance ----------------
     Nominal nom(pl);
     nom.derive();
-    TsbEnv env{TSB_MODE_OP, 0.0, 0.0, 0.0};
+    TsbEnv env{TSB_MODE_OP, 0.0, 0.0, 0.0, 0.0};
     {   // SetupDevices' initial stamp (circuit.go:154-156): only its side effects on device state matter
         double o[64]; std::vector<double> big;
         for (int di : pl.stamp_order) {

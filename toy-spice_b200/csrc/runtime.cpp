@@ -47,11 +47,13 @@ struct TsbArgsHost {
     double* scratch;
     const double* sweep;
     int n_sweep;
+    int skip_linear_resolve;
 };
 
 struct KernelModule {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t optran = nullptr, dc = nullptr;
+    int info_regs = -1, info_spill = -1, min_blocks = 0;
 };
 
 struct tsb_ctx {
@@ -61,6 +63,7 @@ struct tsb_ctx {
     std::string err;
     std::string cache_dir;
     std::map<std::string, KernelModule> modules;      // key -> loaded module
+    std::map<std::string, int> auto_choice;            // key of the min_blocks=auto source -> chosen min blocks
     int64_t launches = 0;
 };
 
@@ -138,7 +141,12 @@ struct Nvrtc {
     int (*DestroyProgram)(void**) = nullptr;
     bool load(std::string& err) {
         if (h) return true;
-        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        // Absolute toolkit paths FIRST: inside a PyTorch process the bare soname resolves to torch's
+        // bundled NVRTC 12.8, whose sm_100a code for these kernels measured up to 8x slower than the
+        // 12.9 toolkit's (profiles/r01_notes.md).  $TSB_NVRTC overrides.
+        const char* env = getenv("TSB_NVRTC");
+        const char* names[] = {env && *env ? env : "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                               "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12", "libnvrtc.so"};
         for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (h) break; }
         if (!h) { err = "NVRTC not found (libnvrtc.so.12) and no cached cubin for this kernel"; return false; }
 #define SYM(f) *(void**)(&f) = dlsym(h, "nvrtc" #f); if (!f) { err = "nvrtc" #f " missing"; return false; }
@@ -156,21 +164,41 @@ std::string compile_options_string(const tsb_opts& o) {
     return s;
 }
 
-bool nvrtc_compile(const std::string& src, const std::string& name, const tsb_opts& o, std::vector<char>& cubin, std::string& err) {
+// ptxas -v figures of the transient kernel: what the launch-bounds auto-selection looks at.
+struct KernelInfo { int regs = -1, spill_st = -1, spill_ld = -1; };
+
+void parse_ptxas_log(const std::string& log, KernelInfo& info) {
+    size_t p = log.find("'tsb_optran'");
+    if (p == std::string::npos) return;
+    size_t s1 = log.find("bytes spill stores", p);
+    size_t u = log.find("Used ", p);
+    if (s1 != std::string::npos) {
+        size_t c = log.rfind(',', s1);
+        if (c != std::string::npos) info.spill_st = atoi(log.c_str() + c + 1);
+        size_t c2 = log.find(',', s1);
+        if (c2 != std::string::npos) info.spill_ld = atoi(log.c_str() + c2 + 1);
+    }
+    if (u != std::string::npos) info.regs = atoi(log.c_str() + u + 5);
+}
+
+bool nvrtc_compile(const std::string& src, const std::string& name, const tsb_opts& o, std::vector<char>& cubin,
+                   KernelInfo& info, std::string& err) {
     std::lock_guard<std::mutex> lk(g_nvrtc_mu);
     if (!g_nvrtc.load(err)) return false;
     void* prog = nullptr;
     if (g_nvrtc.CreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != 0) { err = "nvrtcCreateProgram failed"; return false; }
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", o.strict_fp ? "--fmad=false" : "--fmad=true"};
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", o.strict_fp ? "--fmad=false" : "--fmad=true",
+                                     "--ptxas-options=-v", "-diag-suppress=550"};
     int rc = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+    size_t n = 0; g_nvrtc.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0'); if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
     if (rc != 0) {
-        size_t n = 0; g_nvrtc.GetProgramLogSize(prog, &n);
-        std::string log(n, '\0'); if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
         err = "NVRTC compile failed:\n" + log.substr(0, 4000);
         g_nvrtc.DestroyProgram(&prog);
         return false;
     }
-    size_t n = 0; g_nvrtc.GetCUBINSize(prog, &n);
+    parse_ptxas_log(log, info);
+    n = 0; g_nvrtc.GetCUBINSize(prog, &n);
     cubin.resize(n);
     g_nvrtc.GetCUBIN(prog, cubin.data());
     g_nvrtc.DestroyProgram(&prog);
@@ -182,34 +210,88 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.varying = b->varying; cfg.var_slot = b->var_slot; cfg.n_var = (int)b->slot_ptr.size();
     cfg.block_size = o.block_size > 0 ? o.block_size : 128;
     cfg.dc_param = dc_param;
+    cfg.fast_div = !o.strict_fp;
+    cfg.min_blocks = o.min_blocks;            // 0 = "auto" placeholder (never compiled as such)
+    cfg.skip_linear = o.skip_linear_resolve != 0;
     return cfg;
 }
 
-int get_module(tsb_batch* b, const tsb_opts& o, int dc_param, KernelModule** out) {
+bool read_file(const std::string& path, std::vector<char>& out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    return !out.empty();
+}
+
+// cubin (+ ptxas figures) of one fully specified source: kernel cache first, NVRTC on a miss.
+int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, const tsb_opts& o, std::vector<char>& cubin, KernelInfo& info) {
+    const std::string base = ctx->cache_dir + "/" + key;
+    if (read_file(base + ".cubin", cubin)) {
+        std::ifstream f(base + ".info");
+        if (f) f >> info.regs >> info.spill_st >> info.spill_ld;
+        return TSB_OK;
+    }
+    std::string err;
+    mkdir(ctx->cache_dir.c_str(), 0755);
+    { std::ofstream f(base + ".cu"); f << src; }
+    if (!nvrtc_compile(src, base + ".cu", o, cubin, info, err)) return fail(ctx, TSB_E_COMPILE, err);
+    { std::ofstream f(base + ".cubin", std::ios::binary); f.write(cubin.data(), (std::streamsize)cubin.size()); }
+    { std::ofstream f(base + ".info"); f << info.regs << " " << info.spill_st << " " << info.spill_ld << "\n"; }
+    return TSB_OK;
+}
+
+// Launch bounds of the transient kernel.  One circuit per thread keeps everything in registers, so
+// occupancy is bought with the register cap: the kernels are latency-bound (dependent FP64 chains),
+// more resident warps help until the cap forces spills into the Newton loop.  Rule (measured on B200,
+// profiles/r01_notes.md): the largest min-blocks-per-SM in {4,3,2,1} whose ptxas report shows at most
+// TSB_SPILL_OK bytes of spill stores; __graft_entry__.build() applies the same rule with nvcc.
+const int TSB_SPILL_OK = 64;
+
+int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
     tsb_ctx* ctx = b->ctx;
-    std::string src = generate_source(b->plan->p, make_config(b, o, dc_param));
-    std::string key = source_key(src, compile_options_string(o));
+    std::vector<char> cubin;
+    KernelInfo info;
+    std::string src, key;
+    if (o.min_blocks <= 0) {
+        o.min_blocks = 0;
+        std::string autokey = source_key(generate_source(b->plan->p, make_config(b, o, dc_param)), compile_options_string(o));
+        auto ch = ctx->auto_choice.find(autokey);
+        int chosen = ch != ctx->auto_choice.end() ? ch->second : 0;
+        if (!chosen) {
+            std::ifstream f(ctx->cache_dir + "/" + autokey + ".auto");
+            if (f) f >> chosen;
+        }
+        if (chosen < 1 || chosen > 8) {
+            int best = 1, best_spill = 1 << 30;
+            for (int mb = 4; mb >= 1; --mb) {
+                o.min_blocks = mb;
+                src = generate_source(b->plan->p, make_config(b, o, dc_param));
+                key = source_key(src, compile_options_string(o));
+                KernelInfo ki;
+                int rc = obtain_cubin(ctx, src, key, o, cubin, ki);
+                if (rc != TSB_OK) return rc;
+                int sp = ki.spill_st < 0 ? 0 : ki.spill_st;
+                if (sp < best_spill) { best_spill = sp; best = mb; }
+                if (sp <= TSB_SPILL_OK) { best = mb; break; }
+            }
+            chosen = best;
+            std::ofstream f(ctx->cache_dir + "/" + autokey + ".auto");
+            f << chosen << "\n";
+        }
+        ctx->auto_choice[autokey] = chosen;
+        o.min_blocks = chosen;
+    }
+    src = generate_source(b->plan->p, make_config(b, o, dc_param));
+    key = source_key(src, compile_options_string(o));
     auto it = ctx->modules.find(key);
     if (it != ctx->modules.end()) { *out = &it->second; return TSB_OK; }
-    std::vector<char> cubin;
-    std::string path = ctx->cache_dir + "/" + key + ".cubin";
-    {
-        std::ifstream f(path, std::ios::binary);
-        if (f) cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    }
-    if (cubin.empty()) {
-        std::string err;
-        std::string srcname = ctx->cache_dir + "/" + key + ".cu";
-        mkdir(ctx->cache_dir.c_str(), 0755);
-        { std::ofstream f(srcname); f << src; }
-        if (!nvrtc_compile(src, srcname, o, cubin, err)) return fail(ctx, TSB_E_COMPILE, err);
-        std::ofstream f(path, std::ios::binary);
-        f.write(cubin.data(), (std::streamsize)cubin.size());
-    }
+    int rc = obtain_cubin(ctx, src, key, o, cubin, info);
+    if (rc != TSB_OK) return rc;
     KernelModule m;
     CU(ctx, cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     CU(ctx, cudaLibraryGetKernel(&m.optran, m.lib, "tsb_optran"));
     CU(ctx, cudaLibraryGetKernel(&m.dc, m.lib, "tsb_dc"));
+    m.info_regs = info.regs; m.info_spill = info.spill_st; m.min_blocks = o.min_blocks;
     ctx->modules[key] = m;
     *out = &ctx->modules[key];
     return TSB_OK;
@@ -240,9 +322,9 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     }
     if (!b->d_rows) CU(ctx, cudaMalloc(&b->d_rows, N * sizeof(long long)));
     if (!b->d_status) CU(ctx, cudaMalloc(&b->d_status, N * sizeof(int)));
-    if (!b->d_counters) CU(ctx, cudaMalloc(&b->d_counters, 6 * N * sizeof(long long)));
+    if (!b->d_counters) CU(ctx, cudaMalloc(&b->d_counters, 8 * N * sizeof(long long)));
     if (!b->d_scratch) CU(ctx, cudaMalloc(&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
-    if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 4 * sizeof(unsigned long long)));
+    if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 5 * sizeof(unsigned long long)));
     if (n_sweep > 0) { cudaFree(b->d_sweep); b->d_sweep = nullptr; CU(ctx, cudaMalloc(&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
     b->analysis = analysis; b->ncol = ncol; b->out_flags = out_flags; b->cap_rows = cap_rows;
     return TSB_OK;
@@ -276,10 +358,11 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     a.wave = b->d_wave; a.stats = b->d_stats; a.rows = b->d_rows; a.status = b->d_status;
     a.counters = b->d_counters; a.scratch = b->d_scratch;
     a.out_flags = b->out_flags; a.cap_rows = b->cap_rows;
+    a.skip_linear_resolve = o.skip_linear_resolve;
     return TSB_OK;
 }
 
-tsb_opts resolve(const tsb_opts* o) {
+tsb_opts resolve(const tsb_opts* o, const Plan& plan) {
     tsb_opts r; tsb_default_opts(&r);
     if (o) {
         r = *o;
@@ -287,7 +370,11 @@ tsb_opts resolve(const tsb_opts* o) {
         if (r.block_size <= 0) r.block_size = 128;
     }
     const char* env = getenv("TSB_STRICT_FP");
-    if (env && *env && *env != '0') r.strict_fp = 1;
+    if (env && *env) r.strict_fp = *env != '0';
+    // auto: circuits with mutual couplings have MNA matrices with condition numbers ~1e7-1e8 (the
+    // (1-k^2) L/dt block next to 1e-4 S conductances), where ANY re-association of the arithmetic is
+    // visible at the 1e-9 parity tolerance — they run in the reference-rounding build.
+    if (r.strict_fp < 0) r.strict_fp = plan.has_mutual ? 1 : 0;
     return r;
 }
 
@@ -305,7 +392,7 @@ extern "C" {
 void tsb_default_opts(tsb_opts* o) {
     if (!o) return;
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
-    o->strict_fp = 0; o->block_size = 128; o->reuse_lu = 0;
+    o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -562,7 +649,7 @@ int tsb_batch_set_param_uniform(tsb_batch* b, int dev, int param, double value) 
 int tsb_run_op(tsb_batch* b, const tsb_opts* opts) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
-    tsb_opts o = resolve(opts);
+    tsb_opts o = resolve(opts, b->plan->p);
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
@@ -580,7 +667,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     if (!(tstop > 0) || !(tstep > 0)) return fail(ctx, TSB_E_INVALID, "tstop and tstep must be positive");
     if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
     if ((out_flags & TSB_OUT_WAVE) && wave_cap_rows <= 0) return fail(ctx, TSB_E_INVALID, "wave_cap_rows must be positive");
-    tsb_opts o = resolve(opts);
+    tsb_opts o = resolve(opts, b->plan->p);
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
@@ -606,7 +693,7 @@ int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc,
     if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
     std::vector<double> sweep;
     for (double v = start; v <= stop; v += inc) { sweep.push_back(v); if (sweep.size() > (1u << 24)) break; }   // dc.go:36-42
-    tsb_opts o = resolve(opts);
+    tsb_opts o = resolve(opts, b->plan->p);
     CU(ctx, cudaSetDevice(ctx->device));
     const Dev& sd = p.devs[src_dev];
     int st = sd.src_type();
@@ -656,7 +743,7 @@ static int d2h(tsb_batch* b, void* dst, const void* src, size_t bytes) {
 }
 int tsb_result_rows(tsb_batch* b, int64_t* rows) { return b && rows ? d2h(b, rows, b->d_rows, b->n_inst * sizeof(long long)) : TSB_E_INVALID; }
 int tsb_result_status(tsb_batch* b, int32_t* status) { return b && status ? d2h(b, status, b->d_status, b->n_inst * sizeof(int)) : TSB_E_INVALID; }
-int tsb_result_counters(tsb_batch* b, int64_t* counters) { return b && counters ? d2h(b, counters, b->d_counters, 6 * b->n_inst * sizeof(long long)) : TSB_E_INVALID; }
+int tsb_result_counters(tsb_batch* b, int64_t* counters) { return b && counters ? d2h(b, counters, b->d_counters, 8 * b->n_inst * sizeof(long long)) : TSB_E_INVALID; }
 int tsb_result_wave_all(tsb_batch* b, double* out, int64_t n_doubles) {
     if (!b || !out) return TSB_E_INVALID;
     if ((size_t)n_doubles * sizeof(double) < b->wave_bytes) return fail(b->ctx, TSB_E_INVALID, "output buffer too small");
@@ -682,25 +769,25 @@ int tsb_result_waveform(tsb_batch* b, int64_t inst, double* out, int64_t cap_row
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return TSB_OK;
 }
-int tsb_result_totals(tsb_batch* b, int64_t totals[4]) {
+int tsb_result_totals(tsb_batch* b, int64_t totals[5]) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
     if (!totals || !b->d_counters) return TSB_E_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMemsetAsync(b->d_totals, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaMemsetAsync(b->d_totals, 0, 5 * sizeof(unsigned long long), ctx->stream));
     CU(ctx, launch_totals(b->d_counters, b->n_inst, b->d_totals, ctx->sms, ctx->stream));
     ++ctx->launches;
-    unsigned long long h[4];
+    unsigned long long h[5];
     CU(ctx, cudaMemcpyAsync(h, b->d_totals, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < 4; ++k) totals[k] = (int64_t)h[k];
+    for (int k = 0; k < 5; ++k) totals[k] = (int64_t)h[k];
     return TSB_OK;
 }
 
 // ---- introspection -------------------------------------------------------------------------------
 int tsb_batch_kernel_source(tsb_batch* b, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed) {
     if (!b) return TSB_E_INVALID;
-    tsb_opts o = resolve(opts);
+    tsb_opts o = resolve(opts, b->plan->p);
     std::string src = generate_source(b->plan->p, make_config(b, o, -1));
     if (needed) *needed = (int64_t)src.size() + 1;
     if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", src.c_str()); }
@@ -708,7 +795,7 @@ int tsb_batch_kernel_source(tsb_batch* b, const tsb_opts* opts, char* buf, int64
 }
 int tsb_batch_kernel_key(tsb_batch* b, const tsb_opts* opts, char* buf, int cap) {
     if (!b || !buf || cap < 33) return TSB_E_INVALID;
-    tsb_opts o = resolve(opts);
+    tsb_opts o = resolve(opts, b->plan->p);
     std::string src = generate_source(b->plan->p, make_config(b, o, -1));
     snprintf(buf, cap, "%s", source_key(src, compile_options_string(o)).c_str());
     return TSB_OK;

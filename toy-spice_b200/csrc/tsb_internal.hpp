@@ -86,7 +86,7 @@ struct Plan {
     PivotOrder order_main, order_init;
     LuProgram lu_main, lu_init;
     bool init_struct_singular = false;
-    bool has_nonlinear = false, has_time_dependent = false, has_bjt = false;
+    bool has_nonlinear = false, has_time_dependent = false, has_bjt = false, has_mutual = false;
     std::string error;
 
     int n() const { return n_nodes + n_branches; }
@@ -107,6 +107,9 @@ struct CodegenConfig {
     int n_var = 0;
     int block_size = 128;
     int dc_param = -1;              // flat parameter index overwritten by the DC sweep value
+    bool fast_div = false;          // TSB_FAST_DIV build (non-strict): see device/models.cuh
+    int min_blocks = 1;             // __launch_bounds__ second argument of the transient kernel
+    bool skip_linear = true;        // compile the redundant second linear solve away
 };
 std::string generate_source(const Plan& plan, const CodegenConfig& cfg);
 
