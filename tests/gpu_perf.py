@@ -25,8 +25,8 @@ def main():
     ov = PU.draws(deck, ckt, n)
     dev = {k: torch.from_numpy(v).cuda() for k, v in ov.items()}
     card = ckt.analysis_card()
-    grid = []
-    for strict, skip, mb, bs in itertools.product((0, 1), (1, 0), (1, 3, 4, 5, 6), (64, 128, 256)):
+    grid = [(-1, 1, 0, 128)]        # library defaults: strict=auto, launch bounds=auto
+    for strict, skip, mb, bs in itertools.product((0, 1), (1, 0), (1, 2, 3, 4, 5, 6), (64, 128, 256)):
         if bs != 128 and (mb not in (1, 4)):
             continue
         if strict and (skip == 0 or bs != 128):

@@ -305,8 +305,11 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
 
     // ---- Newton body ----------------------------------------------------------------------------
     e.line("// mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin); mat.Solve()  ->  x");
-    e.line("__device__ __forceinline__ bool assemble_solve(int mode, double time, double dt, double rdt, double gmin) {");
+    e.line("// MODE >= 0 fixes the analysis mode at compile time (the dedicated transient loop): mode selects fold away.");
+    e.line("template <int MODE>");
+    e.line("__device__ __forceinline__ bool assemble_solve(int mode_rt, double time, double dt, double rdt, double gmin) {");
     ++e.ind;
+    e.line("const int mode = MODE >= 0 ? MODE : mode_rt;");
     e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin; e.rdt = rdt;");
     e.line("double A[" + std::to_string(pl.lu_main.pos.size()) + "];");
     e.line("double b[" + std::to_string(n + 1) + "];");

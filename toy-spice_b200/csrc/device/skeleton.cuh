@@ -134,10 +134,65 @@ struct TsbSink {
 };
 
 // ------------------------------------------------------------------------------------------------
+// An accepted transient step (tran.go:137-151): LoadState, Update, advance time, StoreTimeResult with its
+// formatted-time de-duplication (anlysis.go:61-85; `last_key` < 0 = nothing stored yet), step growth.
+template <class Ckt, class Sink>
+__device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& sink, double& time, double& dt,
+                                                double next_time, double lte, long long& last_key) {
+    c.load_state(dt);
+    c.update_state();
+    time = next_time;
+    if (time >= a.tstart) {
+        long long key = tsb_time_key(time);       // equal times give equal keys, so one comparison covers both tests
+        if (key != last_key) {
+            double row[Ckt::NCOL_MAX];
+            row[0] = time;
+            c.signals(row + 1);
+            sink.push(row);
+            last_key = key;
+        }
+    }
+    if (time < a.tstop && dt < a.maxstep) {
+        if (lte < a.trtol / 100) dt = fmin(dt * 2, a.maxstep);
+        else dt = fmin(dt * 1.1, a.maxstep);
+    }
+}
+
+// Transient loop of a circuit WITHOUT nonlinear devices when the redundant second solve is compiled
+// away: one stamp+factor+solve per step attempt, no Newton state machine, analysis mode fixed at compile
+// time (mode selects, the LoadGmin branch and the dt > 0 guards fold away).  Same statements as
+// tran.go:96-151 / 157-216 with iter = 0, 1 collapsed.
+template <class Ckt, class Sink>
+__device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& sink, long long& n_acc, long long& n_rej,
+                                                long long& n_sol_tran, long long& n_exec, int& status, double& fail_at) {
+    double time = 0.0, dt = a.minstep;
+    long long last_key = -1;
+    while (time < a.tstop) {
+        double next_time = time + dt;
+        if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+        c.eval_sources(time, 1.0);
+        const double rdt = 1.0 / dt;
+        const bool solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+        ++n_exec;
+        n_sol_tran += solved ? 2 : 1;              // the reference stops at the failing solve, else runs two
+        if (!solved) {
+            if (dt > a.minstep) { dt /= 2; ++n_rej; continue; }
+            status = TSB_ST_TRAN_FAILED; fail_at = time;
+            return;
+        }
+        const double lte = c.lte(dt, rdt);
+        if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
+        tsb_accept_step(a, c, sink, time, dt, next_time, lte, last_key);
+        ++n_acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Operating point + transient (analysis == TSB_AN_OP stops after the first operating point).
 template <class Ckt>
 __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long long inst) {
     constexpr int N = Ckt::N;
+    constexpr bool LINEAR_LOOP = !Ckt::HAS_NL && (TSB_SKIP_LINEAR_RESOLVE != 0);
     Ckt c;
     c.load(a, inst);
     c.init();
@@ -154,10 +209,10 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     int op_pass = 0, cont = C_MAIN, iter = 0, mode = TSB_MODE_OP, gstep = 0;
     double gmin = 0.0, sfac = 0.0, status_dt = 0.0;
     double time = 0.0, dt = a.minstep, next_time = 0.0, rdt = 0.0;
-    bool have_last = false;
-    double last_time = 0.0;
-    long long last_key = 0;
+    long long last_key = -1;
+    bool linear_tran = false;                  // hand the transient over to tsb_tran_linear
     if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
+    if (LINEAR_LOOP && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
 
     while (phase != PH_DONE) {
         if (phase == PH_OP_START) {
@@ -170,7 +225,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
                 for (int i = 1; i <= N; ++i) c.xo[i] = 0.0;
             }
             gmin = 0.0; cont = C_MAIN; iter = 0; mode = TSB_MODE_OP; phase = PH_NR;
-        } else if (phase == PH_TRAN_BEGIN) {
+        } else if (!LINEAR_LOOP && phase == PH_TRAN_BEGIN) {
             // top of the `for tr.time < tr.stopTime` loop (tran.go:96-111)
             next_time = time + dt;
             if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
@@ -182,7 +237,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         // ---------------- one Newton iteration (op.go:45-86, tran.go:172-213) -------------------
         if (Ckt::HAS_NL && (mode == TSB_MODE_OP || iter > 0)) c.update_nl(c.xo);
         const bool is_tran = mode == TSB_MODE_TRAN;
-        bool solved = c.assemble_solve(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
+        bool solved = c.template assemble_solve<-1>(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
         if (is_tran) ++n_sol_tran; else ++n_sol_op;
         ++n_exec;
         bool conv = false, fail = !solved;
@@ -254,6 +309,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             if (conv) op_done = true; else op_failed = true;
             break;
         case C_TRAN:
+            if (LINEAR_LOOP) break;               // linear circuits run their transient in tsb_tran_linear
             if (fail) {
                 // tran.go:113-120
                 if (dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; }
@@ -263,24 +319,8 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             {
                 double lte = c.lte(dt, rdt);                      // tran.go:122, 239-250
                 if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; break; }
-                c.load_state(dt);                                 // tran.go:137-138
-                c.update_state();
-                time = next_time;
+                tsb_accept_step(a, c, sink, time, dt, next_time, lte, last_key);
                 ++n_acc;
-                if (time >= a.tstart) {                           // StoreTimeResult, anlysis.go:61-85
-                    long long key = tsb_time_key(time);
-                    if (!have_last || !(time == last_time || key == last_key)) {
-                        double row[Ckt::NCOL_MAX];
-                        row[0] = time;
-                        c.signals(row + 1);
-                        sink.push(row);
-                        have_last = true; last_time = time; last_key = key;
-                    }
-                }
-                if (time < a.tstop && dt < a.maxstep) {           // tran.go:145-151
-                    if (lte < a.trtol / 100) dt = fmin(dt * 2, a.maxstep);
-                    else dt = fmin(dt * 1.1, a.maxstep);
-                }
                 phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
             }
             break;
@@ -307,9 +347,11 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             } else {
                 time = 0.0; dt = a.minstep;                        // tran.go:93
                 phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
+                if (LINEAR_LOOP) { linear_tran = true; phase = PH_DONE; }
             }
         }
     }
+    if (LINEAR_LOOP && linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
 
     if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
     if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish();
@@ -340,7 +382,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     if (a.n_sweep > 0) { c.set_dc(a.sweep[0]); c.eval_sources(0.0, 1.0); }
     while (k < a.n_sweep) {
         if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
-        bool solved = c.assemble_solve(TSB_MODE_OP, 0.0, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
+        bool solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
         if (iter < 0) { iter = 0; continue; }
         ++n_sol;
         bool conv = false, fail = !solved;

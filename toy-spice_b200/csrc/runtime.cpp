@@ -245,7 +245,8 @@ int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, c
 // more resident warps help until the cap forces spills into the Newton loop.  Rule (measured on B200,
 // profiles/r01_notes.md): the largest min-blocks-per-SM in {4,3,2,1} whose ptxas report shows at most
 // TSB_SPILL_OK bytes of spill stores; __graft_entry__.build() applies the same rule with nvcc.
-const int TSB_SPILL_OK = 64;
+const int TSB_SPILL_OK = 100;
+const int TSB_MAX_MIN_BLOCKS = 6;
 
 int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
     tsb_ctx* ctx = b->ctx;
@@ -263,7 +264,7 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
         }
         if (chosen < 1 || chosen > 8) {
             int best = 1, best_spill = 1 << 30;
-            for (int mb = 4; mb >= 1; --mb) {
+            for (int mb = TSB_MAX_MIN_BLOCKS; mb >= 1; --mb) {
                 o.min_blocks = mb;
                 src = generate_source(b->plan->p, make_config(b, o, dc_param));
                 key = source_key(src, compile_options_string(o));
