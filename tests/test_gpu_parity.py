@@ -93,17 +93,21 @@ def test_strict_mode_is_bitwise_for_rc(ctx):
 @pytest.mark.parametrize("name", ["rc", "rlc", "transformer2"])
 def test_skipping_the_redundant_linear_solve_changes_no_bit(ctx, name):
     """Linear circuits: the reference's second Newton solve per step re-stamps identical values.  Executing it
-    (skip_linear_resolve=0) or not (default) must give bit-identical waveforms and identical counters."""
+    (skip_linear_resolve=0) or not (default) must give bit-identical waveforms and identical reference-equivalent
+    counters.  Checked in the reference-rounding build: in the fast build the two variants are different
+    translation units and nvcc is free to contract multiply-adds differently."""
     text = T.BUNDLED[name]
     n = 32
     ov = PU.draws(name, T.Circuit.from_netlist(text), n)
     waves, counters = [], []
     for skip in (1, 0):
-        ckt, b, _ = PU.run_gpu(ctx, text, n, ov, cap_rows=12288, opts=T.default_opts(skip_linear_resolve=skip))
+        ckt, b, _ = PU.run_gpu(ctx, text, n, ov, cap_rows=12288, opts=T.default_opts(skip_linear_resolve=skip, strict_fp=1))
         waves.append(b.wave_all())
         counters.append(b.counters())
     assert np.array_equal(waves[0], waves[1], equal_nan=True)
-    assert np.array_equal(counters[0], counters[1])
+    assert np.array_equal(counters[0][:6], counters[1][:6])
+    # executed passes: the skipping build runs one pass where the reference runs two
+    assert np.all(counters[0][6] < counters[1][6])
 
 
 def test_nvrtc_runtime_specialisation(ctx, built):
