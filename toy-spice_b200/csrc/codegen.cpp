@@ -112,6 +112,7 @@ void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_on
 // pivots; back-substitution in ascending column order), so --fmad=false reproduces its rounding.
 void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string& xout) {
     const int n = lu.n;
+    if (!lu.dense) e.line("bool lu_ok = true;");
     if (load_gmin) {
         e.line("if (gmin != 0.0) {   // LoadGmin: added to the pivot positions (Diags[i] after reordering, SURVEY Q17)");
         ++e.ind;
@@ -123,7 +124,11 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
         const LuProgram::Step& st = lu.steps[k];
         std::string piv = "A[" + std::to_string(st.piv) + "]";
         e.line("// step " + std::to_string(k) + ": pivot (" + std::to_string(lu.prow[k]) + "," + std::to_string(lu.pcol[k]) + ")");
-        e.line("if (" + piv + " == 0.0) return false;");
+        // zero pivot = the reference's "matrix factorization failed".  Sparse builds test all pivots with ONE
+        // branch after the elimination (a zero pivot only produces Inf/NaN in values that are then discarded);
+        // the dense (BJT) build returns at once, as the reference does.
+        if (lu.dense) e.line("if (" + piv + " == 0.0) return false;");
+        else e.line("lu_ok = lu_ok & (" + piv + " != 0.0);");
         e.line(piv + " = " + std::string(lu.dense ? "1.0 / " + piv : "tsb_rcp(" + piv + ")") + ";");
         for (size_t ui = 0; ui < st.urow.size(); ++ui) {
             std::string u = "A[" + std::to_string(st.urow[ui]) + "]";
@@ -132,6 +137,7 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
                 e.line("A[" + std::to_string(st.target[ui][li]) + "] -= " + u + " * A[" + std::to_string(st.lcol[li]) + "];");
         }
     }
+    if (!lu.dense) e.line("if (!lu_ok) return false;");
     e.line("double c[" + std::to_string(n + 1) + "];");
     for (int k = 1; k <= n; ++k) e.line("c[" + std::to_string(k) + "] = b[" + std::to_string(lu.prow[k]) + "];");
     for (int k = 1; k <= n; ++k) {

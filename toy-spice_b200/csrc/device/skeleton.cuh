@@ -90,16 +90,16 @@ struct TsbSink {
     long long inst;
     long long n_rows;
     bool overflow;
-    double* sm;                 // this thread's first stats word; stride blockDim.x between words
+    double* sm;                 // this thread's first stats word; words are TSB_BLOCK doubles apart (conflict-free)
     __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false) {
-        sm = tsb_smem + threadIdx.x;
+        sm = tsb_smem + threadIdx.x;          // launched with blockDim.x == TSB_BLOCK: every offset below is an immediate
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
-                sm[(0 * NCOL + j) * blockDim.x] = __longlong_as_double(0x7ff0000000000000LL);    // +inf
-                sm[(1 * NCOL + j) * blockDim.x] = __longlong_as_double(0xfff0000000000000LL);    // -inf
-                sm[(2 * NCOL + j) * blockDim.x] = 0.0;
-                sm[(3 * NCOL + j) * blockDim.x] = 0.0;
+                sm[(0 * NCOL + j) * TSB_BLOCK] = __longlong_as_double(0x7ff0000000000000LL);    // +inf
+                sm[(1 * NCOL + j) * TSB_BLOCK] = __longlong_as_double(0xfff0000000000000LL);    // -inf
+                sm[(2 * NCOL + j) * TSB_BLOCK] = 0.0;
+                sm[(3 * NCOL + j) * TSB_BLOCK] = 0.0;
             }
         }
     }
@@ -114,12 +114,15 @@ struct TsbSink {
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
-                double v = row[j];
-                double* s = sm + j * blockDim.x;
-                s[0] = fmin(s[0], v);
-                s[(1 * NCOL) * blockDim.x] = fmax(s[(1 * NCOL) * blockDim.x], v);
-                s[(2 * NCOL) * blockDim.x] += v;
-                s[(3 * NCOL) * blockDim.x] = v;
+                const double v = row[j];
+                double* s = sm + j * TSB_BLOCK;
+                // running min / max that ignore NaN samples (the accumulators start at +-inf and can never
+                // become NaN themselves), i.e. fmin / fmax semantics without their NaN fix-up code
+                const double mn = s[0], mx = s[(1 * NCOL) * TSB_BLOCK];
+                s[0] = v < mn ? v : mn;
+                s[(1 * NCOL) * TSB_BLOCK] = v > mx ? v : mx;
+                s[(2 * NCOL) * TSB_BLOCK] += v;
+                s[(3 * NCOL) * TSB_BLOCK] = v;
             }
         }
         ++n_rows;
@@ -127,7 +130,7 @@ struct TsbSink {
     __device__ __forceinline__ void finish() {
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
-            for (int k = 0; k < 4 * NCOL; ++k) a.stats[(long long)k * a.n_inst + inst] = sm[k * blockDim.x];
+            for (int k = 0; k < 4 * NCOL; ++k) a.stats[(long long)k * a.n_inst + inst] = sm[k * TSB_BLOCK];
         }
         a.rows[inst] = n_rows;
     }
