@@ -373,8 +373,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         for (int b = pl.n_nodes + 1; b <= n; ++b) e.line("out[" + std::to_string(k++) + "] = -x[" + std::to_string(b) + "];");
         for (const Dev& d : pl.devs)
             if (d.kind == TSB_R)
-                e.line("out[" + std::to_string(k++) + "] = (x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "]) " +
-                       (cfg.fast_div ? "* D[" + std::to_string(d.d_off) + "]" : "/ P[" + std::to_string(d.p_off) + "]") + ";   // I(" + d.name + ")");
+                e.line("out[" + std::to_string(k++) + "] = tsb_div_by(x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "], P[" + std::to_string(d.p_off) + "], D[" + std::to_string(d.d_off) + "]);   // I(" + d.name + ") = (v1 - v2) / R");
     }
     --e.ind;
     e.line("}");
