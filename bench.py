@@ -48,6 +48,14 @@ def f_lu_dense(n: int) -> int:
 STAMP_FLOPS = {0: 5, 1: 8, 2: 9, 3: 5, 4: 2, 5: 30, 6: 90, 7: 80, 8: 12, 9: 9}   # per device kind (adds into A/b + model arithmetic)
 
 
+def ncu_traffic(deck: str, n: int, mode: str):
+    """DRAM bytes per launch of this kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{deck}:{n}:{mode}")
+    except Exception:
+        return None
+
+
 def flops_per_solve(ckt) -> dict:
     n = ckt.n
     stamp = sum(STAMP_FLOPS[d["kind"]] for d in ckt.devices())
@@ -320,11 +328,47 @@ def main():
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": "tsb_optran (rlc.cir)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_traffic(dom["name"], n, "stats"),
         "peak_source": "DFMA-chain microbenchmark measured in this run (tsb_ctx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_solve": dom["flops"], "executed_solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
         "algorithmic_hbm_bytes_per_launch": n * (8 * 3 + 4 * dom["ncol"] * 8 + 8 + 4 + 6 * 8),
     }
+
+    # ---- the HBM-bound regime of the same kernel: rc.cir with every stored row materialised --------------
+    # (8*O bytes per stored row; not part of `value`, reported beside the FP64 roofline)
+    roofline_hbm = None
+    try:
+        rc = decks[0]
+        c = rc["card"]
+        cap = 320
+        bw = rc["ckt"].batch(n)
+        for (d, p), v in rc["dev"].items():
+            bw.set_param(d, p, v)
+        ms_w = []
+        for i in range(4):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            bw.run_tran(c["tstart"], c["tstop"], c["tstep"], c["tmax"], c["uic"], out=T.OUT_WAVE, cap_rows=cap, opts=opts)
+            e1.record(stream)
+            stream.synchronize()
+            if i > 0:
+                ms_w.append(e0.elapsed_time(e1))
+        rows_total = int(bw.totals()[0])                    # rc stores every accepted step (305 rows per instance)
+        alg_bytes = rows_total * rc["ncol"] * 8 + n * (2 * 8 + 8 + 4 + 8 * 8)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            hbm_peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        ach = alg_bytes / (min(ms_w) * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "kernel": "tsb_optran (rc.cir, TSB_OUT_WAVE)", "achieved": ach, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": src,
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": min(ms_w),
+                        "circuit_timesteps_per_sec": rows_total / (min(ms_w) * 1e-3)}
+        del bw
+    except Exception as ex:       # the FP64-bound headline must not depend on this extra measurement
+        roofline_hbm = {"error": str(ex)[:200]}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None
@@ -347,7 +391,7 @@ def main():
             "executed_solves_per_step": exec_job,
             "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world},
             "gpu_launches": int(launches), "failed_instances": bad_status,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

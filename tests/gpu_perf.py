@@ -2,6 +2,7 @@
 variants (precision mode, launch bounds, block size, redundant-solve skipping).
 Usage: python tests/gpu_perf.py [deck] [instances]"""
 import itertools
+import os
 import sys
 import time
 
@@ -33,6 +34,8 @@ def main():
             continue
         grid.append((strict, skip, mb, bs))
     ref_stats = None
+    out_mode = T.OUT_WAVE if os.environ.get("TSB_PERF_OUT") == "wave" else T.OUT_STATS
+    cap = int(os.environ.get("TSB_PERF_CAP", "320"))
     for strict, skip, mb, bs in grid:
         tag = f"strict={strict} skip={skip} minblk={mb} block={bs}"
         if variants and not any(v in tag for v in variants):
@@ -43,22 +46,26 @@ def main():
         opts = T.default_opts(strict_fp=strict, skip_linear_resolve=skip, min_blocks=mb, block_size=bs)
         try:
             t0 = time.time()
-            b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=opts)
+            b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=out_mode, cap_rows=cap, opts=opts)
             b.sync()
             t_first = time.time() - t0
             ms = []
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=opts)
+                b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=out_mode, cap_rows=cap, opts=opts)
                 e1.record(stream)
                 stream.synchronize()
                 ms.append(e0.elapsed_time(e1))
             tot = b.totals()
-            s = b.stats_all()
-            if ref_stats is None:
-                ref_stats = s
-            dev_max = float(np.nanmax(np.abs(s - ref_stats) / (1e-9 * np.abs(ref_stats) + 1e-12)))
+            if out_mode == T.OUT_STATS:
+                s = b.stats_all()
+                if ref_stats is None:
+                    ref_stats = s
+                dev_max = float(np.nanmax(np.abs(s - ref_stats) / (1e-9 * np.abs(ref_stats) + 1e-12)))
+            else:
+                nb = int(b.rows().sum()) * b.dims()[1] * 8
+                dev_max = nb / (min(ms) * 1e-3) / 1e9        # GB/s of waveform written
             print(f"{deck} n={n} {tag:45s} {min(ms):9.2f} ms  steps/s={tot[0] / (min(ms) * 1e-3):.3e}  first={t_first:.2f}s  "
                   f"dev_vs_first={dev_max:.3g}", flush=True)
         except T.TsbError as e:
