@@ -141,12 +141,12 @@ struct TsbSink {
 // formatted-time de-duplication (anlysis.go:61-85; `last_key` < 0 = nothing stored yet), step growth.
 template <class Ckt, class Sink>
 __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& sink, double& time, double& dt,
-                                                double next_time, double lte, long long& last_key) {
+                                                double next_time, double lte, TsbTimeKeyer& keyer, double& last_key) {
     c.load_state(dt);
     c.update_state();
     time = next_time;
     if (time >= a.tstart) {
-        long long key = tsb_time_key(time);       // equal times give equal keys, so one comparison covers both tests
+        double key = keyer.key(time);             // equal times give equal keys, so one comparison covers both tests
         if (key != last_key) {
             double row[Ckt::NCOL_MAX];
             row[0] = time;
@@ -169,11 +169,13 @@ template <class Ckt, class Sink>
 __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& sink, long long& n_acc, long long& n_rej,
                                                 long long& n_sol_tran, long long& n_exec, int& status, double& fail_at) {
     double time = 0.0, dt = a.minstep;
-    long long last_key = -1;
+    double last_key = -1.0;
+    TsbTimeKeyer keyer; keyer.reset();
     while (time < a.tstop) {
         double next_time = time + dt;
         if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
         c.eval_sources(time, 1.0);
+        __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
         const double rdt = 1.0 / dt;
         const bool solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
         ++n_exec;
@@ -185,7 +187,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
         }
         const double lte = c.lte(dt, rdt);
         if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
-        tsb_accept_step(a, c, sink, time, dt, next_time, lte, last_key);
+        tsb_accept_step(a, c, sink, time, dt, next_time, lte, keyer, last_key);
         ++n_acc;
     }
 }
@@ -212,7 +214,8 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     int op_pass = 0, cont = C_MAIN, iter = 0, mode = TSB_MODE_OP, gstep = 0;
     double gmin = 0.0, sfac = 0.0, status_dt = 0.0;
     double time = 0.0, dt = a.minstep, next_time = 0.0, rdt = 0.0;
-    long long last_key = -1;
+    double last_key = -1.0;
+    TsbTimeKeyer keyer; keyer.reset();
     bool linear_tran = false;                  // hand the transient over to tsb_tran_linear
     if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
     if (LINEAR_LOOP && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
@@ -322,7 +325,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             {
                 double lte = c.lte(dt, rdt);                      // tran.go:122, 239-250
                 if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; break; }
-                tsb_accept_step(a, c, sink, time, dt, next_time, lte, last_key);
+                tsb_accept_step(a, c, sink, time, dt, next_time, lte, keyer, last_key);
                 ++n_acc;
                 phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
             }
