@@ -83,11 +83,14 @@ def test_rr_plumbing_batch_of_one(ctx):
     assert int(tr.batch.counters()[0, 0]) == 38 and int(tr.batch.counters()[2, 0]) == 76
 
 
-def test_strict_mode_is_bitwise_for_rc(ctx):
-    """With --fmad=false and the same pivot order the GPU reproduces the oracle's rounding on rc.cir
-    except for the source term (CUDA sin vs the restated Go sin): V(2) agrees to a few ulp."""
-    rep, batch, ores = _parity(ctx, "rc", 32, 1, cap=320)
-    assert rep["row_mismatch"] == 0 and rep["max_abs"] < 5e-15
+@pytest.mark.parametrize("name", ["rc", "rl", "rlc", "isin", "ipulse", "rr"])
+def test_strict_build_is_bit_identical_on_linear_decks(ctx, name):
+    """The reference-rounding build (no FMA contraction, IEEE-exact quotients, restated Go math.Sin, the oracle's
+    pivot order) reproduces the CPU oracle BIT FOR BIT on the linear decks whose instances keep the nominal pivot
+    order: every stored value of every instance, not just within tolerance."""
+    rep, batch, ores = _parity(ctx, name, 48, 1)
+    assert rep["row_mismatch"] == 0 and rep["status_mismatch"] == 0 and rep["counter_mismatch"] == 0
+    assert rep["compared_points"] > 0 and rep["max_abs"] == 0.0, rep
 
 
 @pytest.mark.parametrize("name", ["rc", "rlc", "transformer2"])
