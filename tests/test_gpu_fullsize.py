@@ -123,3 +123,19 @@ def test_config4_transformers(ctx, name, n_log2):
     # (min, max, last; the sum differs with the number of stored rows only through rounding as well)
     for stat in (0, 1, 3):
         assert np.allclose(s[stat, 1, :], s[stat, 1, 0], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["diode2", "bjt2", "mosfet1"])
+def test_lane_refill_is_bit_identical_to_static_mapping(ctx, name):
+    """tsb_opts.lane_refill: finished lanes of a resident grid take the next unprocessed instance from a work
+    counter.  Instances are independent, so the result of every instance must not depend on which lane ran it:
+    2^19 instances (several times the resident grid) with refill vs. one thread per instance, bit for bit."""
+    n = 1 << 19
+    ov = PU.draws(name, T.Circuit.from_netlist(T.BUNDLED[name]), n)
+    res = []
+    for refill in (1, 0):
+        _, b, _ = PU.run_gpu(ctx, T.BUNDLED[name], n, ov, out=T.OUT_STATS, opts=T.default_opts(lane_refill=refill))
+        res.append((b.stats_all(), b.rows(), b.status(), b.counters()))
+        del b
+    for x, y in zip(*res):
+        assert np.array_equal(x, y, equal_nan=True), name

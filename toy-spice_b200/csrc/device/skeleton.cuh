@@ -40,7 +40,9 @@ struct TsbArgs {
     double* scratch;           // [N+1][n_inst]  "currentSolution" of the OP fallbacks
     const double* sweep;       // [n_sweep] DC sweep values
     int n_sweep;
-    int skip_linear_resolve;   // linear circuits: do not execute the second, bit-identical Newton solve
+    int skip_linear_resolve;   // (compile-time TSB_SKIP_LINEAR_RESOLVE decides; kept for layout stability)
+    unsigned long long* work_counter;   // lane refill: next unprocessed instance = first_free + atomicAdd(counter, 1)
+    long long first_free;
 };
 
 #define TSB_ST_OK 0
@@ -93,6 +95,9 @@ struct TsbSink {
     double* sm;                 // this thread's first stats word; words are TSB_BLOCK doubles apart (conflict-free)
     __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false) {
         sm = tsb_smem + threadIdx.x;          // launched with blockDim.x == TSB_BLOCK: every offset below is an immediate
+    }
+    __device__ __forceinline__ void begin(long long inst_) {      // (re)start for one instance
+        inst = inst_; n_rows = 0; overflow = false;
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
@@ -198,29 +203,71 @@ template <class Ckt>
 __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long long inst) {
     constexpr int N = Ckt::N;
     constexpr bool LINEAR_LOOP = !Ckt::HAS_NL && (TSB_SKIP_LINEAR_RESOLVE != 0);
+    // Lane refill (the "compaction of finished lanes" of the north star): lanes of a NONLINEAR circuit finish
+    // at different trips (Newton counts differ, some lanes fail early).  Instead of idling until the slowest
+    // lane of the warp is done, a finished lane writes its results, takes the next unprocessed instance from a
+    // global counter and re-enters the SAME loop, so every trip keeps doing useful work in every lane.  Linear
+    // circuits have identical step sequences in every lane of the bundled sweeps and keep the static mapping.
+    // Compile-time option (tsb_opts.lane_refill -> TSB_LANE_REFILL): a de-synchronised warp executes the
+    // phase-specific code (OP start, initial estimate, accept) once per distinct phase, so on sweeps whose lanes
+    // all take similar trip counts refill LOSES 3-17 % (profiles/r01_notes.md) and is off by default.
+    constexpr bool REFILL = Ckt::HAS_NL && (TSB_LANE_REFILL != 0);
     Ckt c;
-    c.load(a, inst);
-    c.init();
     TsbSink<Ckt::NCOL_MAX> sink(a, inst);   // NCOL_MAX = transient column count (>= OP column count)
 
-    long long n_acc = 0, n_rej = 0, n_sol_tran = 0, n_sol_op = 0;   // as the reference would count them
-    long long n_exec = 0;                                            // factor+solve passes actually executed
-    int op_path = 0, status = TSB_ST_OK;
-    double fail_at = 0.0;
+    long long n_acc, n_rej, n_sol_tran, n_sol_op;   // as the reference would count them
+    long long n_exec;                               // factor+solve passes actually executed
+    int op_path, status;
+    double fail_at;
 
     enum { PH_OP_START, PH_TRAN_BEGIN, PH_NR, PH_DONE };
     enum { C_MAIN, C_GMIN, C_GFINAL, C_SRC, C_SFINAL, C_TRAN };
-    int phase = (a.analysis == TSB_AN_TRAN && a.uic) ? PH_TRAN_BEGIN : PH_OP_START;
-    int op_pass = 0, cont = C_MAIN, iter = 0, mode = TSB_MODE_OP, gstep = 0;
-    double gmin = 0.0, sfac = 0.0, status_dt = 0.0;
-    double time = 0.0, dt = a.minstep, next_time = 0.0, rdt = 0.0;
-    double last_key = -1.0;
-    TsbTimeKeyer keyer; keyer.reset();
-    bool linear_tran = false;                  // hand the transient over to tsb_tran_linear
-    if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
-    if (LINEAR_LOOP && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
+    int phase, op_pass, cont, iter, mode, gstep;
+    double gmin, sfac, status_dt;
+    double time, dt, next_time, rdt;
+    double last_key;
+    TsbTimeKeyer keyer;
+    bool linear_tran;                          // hand the transient over to tsb_tran_linear
 
-    while (phase != PH_DONE) {
+    auto begin_instance = [&]() {
+        c.load(a, inst);
+        c.init();
+        sink.begin(inst);
+        n_acc = n_rej = n_sol_tran = n_sol_op = n_exec = 0;
+        op_path = 0; status = TSB_ST_OK; fail_at = 0.0;
+        phase = (a.analysis == TSB_AN_TRAN && a.uic) ? PH_TRAN_BEGIN : PH_OP_START;
+        op_pass = 0; cont = C_MAIN; iter = 0; mode = TSB_MODE_OP; gstep = 0;
+        gmin = 0.0; sfac = 0.0; status_dt = 0.0;
+        time = 0.0; dt = a.minstep; next_time = 0.0; rdt = 0.0;
+        last_key = -1.0; keyer.reset();
+        linear_tran = false;
+        if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
+        if (LINEAR_LOOP && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
+    };
+    auto finish_instance = [&]() {
+        if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
+        if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish();
+        a.status[inst] = status;
+        a.counters[0 * a.n_inst + inst] = n_acc;
+        a.counters[1 * a.n_inst + inst] = n_rej;
+        a.counters[2 * a.n_inst + inst] = n_sol_tran;
+        a.counters[3 * a.n_inst + inst] = n_sol_op;
+        a.counters[4 * a.n_inst + inst] = op_path;
+        a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+        a.counters[6 * a.n_inst + inst] = n_exec;
+    };
+    begin_instance();
+
+    for (;;) {
+        if (phase == PH_DONE) {
+            if (LINEAR_LOOP && linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
+            finish_instance();
+            if (!REFILL) break;
+            inst = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
+            if (inst >= a.n_inst) break;
+            begin_instance();
+            continue;
+        }
         if (phase == PH_OP_START) {
             // OperatingPoint.Execute(): linear-only initial estimate from a separate sparse matrix
             c.eval_sources(0.0, 1.0);
@@ -357,18 +404,6 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             }
         }
     }
-    if (LINEAR_LOOP && linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
-
-    if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
-    if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish();
-    a.status[inst] = status;
-    a.counters[0 * a.n_inst + inst] = n_acc;
-    a.counters[1 * a.n_inst + inst] = n_rej;
-    a.counters[2 * a.n_inst + inst] = n_sol_tran;
-    a.counters[3 * a.n_inst + inst] = n_sol_op;
-    a.counters[4 * a.n_inst + inst] = op_path;
-    a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
-    a.counters[6 * a.n_inst + inst] = n_exec;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -48,6 +48,8 @@ struct TsbArgsHost {
     const double* sweep;
     int n_sweep;
     int skip_linear_resolve;
+    unsigned long long* work_counter;
+    long long first_free;
 };
 
 struct KernelModule {
@@ -90,6 +92,7 @@ struct tsb_batch {
     long long *d_rows = nullptr, *d_counters = nullptr;
     int* d_status = nullptr;
     unsigned long long* d_totals = nullptr;
+    unsigned long long* d_work = nullptr;              // lane-refill work counter
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -213,6 +216,7 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.fast_div = !o.strict_fp;
     cfg.min_blocks = o.min_blocks;            // 0 = "auto" placeholder (never compiled as such)
     cfg.skip_linear = o.skip_linear_resolve != 0;
+    cfg.lane_refill = o.lane_refill != 0;
     return cfg;
 }
 
@@ -300,7 +304,8 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
 
 void free_results(tsb_batch* b) {
     cudaFree(b->d_wave); cudaFree(b->d_stats); cudaFree(b->d_rows); cudaFree(b->d_status);
-    cudaFree(b->d_counters); cudaFree(b->d_scratch); cudaFree(b->d_sweep); cudaFree(b->d_totals);
+    cudaFree(b->d_counters); cudaFree(b->d_scratch); cudaFree(b->d_sweep); cudaFree(b->d_totals); cudaFree(b->d_work);
+    b->d_work = nullptr;
     b->d_wave = b->d_stats = b->d_scratch = b->d_sweep = nullptr;
     b->d_rows = b->d_counters = nullptr; b->d_status = nullptr; b->d_totals = nullptr;
     b->wave_bytes = b->stats_bytes = 0;
@@ -326,12 +331,13 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     if (!b->d_counters) CU(ctx, cudaMalloc(&b->d_counters, 8 * N * sizeof(long long)));
     if (!b->d_scratch) CU(ctx, cudaMalloc(&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
     if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 5 * sizeof(unsigned long long)));
+    if (!b->d_work) CU(ctx, cudaMalloc(&b->d_work, sizeof(unsigned long long)));
     if (n_sweep > 0) { cudaFree(b->d_sweep); b->d_sweep = nullptr; CU(ctx, cudaMalloc(&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
     b->analysis = analysis; b->ncol = ncol; b->out_flags = out_flags; b->cap_rows = cap_rows;
     return TSB_OK;
 }
 
-int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args) {
+int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args, bool persistent = false, int min_blocks = 0) {
     tsb_ctx* ctx = b->ctx;
     int block = o.block_size > 0 ? o.block_size : 128;
     size_t smem = (args.out_flags & TSB_OUT_STATS) ? (size_t)4 * b->plan->p.num_columns(TSB_AN_TRAN) * block * sizeof(double) : 0;
@@ -339,6 +345,23 @@ int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& ar
     long long blocks = (b->n_inst + block - 1) / block;
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
     if (blocks < 1) blocks = 1;
+    if (!persistent) {
+        args.work_counter = b->d_work;          // static mapping: the first fetch of every lane is already out of range
+        args.first_free = b->n_inst;
+    } else {
+        // Lane refill (skeleton.cuh): a resident grid of SMs x blocks-per-SM; lanes that finish an instance take
+        // the next one from the work counter.  Sized from the occupancy the launch-bounds choice bought.
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kernel, block, smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = min_blocks > 0 ? min_blocks : 2;
+        }
+        long long resident = (long long)ctx->sms * per_sm;
+        if (blocks > resident) blocks = resident;
+        CU(ctx, cudaMemsetAsync(b->d_work, 0, sizeof(unsigned long long), ctx->stream));
+        args.work_counter = b->d_work;
+        args.first_free = blocks * block;
+    }
     void* kargs[] = {&args};
     CU(ctx, cudaLaunchKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
     ++ctx->launches;
@@ -393,7 +416,7 @@ extern "C" {
 void tsb_default_opts(tsb_opts* o) {
     if (!o) return;
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
-    o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0;
+    o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -658,7 +681,7 @@ int tsb_run_op(tsb_batch* b, const tsb_opts* opts) {
     TsbArgsHost a;
     if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
     a.analysis = TSB_AN_OP;
-    return launch(b, o, m->optran, a);
+    return launch(b, o, m->optran, a, b->plan->p.has_nonlinear && o.lane_refill != 0, m->min_blocks);
 }
 
 int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double tmax, int uic, int out_flags,
@@ -681,7 +704,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     if (tmax == 0) tmax = tstep;
     a.analysis = TSB_AN_TRAN; a.uic = uic;
     a.tstart = tstart; a.tstop = tstop; a.tstep = tstep; a.maxstep = tmax; a.minstep = minstep;
-    return launch(b, o, m->optran, a);
+    return launch(b, o, m->optran, a, b->plan->p.has_nonlinear && o.lane_refill != 0, m->min_blocks);
 }
 
 int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts) {
