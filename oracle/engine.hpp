@@ -209,7 +209,7 @@ struct Inductor : Device {
     double CalculateLTE(const Status& st) override {                            // :116-121
         double currentLTE = std::fabs(Current0 - Current1) / (2.0 * st.TimeStep);
         double voltageLTE = std::fabs(Voltage0 - Voltage1) / (2.0 * st.TimeStep);
-        return std::fmax(currentLTE, voltageLTE);
+        return go_max(currentLTE, voltageLTE);
     }
 };
 
@@ -373,7 +373,7 @@ struct Bjt : Device {
         double vt = thermalVoltage(temp);
         double targetIc = 1e-3;
         vbe = Nf * vt * std::log(targetIc / Ies);
-        vce = std::fmax(2.0, vbe + 1.0);
+        vce = go_max(2.0, vbe + 1.0);
         vbc = vbe - vce;
     }
     void calculateCurrents(double temp) {                        // :214-255
@@ -461,7 +461,7 @@ struct Mosfet : Device {
     double calculateVth(double vbs_) const {                     // :296-318
         double vt0 = VTO;
         if (GAMMA > 0) {
-            double vth = vt0 + GAMMA * (std::sqrt(std::fmax(0, PHI - vbs_)) - std::sqrt(PHI));
+            double vth = vt0 + GAMMA * (std::sqrt(go_max(0, PHI - vbs_)) - std::sqrt(PHI));
             if (pmos) vth = -vth;
             return vth;
         }
@@ -485,7 +485,7 @@ struct Mosfet : Device {
         double vdsat = vgst;
         if (VMAX > 0) {
             double ecrit = VMAX / ueff * 100;
-            vdsat = std::fmin(vgst, ecrit * L);
+            vdsat = go_min(vgst, ecrit * L);
         }
         double beta = ueff * cox * W / (L * 100);
         if (vds_ < vdsat) { i = beta * (vgst * vds_ - 0.5 * vds_ * vds_) * (1.0 + LAMBDA * vds_); reg = LINEAR; }
@@ -548,11 +548,11 @@ struct Mosfet : Device {
             double id0 = id;
             double idg, idd, idb; int r;
             calculateCurrents(vgs_ + delta, vds_, vbs_, idg, r);
-            gm = std::fmax((idg - id0) / delta, gmin);
+            gm = go_max((idg - id0) / delta, gmin);
             calculateCurrents(vgs_, vds_ + delta, vbs_, idd, r);
-            gds = std::fmax((idd - id0) / delta, gmin);
+            gds = go_max((idd - id0) / delta, gmin);
             calculateCurrents(vgs_, vds_, vbs_ + delta, idb, r);
-            gmbs = std::fmax((idb - id0) / delta, gmin);
+            gmbs = go_max((idb - id0) / delta, gmin);
             break;
         }
         default: break;     // other levels: Go switch has no default -> gm/gds keep stale values
@@ -803,7 +803,7 @@ struct OperatingPoint {
     bool same(const std::vector<double>& s, const std::vector<double>& o) const {   // op.go:67-77
         for (size_t i = 1; i < s.size(); ++i) {
             double diff = std::fabs(s[i] - o[i]);
-            double tol = conv.reltol * std::fmax(std::fabs(s[i]), std::fabs(o[i])) + conv.abstol;
+            double tol = conv.reltol * go_max(std::fabs(s[i]), std::fabs(o[i])) + conv.abstol;
             if (diff > tol) return false;
         }
         return true;
@@ -932,7 +932,7 @@ struct Transient {
                 bool all = true;
                 for (size_t i = 1; i < sol.size(); ++i) {
                     double diff = std::fabs(sol[i] - old[i]);
-                    double tol = conv.reltol * std::fmax(std::fabs(sol[i]), std::fabs(old[i])) + conv.abstol;
+                    double tol = conv.reltol * go_max(std::fabs(sol[i]), std::fabs(old[i])) + conv.abstol;
                     if (diff > tol) { all = false; break; }
                 }
                 if (all) return true;
@@ -990,8 +990,8 @@ struct Transient {
             ++cnt.accepted;
             if (time >= startTime) StoreTimeResult(rs, time);
             if (time < stopTime && timeStep < maxStep) {
-                if (lte < trtol / 100) timeStep = std::fmin(timeStep * 2, maxStep);
-                else timeStep = std::fmin(timeStep * 1.1, maxStep);
+                if (lte < trtol / 100) timeStep = go_min(timeStep * 2, maxStep);
+                else timeStep = go_min(timeStep * 1.1, maxStep);
             }
         }
         cnt.tran_solves = ckt->Matrix->n_solves - cnt.op_solves;

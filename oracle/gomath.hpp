@@ -49,4 +49,19 @@ inline double go_sin(double x) {
     return sign ? -y : y;
 }
 
+// math.Max / math.Min (src/math/dim.go): +Inf / -Inf win over NaN, otherwise NaN propagates (C's fmax / fmin DROP
+// a NaN operand), and Max(+0, -0) = +0, Min(+0, -0) = -0.
+inline double go_max(double x, double y) {
+    if ((std::isinf(x) && x > 0) || (std::isinf(y) && y > 0)) return INFINITY;
+    if (std::isnan(x) || std::isnan(y)) return std::nan("");
+    if (x == 0 && x == y) return std::signbit(x) ? y : x;
+    return x > y ? x : y;
+}
+inline double go_min(double x, double y) {
+    if ((std::isinf(x) && x < 0) || (std::isinf(y) && y < 0)) return -INFINITY;
+    if (std::isnan(x) || std::isnan(y)) return std::nan("");
+    if (x == 0 && x == y) return std::signbit(x) ? x : y;
+    return x < y ? x : y;
+}
+
 }  // namespace orc

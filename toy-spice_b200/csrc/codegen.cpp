@@ -12,7 +12,9 @@
 // with the per-device stamp arithmetic delegated to device/models.cuh and the analysis drivers
 // to device/skeleton.cuh (both embedded verbatim so the unit compiles under NVRTC and nvcc alike).
 #include <cstdio>
+#include <set>
 #include <sstream>
+#include <vector>
 #include "tsb_internal.hpp"
 
 namespace tsb {
@@ -77,8 +79,44 @@ void emit_eval(Emitter& e, const Plan& pl, int di, const std::string& ov) {
     }
 }
 
+// Targets ("A[k]" / "b[i]") written by the stamps of the listed devices.
+std::set<std::string> stamp_targets(const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only) {
+    std::set<std::string> t;
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (linear_only && d.nonlinear()) continue;
+        if (op_only && d.kind == TSB_K) continue;
+        for (const StampEntry& s : pl.stamps[di]) {
+            if (op_only && s.tran_only) continue;
+            if (s.col == 0) t.insert("b[" + std::to_string(s.row) + "]");
+            else {
+                auto it = lu.index.find({s.row, s.col});
+                if (it != lu.index.end()) t.insert("A[" + std::to_string(it->second) + "]");
+            }
+        }
+    }
+    return t;
+}
+
+// Zero-initialisation of A[] and b[] (mat.Clear()).  With `first_assign` only the entries no stamp writes are
+// zeroed: the first stamp into an entry then ASSIGNS instead of accumulating onto 0.0 (emit_stamps) — ptxas cannot
+// fold 0.0 + x (it is not x for x = -0.0) and the first profile showed one DADD RZ per stamped entry.
+void emit_clear(Emitter& e, const LuProgram& lu, int n, const std::set<std::string>* assigned) {
+    for (size_t k = 0; k < lu.pos.size(); ++k) {
+        std::string t = "A[" + std::to_string(k) + "]";
+        if (assigned && assigned->count(t)) continue;
+        e.line(t + " = 0.0;   // (" + std::to_string(lu.pos[k].first) + "," + std::to_string(lu.pos[k].second) + ")");
+    }
+    for (int i = 0; i <= n; ++i) {
+        std::string t = "b[" + std::to_string(i) + "]";
+        if (assigned && assigned->count(t)) continue;
+        e.line(t + " = 0.0;");
+    }
+}
+
 // Emits the stamps of the listed devices into A[] (indexed through `lu.index`) and b[].
-void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only) {
+void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only, bool first_assign = false) {
+    std::set<std::string> touched;
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
         if (linear_only && d.nonlinear()) continue;
@@ -100,7 +138,8 @@ void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_on
                 if (it == lu.index.end()) continue;     // cannot happen: pattern built from these entries
                 tgt = "A[" + std::to_string(it->second) + "]";
             }
-            e.line(tgt + (s.sign < 0 ? " -= " : " += ") + val + ";");
+            if (first_assign && touched.insert(tgt).second) e.line(tgt + (s.sign < 0 ? " = -" : " = ") + val + ";");
+            else e.line(tgt + (s.sign < 0 ? " -= " : " += ") + val + ";");
         }
         --e.ind;
         e.line("}");
@@ -110,7 +149,10 @@ void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_on
 // Factor + solve in the frozen order.  Same operation order per element as Sparse 1.3's
 // spFactor/spSolve (u = a*(1/pivot); a_ij -= u_kj*l_ik for k ascending; forward with reciprocal
 // pivots; back-substitution in ascending column order), so --fmad=false reproduces its rounding.
-void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string& xout) {
+// `b_zero` (fast sparse builds): rows of b no stamp writes — forward / back substitution skips the operations whose
+// operand is such a structural zero.  `early_cond`: condition under which a zero pivot returns before the solve.
+void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string& xout, const std::set<int>* b_zero = nullptr,
+             const std::string& early_cond = "!lu_ok") {
     const int n = lu.n;
     if (!lu.dense) e.line("bool lu_ok = true;");
     if (load_gmin) {
@@ -137,22 +179,36 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
                 e.line("A[" + std::to_string(st.target[ui][li]) + "] -= " + u + " * A[" + std::to_string(st.lcol[li]) + "];");
         }
     }
-    if (!lu.dense) e.line("if (!lu_ok) return false;");
+    if (!lu.dense) e.line("if (" + early_cond + ") return false;");
     e.line("double c[" + std::to_string(n + 1) + "];");
-    for (int k = 1; k <= n; ++k) e.line("c[" + std::to_string(k) + "] = b[" + std::to_string(lu.prow[k]) + "];");
+    std::vector<char> cz(n + 1, 0);          // c[k] is a structural zero so far
+    for (int k = 1; k <= n; ++k) {
+        cz[k] = (b_zero && !lu.dense && b_zero->count(lu.prow[k])) ? 1 : 0;
+        e.line("c[" + std::to_string(k) + "] = " + (cz[k] ? std::string("0.0") : "b[" + std::to_string(lu.prow[k]) + "]") + ";");
+    }
     for (int k = 1; k <= n; ++k) {
         const LuProgram::Step& st = lu.steps[k];
         std::string ck = "c[" + std::to_string(k) + "]";
+        if (cz[k]) continue;
         if (lu.dense) { e.line("if (" + ck + " != 0.0) {"); ++e.ind; }
         e.line(ck + " *= A[" + std::to_string(st.piv) + "];");
-        for (size_t li = 0; li < st.lcol.size(); ++li)
-            e.line("c[" + std::to_string(st.lrow_step[li]) + "] -= " + ck + " * A[" + std::to_string(st.lcol[li]) + "];");
+        for (size_t li = 0; li < st.lcol.size(); ++li) {
+            int j = st.lrow_step[li];
+            std::string prod = ck + " * A[" + std::to_string(st.lcol[li]) + "]";
+            if (cz[j]) { e.line("c[" + std::to_string(j) + "] = -(" + prod + ");"); cz[j] = 0; }
+            else e.line("c[" + std::to_string(j) + "] -= " + prod + ";");
+        }
         if (lu.dense) { --e.ind; e.line("}"); }
     }
     for (int k = n; k >= 1; --k) {
         const LuProgram::Step& st = lu.steps[k];
-        for (size_t ui = 0; ui < st.urow.size(); ++ui)
-            e.line("c[" + std::to_string(k) + "] -= A[" + std::to_string(st.urow[ui]) + "] * c[" + std::to_string(st.ucol_step[ui]) + "];");
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            int j = st.ucol_step[ui];
+            if (cz[j]) continue;
+            std::string prod = "A[" + std::to_string(st.urow[ui]) + "] * c[" + std::to_string(j) + "]";
+            if (cz[k]) { e.line("c[" + std::to_string(k) + "] = -(" + prod + ");"); cz[k] = 0; }
+            else e.line("c[" + std::to_string(k) + "] -= " + prod + ";");
+        }
     }
     for (int k = 1; k <= n; ++k) e.line(xout + "[" + std::to_string(lu.pcol[k]) + "] = c[" + std::to_string(k) + "];");
 }
@@ -171,6 +227,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("#define TSB_MIN_BLOCKS " + std::to_string(cfg.min_blocks));
     e.line("#define TSB_SKIP_LINEAR_RESOLVE " + std::to_string(cfg.skip_linear ? 1 : 0));
     e.line("#define TSB_LANE_REFILL " + std::to_string(cfg.lane_refill && pl.has_nonlinear ? 1 : 0));
+    if (!cfg.extra_defines.empty()) e.os << cfg.extra_defines << "\n";     // development knob ($TSB_EXTRA_DEFINES)
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
     e.line("struct Ckt {");
@@ -264,6 +321,27 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     --e.ind;
     e.line("}");
 
+    e.line("// Same at fac = 1 with the branch-free math.Sin restatement; false when an argument is outside its range");
+    e.line("// (|x| >= 2^29) — the caller then re-evaluates with eval_sources().");
+    e.line("__device__ __forceinline__ bool eval_sources_nb(double t) {");
+    ++e.ind;
+    e.line("bool ok = true;");
+    for (const Dev& d : pl.devs) {
+        if (d.src_slot < 0) continue;
+        std::string sv = "SV[" + std::to_string(d.src_slot) + "]";
+        std::string P = "P + " + std::to_string(d.p_off);
+        switch (d.src_type()) {
+        case TSB_SRC_DC: e.line(sv + " = P[" + std::to_string(d.p_off) + "] * 1.0;"); break;
+        case TSB_SRC_SIN: e.line(sv + " = tsb_src_sin_nb(" + P + ", t, ok);"); break;
+        case TSB_SRC_PULSE: e.line(sv + " = tsb_src_pulse(" + P + ", t);"); break;
+        case TSB_SRC_PWL: e.line(sv + " = tsb_src_pwl(U_ + " + std::to_string(d.p_off) + ", " + std::to_string(d.p.size() / 2) + ", t);"); break;
+        }
+    }
+    e.line("(void)t;");
+    e.line("return ok;");
+    --e.ind;
+    e.line("}");
+
     // ---- DC sweep source override --------------------------------------------------------------
     e.line("__device__ __forceinline__ void set_dc(double v) {");
     ++e.ind;
@@ -299,11 +377,16 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         e.line("TsbEnv e; e.mode = TSB_MODE_OP; e.time = 0.0; e.dt = status_dt; e.gmin = 0.0; e.rdt = status_dt > 0 ? 1.0 / status_dt : 0.0;");
         e.line("double A[" + std::to_string(pl.lu_init.pos.size()) + "];");
         e.line("double b[" + std::to_string(n + 1) + "];");
-        for (size_t k = 0; k < pl.lu_init.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;");
-        for (int i = 0; i <= n; ++i) e.line("b[" + std::to_string(i) + "] = 0.0;");
-        emit_stamps(e, pl, pl.lu_init, true, true);
-        e.line("double xt[" + std::to_string(n + 1) + "];");
-        emit_lu(e, pl.lu_init, false, "xt");
+        {
+            const bool fa = cfg.fast_div && !pl.lu_init.dense;
+            std::set<std::string> tg = stamp_targets(pl, pl.lu_init, true, true);
+            std::set<int> bz;
+            for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
+            emit_clear(e, pl.lu_init, n, fa ? &tg : nullptr);
+            emit_stamps(e, pl, pl.lu_init, true, true, fa);
+            e.line("double xt[" + std::to_string(n + 1) + "];");
+            emit_lu(e, pl.lu_init, false, "xt", fa ? &bz : nullptr);
+        }
         for (int i = 1; i <= n; ++i) e.line("out[" + std::to_string(i) + "] = xt[" + std::to_string(i) + "];");
         e.line("return true;");
     }
@@ -313,20 +396,27 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     // ---- Newton body ----------------------------------------------------------------------------
     e.line("// mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin); mat.Solve()  ->  x");
     e.line("// MODE >= 0 fixes the analysis mode at compile time (the dedicated transient loop): mode selects fold away.");
-    e.line("template <int MODE>");
+    e.line("// EARLY = false (the dedicated linear transient loop): a zero pivot does not return before the solve — the body");
+    e.line("// stays one basic block; the caller discards x when the result is false.");
+    e.line("template <int MODE, bool EARLY = true>");
     e.line("__device__ __forceinline__ bool assemble_solve(int mode_rt, double time, double dt, double rdt, double gmin) {");
     ++e.ind;
     e.line("const int mode = MODE >= 0 ? MODE : mode_rt;");
     e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin; e.rdt = rdt;");
     e.line("double A[" + std::to_string(pl.lu_main.pos.size()) + "];");
     e.line("double b[" + std::to_string(n + 1) + "];");
-    for (size_t k = 0; k < pl.lu_main.pos.size(); ++k) e.line("A[" + std::to_string(k) + "] = 0.0;   // (" + std::to_string(pl.lu_main.pos[k].first) + "," + std::to_string(pl.lu_main.pos[k].second) + ")");
-    for (int i = 0; i <= n; ++i) e.line("b[" + std::to_string(i) + "] = 0.0;");
-    emit_stamps(e, pl, pl.lu_main, false, false);
-    e.line("double xt[" + std::to_string(n + 1) + "];");
-    emit_lu(e, pl.lu_main, true, "xt");
+    {
+        const bool fa = cfg.fast_div && !pl.lu_main.dense;
+        std::set<std::string> tg = stamp_targets(pl, pl.lu_main, false, false);
+        std::set<int> bz;
+        for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
+        emit_clear(e, pl.lu_main, n, fa ? &tg : nullptr);
+        emit_stamps(e, pl, pl.lu_main, false, false, fa);
+        e.line("double xt[" + std::to_string(n + 1) + "];");
+        emit_lu(e, pl.lu_main, true, "xt", fa ? &bz : nullptr, "EARLY && !lu_ok");
+    }
     for (int i = 1; i <= n; ++i) e.line("x[" + std::to_string(i) + "] = xt[" + std::to_string(i) + "];");
-    e.line("return true;");
+    e.line(pl.lu_main.dense ? "return true;" : "return lu_ok;");
     --e.ind;
     e.line("}");
 
@@ -355,10 +445,20 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("__device__ __forceinline__ double lte(double dt, double rdt) {   // Transient.calculateTruncError (tran.go:239-250)");
     ++e.ind;
     e.line("double m = 0.0, l;");
-    for (int di : pl.stamp_order) {
-        const Dev& d = pl.devs[di];
-        if (d.kind == TSB_C) e.line("l = tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt, rdt); if (l > m) m = l;");
-        if (d.kind == TSB_L) e.line("l = tsb_ind_lte(S + " + std::to_string(d.s_off) + ", dt, rdt); if (l > m) m = l;");
+    {
+        // maxLTE := 0.0; if lte > maxLTE { maxLTE = lte }.  Every term is >= +0 or NaN, so the first update is
+        // "l unless NaN" (a compare-with-itself select instead of the max(0, l) NaN fix-up sequence).
+        bool first = true;
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            std::string call;
+            if (d.kind == TSB_C) call = "tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt, rdt)";
+            if (d.kind == TSB_L) call = "tsb_ind_lte(S + " + std::to_string(d.s_off) + ", dt, rdt)";
+            if (call.empty()) continue;
+            if (first) e.line("l = " + call + "; m = (l != l) ? 0.0 : l;");
+            else e.line("l = " + call + "; if (l > m) m = l;");
+            first = false;
+        }
     }
     e.line("(void)dt; (void)rdt; (void)l;");
     e.line("return m;");

@@ -86,25 +86,28 @@ __device__ __forceinline__ bool tsb_converged_dc(const double* x, const double* 
 // Result sink of one instance: waveform rows to HBM (instance-fastest layout, so a warp whose
 // lanes are at the same row index writes 256 contiguous bytes per column) and running
 // min / max / sum / last per column in shared memory.
+// Shared-memory layout: per column two double2 arrays of TSB_BLOCK entries, {min, max} and {sum, last}; a thread
+// owns entry threadIdx.x of each, so a warp reads or writes 512 contiguous bytes per 128-bit access (conflict-free)
+// and one stored row costs 4 shared-memory instructions per column instead of 7 scalar ones.  Column 0 (TIME /
+// the sweep value) is monotone by construction: its extremes are the first and the last row — only {sum, last} updated.
 template <int NCOL>
 struct TsbSink {
     const TsbArgs& a;
     long long inst;
     long long n_rows;
     bool overflow;
-    double* sm;                 // this thread's first stats word; words are TSB_BLOCK doubles apart (conflict-free)
+    double2* sm;                // this thread's first pair; pairs are TSB_BLOCK double2 apart
     __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false) {
-        sm = tsb_smem + threadIdx.x;          // launched with blockDim.x == TSB_BLOCK: every offset below is an immediate
+        sm = reinterpret_cast<double2*>(tsb_smem) + threadIdx.x;   // launched with blockDim.x == TSB_BLOCK: every offset below is an immediate
     }
     __device__ __forceinline__ void begin(long long inst_) {      // (re)start for one instance
         inst = inst_; n_rows = 0; overflow = false;
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
-                sm[(0 * NCOL + j) * TSB_BLOCK] = __longlong_as_double(0x7ff0000000000000LL);    // +inf
-                sm[(1 * NCOL + j) * TSB_BLOCK] = __longlong_as_double(0xfff0000000000000LL);    // -inf
-                sm[(2 * NCOL + j) * TSB_BLOCK] = 0.0;
-                sm[(3 * NCOL + j) * TSB_BLOCK] = 0.0;
+                sm[(2 * j) * TSB_BLOCK] = make_double2(__longlong_as_double(0x7ff0000000000000LL),     // +inf
+                                                       __longlong_as_double(0xfff0000000000000LL));    // -inf
+                sm[(2 * j + 1) * TSB_BLOCK] = make_double2(0.0, 0.0);
             }
         }
     }
@@ -117,17 +120,22 @@ struct TsbSink {
             } else overflow = true;
         }
         if (a.out_flags & TSB_OUT_STATS) {
+            if (n_rows == 0) sm[0] = make_double2(row[0], row[0]);     // column 0: the first row, kept in the {min, max} slot
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
                 const double v = row[j];
-                double* s = sm + j * TSB_BLOCK;
-                // running min / max that ignore NaN samples (the accumulators start at +-inf and can never
-                // become NaN themselves), i.e. fmin / fmax semantics without their NaN fix-up code
-                const double mn = s[0], mx = s[(1 * NCOL) * TSB_BLOCK];
-                s[0] = v < mn ? v : mn;
-                s[(1 * NCOL) * TSB_BLOCK] = v > mx ? v : mx;
-                s[(2 * NCOL) * TSB_BLOCK] += v;
-                s[(3 * NCOL) * TSB_BLOCK] = v;
+                if (j > 0) {
+                    // running min / max that ignore NaN samples (the accumulators start at +-inf and can never
+                    // become NaN themselves), i.e. fmin / fmax semantics without their NaN fix-up code
+                    double2 mm = sm[(2 * j) * TSB_BLOCK];
+                    mm.x = v < mm.x ? v : mm.x;
+                    mm.y = v > mm.y ? v : mm.y;
+                    sm[(2 * j) * TSB_BLOCK] = mm;
+                }
+                double2 sl = sm[(2 * j + 1) * TSB_BLOCK];
+                sl.x += v;
+                sl.y = v;
+                sm[(2 * j + 1) * TSB_BLOCK] = sl;
             }
         }
         ++n_rows;
@@ -135,7 +143,18 @@ struct TsbSink {
     __device__ __forceinline__ void finish() {
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
-            for (int k = 0; k < 4 * NCOL; ++k) a.stats[(long long)k * a.n_inst + inst] = sm[k * TSB_BLOCK];
+            for (int j = 0; j < NCOL; ++j) {
+                double2 mm = sm[(2 * j) * TSB_BLOCK];
+                const double2 sl = sm[(2 * j + 1) * TSB_BLOCK];
+                if (j == 0 && n_rows > 0) {          // monotone in either direction: extremes are the first and the last row
+                    const double f = mm.x, l = sl.y;
+                    mm.x = f < l ? f : l; mm.y = f < l ? l : f;
+                }
+                a.stats[(long long)(0 * NCOL + j) * a.n_inst + inst] = mm.x;
+                a.stats[(long long)(1 * NCOL + j) * a.n_inst + inst] = mm.y;
+                a.stats[(long long)(2 * NCOL + j) * a.n_inst + inst] = sl.x;
+                a.stats[(long long)(3 * NCOL + j) * a.n_inst + inst] = sl.y;
+            }
         }
         a.rows[inst] = n_rows;
     }
@@ -161,40 +180,70 @@ __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& 
         }
     }
     if (time < a.tstop && dt < a.maxstep) {
-        if (lte < a.trtol / 100) dt = fmin(dt * 2, a.maxstep);
-        else dt = fmin(dt * 1.1, a.maxstep);
+        // math.Min of two finite positive numbers (dt is never NaN): a plain select
+        const double grown = lte < a.trtol / 100 ? dt * 2 : dt * 1.1;
+        dt = grown < a.maxstep ? grown : a.maxstep;
     }
 }
 
-// Transient loop of a circuit WITHOUT nonlinear devices when the redundant second solve is compiled
-// away: one stamp+factor+solve per step attempt, no Newton state machine, analysis mode fixed at compile
-// time (mode selects, the LoadGmin branch and the dt > 0 guards fold away).  Same statements as
-// tran.go:96-151 / 157-216 with iter = 0, 1 collapsed.
+// Transient loop of a circuit WITHOUT nonlinear devices when work whose result the reference discards is compiled
+// away (tsb_opts.skip_linear_resolve): no Newton state machine, analysis mode fixed at compile time (mode selects,
+// the LoadGmin branch and the dt > 0 guards fold away).  Same statements as tran.go:96-151 / 157-216 with
+//   * iter = 0, 1 collapsed into one stamp+factor+solve (the second solve repeats identical bits);
+//   * the truncation-error test hoisted ABOVE the solve: calculateTruncError (tran.go:239-250) reads only the device
+//     state of the last ACCEPTED steps (CalculateLTE uses Voltage0/1, Current0/1, set by LoadState/UpdateState after
+//     an accept), never the solution just computed, so a step the reference rejects for LTE is known to be rejected
+//     before its solve — which the reference executes and throws away.  Not executed here; counted as the
+//     reference counts it (2 solves; a lane whose matrix is singular exactly at such a step would count 1);
+//   * the step body kept free of branches up to the accept (TSB_X_NB): reciprocal of dt, source evaluation,
+//     factorisation and substitution form one basic block, so the independent chains (math.Sin polynomial, 1/dt,
+//     pivot reciprocals) overlap instead of queueing behind each other's latency.
+#ifndef TSB_X_PRELTE
+#define TSB_X_PRELTE 1
+#endif
+#ifndef TSB_X_NB
+#define TSB_X_NB 1
+#endif
 template <class Ckt, class Sink>
-__device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& sink, long long& n_acc, long long& n_rej,
-                                                long long& n_sol_tran, long long& n_exec, int& status, double& fail_at) {
+__device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& sink, long long& n_acc_out, long long& n_rej_out,
+                                                long long& n_sol_tran_out, long long& n_exec_out, int& status, double& fail_at) {
     double time = 0.0, dt = a.minstep;
     double last_key = -1.0;
     TsbTimeKeyer keyer; keyer.reset();
+    int n_acc = 0, n_rej = 0, n_skip = 0, n_bad = 0;   // accepted, rejected, rejected without executing the solve, failed solves
     while (time < a.tstop) {
         double next_time = time + dt;
         if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
-        c.eval_sources(time, 1.0);
         __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
-        const double rdt = 1.0 / dt;
-        const bool solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
-        ++n_exec;
-        n_sol_tran += solved ? 2 : 1;              // the reference stops at the failing solve, else runs two
+        const double rdt = TSB_X_NB ? tsb_rcp_dt(dt) : 1.0 / dt;
+        const double lte = c.lte(dt, rdt);
+        if (TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; ++n_skip; continue; }
+        bool solved;
+        if (TSB_X_NB) {
+            const bool in_range = c.eval_sources_nb(time);
+            solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+            if (!in_range) {                      // a math.Sin argument beyond 2^29: redo with the general routine
+                c.eval_sources(time, 1.0);
+                solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+            }
+        } else {
+            c.eval_sources(time, 1.0);
+            solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+        }
         if (!solved) {
+            ++n_bad;
             if (dt > a.minstep) { dt /= 2; ++n_rej; continue; }
             status = TSB_ST_TRAN_FAILED; fail_at = time;
-            return;
+            break;
         }
-        const double lte = c.lte(dt, rdt);
-        if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
+        if (!TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
         tsb_accept_step(a, c, sink, time, dt, next_time, lte, keyer, last_key);
         ++n_acc;
     }
+    n_acc_out += n_acc; n_rej_out += n_rej;
+    const int failed = status == TSB_ST_TRAN_FAILED ? 1 : 0;
+    n_exec_out += n_acc + n_rej - n_skip + failed;
+    n_sol_tran_out += 2LL * (n_acc + n_rej) - n_bad + 2 * failed;      // the reference stops at a failing solve, else runs two
 }
 
 // ------------------------------------------------------------------------------------------------

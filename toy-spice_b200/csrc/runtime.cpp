@@ -217,6 +217,17 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.min_blocks = o.min_blocks;            // 0 = "auto" placeholder (never compiled as such)
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
+    if (const char* x = getenv("TSB_EXTRA_DEFINES")) {          // development knob for A/B kernel experiments
+        std::string item;
+        for (const char* c = x;; ++c) {
+            if (*c == ';' || *c == '\0') {
+                size_t eq = item.find('=');
+                if (!item.empty()) cfg.extra_defines += "#define " + (eq == std::string::npos ? item + " 1" : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
+                item.clear();
+                if (*c == '\0') break;
+            } else item += *c;
+        }
+    }
     return cfg;
 }
 
