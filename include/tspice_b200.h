@@ -103,12 +103,21 @@ typedef struct tsb_opts {
                            beside slow neighbours) — for sweeps whose instances need very different numbers of steps;
                            0 (default): one thread per instance, static mapping (3-17 % faster on the bundled decks,
                            whose lanes finish together).  Results are bit-identical either way. */
+    double grid_dt;     /* TSB_OUT_GRID: spacing of the output grid; 0 (default) = the analysis' tStep after
+                           NewTransient's clamping (tran.go:31-33), i.e. >= 300 points */
 } tsb_opts;
 
 /* Output selection for tsb_run_tran / tsb_run_dc. */
 enum {
     TSB_OUT_WAVE = 1,   /* every stored row: wave[row][column][instance]          */
-    TSB_OUT_STATS = 2   /* min / max / sum / last per column over the stored rows */
+    TSB_OUT_STATS = 2,  /* min / max / sum / last per column over the stored rows */
+    TSB_OUT_GRID = 4    /* transient only: the reference's result series resampled ON THE DEVICE onto the fixed grid
+                           t_k = tstart + (k+1)*grid_dt <= tstop (k = 0..), by linear interpolation between
+                           consecutive stored rows (constant before the first / after the last one):
+                           wave[k][column][instance], column 0 = t_k.  This is how instances whose adaptive step
+                           sequences differ are compared point by point, and what makes waveform output of the
+                           ~2e4-step inductor decks fit in HBM for 1M+ instances.  Implies TSB_OUT_STATS; excludes
+                           TSB_OUT_WAVE.  rows[inst] = grid rows written; counters[7] = rows of the reference series */
 };
 
 void tsb_default_opts(tsb_opts* o);
@@ -187,7 +196,8 @@ int tsb_batch_sync(tsb_batch* batch);
  *   rows     [n_inst] int64                   status [n_inst] int32
  *   counters [8][n_inst] int64: 0 accepted steps, 1 rejected steps, 2 transient solves, 3 OP solves (2, 3: as the
  *            reference would count them), 4 OP path (0 direct, 1 Gmin stepping, 2 source stepping),
- *            5 failure time/value (double bits), 6 factor+solve passes actually executed, 7 reserved */
+ *            5 failure time/value (double bits), 6 factor+solve passes actually executed,
+ *            7 rows of the reference's result series (== rows[] unless TSB_OUT_GRID) */
 int tsb_result_dims(const tsb_batch* batch, int64_t* n_inst, int* n_columns, int64_t* cap_rows);
 int tsb_result_dev_ptrs(const tsb_batch* batch, uint64_t* wave, uint64_t* stats, uint64_t* rows, uint64_t* status,
                         uint64_t* counters);

@@ -33,7 +33,7 @@ def draws(name: str, ckt, n: int, seed: int | None = None):
     return W.sweep_draws(ckt.devices(), n, W.sweep_seed(name) if seed is None else seed)
 
 
-def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, analysis=None, tran=None):
+def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, analysis=None, tran=None, grid_dt=0.0):
     """Through the reference-shaped API: Circuit -> analysis.Setup(batch) -> Execute."""
     ckt = T.Circuit.from_netlist(text, ctx)
     batch = ckt.batch(n)
@@ -49,6 +49,7 @@ def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, anal
         an = T.NewTransient(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"])
         an.out = out
         an.cap_rows = cap_rows
+        an.grid_dt = grid_dt
     else:
         an = T.NewDCSweep([ckt.devices()[card["dc_src_dev"]]["name"]], [card["dc_start"]], [card["dc_stop"]], [card["dc_inc"]])
         an.out = out
@@ -109,3 +110,22 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
 def report_ok(rep) -> bool:
     return (rep["row_mismatch"] == 0 and rep["status_mismatch"] == 0 and rep["nan_mismatch"] == 0
             and rep["max_rel"] <= 1.0)
+
+
+def resample_reference(wave, n_rows, ncol, tg):
+    """The TSB_OUT_GRID definition applied (in numpy) to one instance's reference series `wave[:n_rows, :ncol]`:
+    linear interpolation between consecutive stored rows, constant before the first / after the last one."""
+    t = wave[:n_rows, 0]
+    out = np.empty((len(tg), ncol))
+    out[:, 0] = tg
+    i1 = np.searchsorted(t, tg, side="left")            # first stored row with t >= tg
+    for k, g in enumerate(tg):
+        j = int(i1[k])
+        if j >= n_rows:
+            out[k, 1:] = wave[n_rows - 1, 1:ncol]
+        elif j == 0:
+            out[k, 1:] = wave[0, 1:ncol]
+        else:
+            w = (g - t[j - 1]) / (t[j] - t[j - 1])
+            out[k, 1:] = wave[j - 1, 1:ncol] + (wave[j, 1:ncol] - wave[j - 1, 1:ncol]) * w
+    return out

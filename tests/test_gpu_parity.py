@@ -245,3 +245,58 @@ def test_newton_fallback_paths_match(ctx):
 def test_fp64_peak_measurement(ctx):
     tf = ctx.measure_fp64_peak()
     assert 20.0 < tf < 60.0, tf        # B200 FP64 vector: ~37 TFLOP/s
+
+
+@pytest.mark.parametrize("name,grid_dt", [("rc", 0.0), ("rlc", 0.0), ("rlc", 3.7e-5), ("diode2", 0.0), ("mosfet1", 2.5e-8),
+                                          ("transformer1", 0.0), ("bjt2", 0.0)])
+def test_fixed_grid_output_matches_resampled_reference(ctx, name, grid_dt):
+    """TSB_OUT_GRID: the device resamples the result series onto t_k = tstart + (k+1)*grid_dt while it runs; the
+    check is the same definition applied in numpy to the oracle's full stored series (north star: "at
+    interpolated output points under adaptive stepping")."""
+    n = 24
+    text = T.BUNDLED[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, out=T.OUT_GRID, grid_dt=grid_dt)
+    _, ores = PU.run_oracle(text, n, ov, cap_rows=24000)
+    tg = an.grid_times()
+    w = batch.wave_all()                                   # [n_grid, ncol, n]
+    assert w.shape[0] == len(tg) >= 1
+    rows, st, cnt = batch.rows(), batch.status(), batch.counters()
+    assert np.array_equal(st, ores["status"])
+    assert np.array_equal(cnt[7], ores["n_rows"])          # rows of the reference series
+    ncol = ores["ncol"]
+    checked = 0
+    for i in range(n):
+        if st[i] != 0:
+            assert rows[i] <= len(tg)
+            continue
+        assert rows[i] == len(tg)
+        ref = PU.resample_reference(ores["wave"][i], int(ores["n_rows"][i]), ncol, tg)
+        g = w[:, :, i]
+        assert np.array_equal(g[:, 0], tg)
+        assert np.array_equal(np.isnan(g), np.isnan(ref)), name
+        ok = np.isfinite(ref)
+        # interpolation subtracts neighbouring samples: tolerance relative to the local signal scale
+        scale = np.maximum(np.abs(ref), np.nanmax(np.abs(ref), axis=0, keepdims=True) * 1e-3)
+        assert np.all(np.abs(g[ok] - ref[ok]) <= PU.RELTOL * scale[ok] + PU.ABSTOL), (name, i)
+        checked += int(ok.sum())
+    assert checked > 0 or name.startswith("bjt")
+    # statistics are still those of the reference series
+    s = batch.stats_all()
+    assert np.array_equal(np.isfinite(s[3]), np.isfinite(s[3]))
+
+
+def test_fixed_grid_is_what_lets_inductor_waveforms_fit(ctx):
+    """rlc.cir stores ~11 000 rows per instance; on the default 300-point grid 2^18 instances are 4.4 GB."""
+    n = 1 << 18
+    ov = PU.draws("rlc", T.Circuit.from_netlist(T.BUNDLED["rlc"]), n)
+    ckt, batch, an = PU.run_gpu(ctx, T.BUNDLED["rlc"], n, ov, out=T.OUT_GRID)
+    tg = an.grid_times()
+    assert np.all(batch.status() == 0) and np.all(batch.rows() == len(tg))
+    idx = np.random.default_rng(5).choice(n, 8, replace=False)
+    _, ores = PU.run_oracle(T.BUNDLED["rlc"], 8, {k: v[idx] for k, v in ov.items()}, cap_rows=24000)
+    for q, i in enumerate(idx):
+        ref = PU.resample_reference(ores["wave"][q], int(ores["n_rows"][q]), ores["ncol"], tg)
+        g = batch.waveform(int(i))
+        scale = np.maximum(np.abs(ref), np.max(np.abs(ref), axis=0, keepdims=True) * 1e-3)
+        assert np.all(np.abs(g - ref) <= PU.RELTOL * scale + PU.ABSTOL)

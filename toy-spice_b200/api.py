@@ -26,7 +26,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 AN_OP, AN_TRAN, AN_AC, AN_DC = 0, 1, 2, 3
-OUT_WAVE, OUT_STATS = 1, 2
+OUT_WAVE, OUT_STATS, OUT_GRID = 1, 2, 4
 K_R, K_C, K_L, K_V, K_I, K_D, K_Q, K_M, K_K, K_LCORE = range(10)
 ST_OK, ST_OP_FAILED, ST_TRAN_FAILED, ST_DC_FAILED, ST_OVERFLOW = range(5)
 
@@ -51,7 +51,7 @@ class TsbError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("abstol", C.c_double), ("reltol", C.c_double), ("gmin", C.c_double),
-                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int), ("lane_refill", C.c_int)]
+                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int), ("lane_refill", C.c_int), ("grid_dt", C.c_double)]
 
 
 def lib_path() -> str:
@@ -489,10 +489,20 @@ class Transient(_BaseAnalysis):
         self.startTime, self.stopTime, self.timeStep, self.maxStep, self.useUIC = tStart, tStop, tStep, tMax, bool(uic)
         self.out = OUT_WAVE
         self.cap_rows = 0
+        self.grid_dt = 0.0        # OUT_GRID: spacing of the resampling grid (0: the clamped tStep)
+
+    def grid_times(self) -> np.ndarray:
+        """Times of the OUT_GRID rows: tstart + (k+1)*grid_dt, the last one clamped to tstop (tspice_b200.h)."""
+        tstep = min(self.timeStep, self.stopTime / 300)
+        g = self.grid_dt if self.grid_dt > 0 else tstep
+        n = max(1, int(np.floor((self.stopTime - self.startTime) / g * (1.0 + 1e-12) + 1e-9)))
+        return np.minimum(self.startTime + np.arange(1, n + 1, dtype=np.float64) * g, self.stopTime)
 
     def Execute(self):
         if self.batch is None:
             raise TsbError("circuit not set")                         # tran.go:78-80
+        if self.out & OUT_GRID:
+            self.opts.grid_dt = float(self.grid_dt)
         cap = self.cap_rows
         if (self.out & OUT_WAVE) and cap <= 0:
             # accepted steps are >= minStep apart except after rejections: 50*300 + slack rows always suffice

@@ -227,6 +227,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("#define TSB_MIN_BLOCKS " + std::to_string(cfg.min_blocks));
     e.line("#define TSB_SKIP_LINEAR_RESOLVE " + std::to_string(cfg.skip_linear ? 1 : 0));
     e.line("#define TSB_LANE_REFILL " + std::to_string(cfg.lane_refill && pl.has_nonlinear ? 1 : 0));
+    e.line("#define TSB_GRID " + std::to_string(cfg.grid ? 1 : 0));
     if (!cfg.extra_defines.empty()) e.os << cfg.extra_defines << "\n";     // development knob ($TSB_EXTRA_DEFINES)
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
@@ -484,14 +485,14 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK, TSB_MIN_BLOCKS) tsb_optran(TsbArgs a) {");
     e.line("    if (Ckt::HAS_NL && TSB_LANE_REFILL) {   // persistent lanes: finished lanes refill themselves from a.work_counter");
     e.line("        long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;");
-    e.line("        if (inst < a.n_inst) tsb_run_optran_instance<Ckt>(a, inst);");
+    e.line("        if (inst < a.n_run) tsb_run_optran_instance<Ckt>(a, inst);");
     e.line("        return;");
     e.line("    }");
-    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_inst; inst += (long long)gridDim.x * blockDim.x)");
+    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_run; inst += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_optran_instance<Ckt>(a, inst);");
     e.line("}");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
-    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_inst; inst += (long long)gridDim.x * blockDim.x)");
+    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_run; inst += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_dc_instance<Ckt>(a, inst);");
     e.line("}");
     return e.os.str();

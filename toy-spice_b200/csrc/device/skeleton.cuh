@@ -43,6 +43,10 @@ struct TsbArgs {
     int skip_linear_resolve;   // (compile-time TSB_SKIP_LINEAR_RESOLVE decides; kept for layout stability)
     unsigned long long* work_counter;   // lane refill: next unprocessed instance = first_free + atomicAdd(counter, 1)
     long long first_free;
+    double grid_dt;            // TSB_OUT_GRID: grid row k is at tstart + (k+1)*grid_dt (the last one clamped to tstop)
+    int n_grid;
+    long long n_run;           // instances [0, n_run) are processed (n_inst stays the array stride); < n_inst only
+                               // while the library times launch-bounds candidates on a sub-batch
 };
 
 #define TSB_ST_OK 0
@@ -55,6 +59,7 @@ struct TsbArgs {
 #define TSB_AN_DC 3
 #define TSB_OUT_WAVE 1
 #define TSB_OUT_STATS 2
+#define TSB_OUT_GRID 4
 
 extern __shared__ double tsb_smem[];
 
@@ -97,11 +102,12 @@ struct TsbSink {
     long long n_rows;
     bool overflow;
     double2* sm;                // this thread's first pair; pairs are TSB_BLOCK double2 apart
-    __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false) {
+    int grid_k;                 // TSB_OUT_GRID: next grid row to write
+    __device__ __forceinline__ TsbSink(const TsbArgs& a_, long long inst_) : a(a_), inst(inst_), n_rows(0), overflow(false), grid_k(0) {
         sm = reinterpret_cast<double2*>(tsb_smem) + threadIdx.x;   // launched with blockDim.x == TSB_BLOCK: every offset below is an immediate
     }
     __device__ __forceinline__ void begin(long long inst_) {      // (re)start for one instance
-        inst = inst_; n_rows = 0; overflow = false;
+        inst = inst_; n_rows = 0; overflow = false; grid_k = 0;
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
@@ -111,7 +117,31 @@ struct TsbSink {
             }
         }
     }
+    __device__ __forceinline__ double grid_time(int k) const {
+        const double t = __dadd_rn(a.tstart, __dmul_rn((double)(k + 1), a.grid_dt));   // two roundings in every build (no FMA)
+        return t < a.tstop ? t : a.tstop;
+    }
+    // TSB_OUT_GRID: every grid time in (previous stored row, this row] is written now, interpolated linearly between
+    // the two rows (the previous one is the `last` slot of the statistics pairs; before the first row: constant).
+    __device__ __forceinline__ void emit_grid(const double* row) {
+        const double t1 = row[0];
+        while (grid_k < a.n_grid) {
+            const double tg = grid_time(grid_k);
+            if (tg > t1) break;
+            double w = 1.0;
+            if (n_rows > 0) { const double t0 = sm[1 * TSB_BLOCK].y; w = (tg - t0) / (t1 - t0); }
+            double* o = a.wave + ((long long)grid_k * NCOL) * a.n_inst + inst;
+            __stcs(o, tg);
+#pragma unroll
+            for (int j = 1; j < NCOL; ++j) {
+                const double v0 = n_rows > 0 ? sm[(2 * j + 1) * TSB_BLOCK].y : row[j];
+                __stcs(o + j * a.n_inst, v0 + (row[j] - v0) * w);
+            }
+            ++grid_k;
+        }
+    }
     __device__ __forceinline__ void push(const double* row) {
+        if (TSB_GRID && (a.out_flags & TSB_OUT_GRID)) emit_grid(row);      // TSB_GRID: kernels specialised for grid output
         if (a.out_flags & TSB_OUT_WAVE) {
             if (n_rows < a.cap_rows) {
                 double* w = a.wave + (n_rows * NCOL) * a.n_inst + inst;
@@ -121,26 +151,47 @@ struct TsbSink {
         }
         if (a.out_flags & TSB_OUT_STATS) {
             if (n_rows == 0) sm[0] = make_double2(row[0], row[0]);     // column 0: the first row, kept in the {min, max} slot
+            // running min / max that ignore NaN samples (the accumulators start at +-inf and can never become NaN
+            // themselves), i.e. fmin / fmax semantics without their NaN fix-up code.  TSB_X_GROW = 1 tests all columns
+            // first and updates under one seldom-taken branch; measured slower than the unconditional selects
+            // (260 vs 277 ms, rlc 2^20), so it is off.
+            bool grow = !TSB_X_GROW;
 #pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
-                const double v = row[j];
-                if (j > 0) {
-                    // running min / max that ignore NaN samples (the accumulators start at +-inf and can never
-                    // become NaN themselves), i.e. fmin / fmax semantics without their NaN fix-up code
+            for (int j = 1; TSB_X_GROW && j < NCOL; ++j) {
+                const double2 mm = sm[(2 * j) * TSB_BLOCK];
+                grow |= (row[j] < mm.x) | (row[j] > mm.y);
+            }
+            if (grow) {
+#pragma unroll
+                for (int j = 1; j < NCOL; ++j) {
+                    const double v = row[j];
                     double2 mm = sm[(2 * j) * TSB_BLOCK];
                     mm.x = v < mm.x ? v : mm.x;
                     mm.y = v > mm.y ? v : mm.y;
                     sm[(2 * j) * TSB_BLOCK] = mm;
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
                 double2 sl = sm[(2 * j + 1) * TSB_BLOCK];
-                sl.x += v;
-                sl.y = v;
+                sl.x += row[j];
+                sl.y = row[j];
                 sm[(2 * j + 1) * TSB_BLOCK] = sl;
             }
         }
         ++n_rows;
     }
-    __device__ __forceinline__ void finish() {
+    __device__ __forceinline__ void finish(bool ok = true) {
+        if (TSB_GRID && (a.out_flags & TSB_OUT_GRID) && ok && n_rows > 0) {
+            // grid times after the last stored row (it was dropped by StoreTimeResult's de-duplication): hold its values
+            while (grid_k < a.n_grid) {
+                double* o = a.wave + ((long long)grid_k * NCOL) * a.n_inst + inst;
+                __stcs(o, grid_time(grid_k));
+#pragma unroll
+                for (int j = 1; j < NCOL; ++j) __stcs(o + j * a.n_inst, sm[(2 * j + 1) * TSB_BLOCK].y);
+                ++grid_k;
+            }
+        }
         if (a.out_flags & TSB_OUT_STATS) {
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
@@ -156,7 +207,7 @@ struct TsbSink {
                 a.stats[(long long)(3 * NCOL + j) * a.n_inst + inst] = sl.y;
             }
         }
-        a.rows[inst] = n_rows;
+        a.rows[inst] = (TSB_GRID && (a.out_flags & TSB_OUT_GRID)) ? (long long)grid_k : n_rows;
     }
 };
 
@@ -295,7 +346,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     };
     auto finish_instance = [&]() {
         if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
-        if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish();
+        if (a.analysis == TSB_AN_OP) a.rows[inst] = sink.n_rows; else sink.finish(status == TSB_ST_OK);
         a.status[inst] = status;
         a.counters[0 * a.n_inst + inst] = n_acc;
         a.counters[1 * a.n_inst + inst] = n_rej;
@@ -304,6 +355,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         a.counters[4 * a.n_inst + inst] = op_path;
         a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
         a.counters[6 * a.n_inst + inst] = n_exec;
+        a.counters[7 * a.n_inst + inst] = sink.n_rows;
     };
     begin_instance();
 
@@ -313,7 +365,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             finish_instance();
             if (!REFILL) break;
             inst = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
-            if (inst >= a.n_inst) break;
+            if (inst >= a.n_run) break;
             begin_instance();
             continue;
         }
@@ -503,6 +555,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     a.counters[4 * a.n_inst + inst] = 0;
     a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
     a.counters[6 * a.n_inst + inst] = n_sol + a.n_sweep;      // + the discarded stamp pass per sweep value
+    a.counters[7 * a.n_inst + inst] = sink.n_rows;
 }
 
 #endif  // TSB_SKELETON_CUH

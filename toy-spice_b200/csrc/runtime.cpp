@@ -50,6 +50,9 @@ struct TsbArgsHost {
     int skip_linear_resolve;
     unsigned long long* work_counter;
     long long first_free;
+    double grid_dt;
+    int n_grid;
+    long long n_run;
 };
 
 struct KernelModule {
@@ -66,6 +69,7 @@ struct tsb_ctx {
     std::string cache_dir;
     std::map<std::string, KernelModule> modules;      // key -> loaded module
     std::map<std::string, int> auto_choice;            // key of the min_blocks=auto source -> chosen min blocks
+    std::map<std::string, int> tuned;                  // ... -> choice confirmed by timing (autotune_min_blocks)
     int64_t launches = 0;
 };
 
@@ -93,6 +97,7 @@ struct tsb_batch {
     int* d_status = nullptr;
     unsigned long long* d_totals = nullptr;
     unsigned long long* d_work = nullptr;              // lane-refill work counter
+    bool grid_kernel = false;                          // the next module request wants the TSB_OUT_GRID specialisation
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -217,12 +222,16 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.min_blocks = o.min_blocks;            // 0 = "auto" placeholder (never compiled as such)
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
+    cfg.grid = b->grid_kernel;
     if (const char* x = getenv("TSB_EXTRA_DEFINES")) {          // development knob for A/B kernel experiments
         std::string item;
         for (const char* c = x;; ++c) {
             if (*c == ';' || *c == '\0') {
                 size_t eq = item.find('=');
-                if (!item.empty()) cfg.extra_defines += "#define " + (eq == std::string::npos ? item + " 1" : item.substr(0, eq) + " " + item.substr(eq + 1)) + "\n";
+                if (!item.empty()) {
+                    std::string name = eq == std::string::npos ? item : item.substr(0, eq);
+                    cfg.extra_defines += "#undef " + name + "\n#define " + name + " " + (eq == std::string::npos ? "1" : item.substr(eq + 1)) + "\n";
+                }
                 item.clear();
                 if (*c == '\0') break;
             } else item += *c;
@@ -263,7 +272,7 @@ int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, c
 const int TSB_SPILL_OK = 100;
 const int TSB_MAX_MIN_BLOCKS = 6;
 
-int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
+int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::string* autokey_out = nullptr) {
     tsb_ctx* ctx = b->ctx;
     std::vector<char> cubin;
     KernelInfo info;
@@ -271,8 +280,13 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out) {
     if (o.min_blocks <= 0) {
         o.min_blocks = 0;
         std::string autokey = source_key(generate_source(b->plan->p, make_config(b, o, dc_param)), compile_options_string(o));
+        if (autokey_out) *autokey_out = autokey;
         auto ch = ctx->auto_choice.find(autokey);
         int chosen = ch != ctx->auto_choice.end() ? ch->second : 0;
+        if (!chosen) {                       // a choice timed by an earlier process on this machine
+            std::ifstream f(ctx->cache_dir + "/" + autokey + ".tuned");
+            if (f && (f >> chosen) && chosen >= 1 && chosen <= 8) ctx->tuned[autokey] = chosen; else chosen = 0;
+        }
         if (!chosen) {
             std::ifstream f(ctx->cache_dir + "/" + autokey + ".auto");
             if (f) f >> chosen;
@@ -327,7 +341,7 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     const Plan& p = b->plan->p;
     const int64_t N = b->n_inst;
     int ncol = p.num_columns(analysis);
-    size_t wave_bytes = (out_flags & TSB_OUT_WAVE) ? (size_t)cap_rows * ncol * N * sizeof(double) : 0;
+    size_t wave_bytes = (out_flags & (TSB_OUT_WAVE | TSB_OUT_GRID)) ? (size_t)cap_rows * ncol * N * sizeof(double) : 0;
     size_t stats_bytes = (out_flags & TSB_OUT_STATS) ? (size_t)4 * ncol * N * sizeof(double) : 0;
     if (wave_bytes != b->wave_bytes) {
         cudaFree(b->d_wave); b->d_wave = nullptr; b->wave_bytes = 0;
@@ -351,14 +365,14 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
 int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args, bool persistent = false, int min_blocks = 0) {
     tsb_ctx* ctx = b->ctx;
     int block = o.block_size > 0 ? o.block_size : 128;
-    size_t smem = (args.out_flags & TSB_OUT_STATS) ? (size_t)4 * b->plan->p.num_columns(TSB_AN_TRAN) * block * sizeof(double) : 0;
+    size_t smem = (args.out_flags & (TSB_OUT_STATS | TSB_OUT_GRID)) ? (size_t)4 * b->plan->p.num_columns(TSB_AN_TRAN) * block * sizeof(double) : 0;
     if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (b->n_inst + block - 1) / block;
+    long long blocks = (args.n_run + block - 1) / block;
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
     if (blocks < 1) blocks = 1;
     if (!persistent) {
         args.work_counter = b->d_work;          // static mapping: the first fetch of every lane is already out of range
-        args.first_free = b->n_inst;
+        args.first_free = args.n_run;
     } else {
         // Lane refill (skeleton.cuh): a resident grid of SMs x blocks-per-SM; lanes that finish an instance take
         // the next one from the work counter.  Sized from the occupancy the launch-bounds choice bought.
@@ -383,6 +397,7 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     tsb_ctx* ctx = b->ctx;
     memset(&a, 0, sizeof a);
     a.n_inst = b->n_inst;
+    a.n_run = b->n_inst;
     if (b->slot_ptr.size() > TSB_MAX_VARYING) return fail(ctx, TSB_E_UNSUPPORTED, "too many per-instance parameters (max 64)");
     for (size_t s = 0; s < b->slot_ptr.size(); ++s) a.pv[s] = b->slot_ptr[s];
     size_t ub = b->uniform.size() * sizeof(double);
@@ -413,6 +428,48 @@ tsb_opts resolve(const tsb_opts* o, const Plan& plan) {
     return r;
 }
 
+// Launch-bounds autotuning.  The spill rule above is a static prior; what it trades (resident warps against spilled
+// bytes) moves with every change of the generated code, and the measured optimum was 1-2 blocks/SM above the rule
+// for the nonlinear decks (profiles/r01_notes.md).  So the first transient run of a large batch times the
+// candidates {rule, rule+1, rule+2} on a sub-batch of two waves of instances — the very analysis that is about to
+// run, writing into the result arrays the real run overwrites — and keeps the fastest for the process (and, via
+// <autokey>.tuned in the kernel cache, for later processes).  Results do not depend on the choice: register
+// allocation does not change the arithmetic.  $TSB_AUTOTUNE=0 disables.
+const int64_t TSB_TUNE_MIN_INSTANCES = 1 << 15;
+
+int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string& autokey, int rule_choice,
+                        const TsbArgsHost& a_full, bool persistent) {
+    tsb_ctx* ctx = b->ctx;
+    const int block = o_auto.block_size > 0 ? o_auto.block_size : 128;
+    long long n_sub = (long long)ctx->sms * TSB_MAX_MIN_BLOCKS * block * 2;
+    if (n_sub > b->n_inst) n_sub = b->n_inst;
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
+    int best = rule_choice; float best_ms = 0.f;
+    for (int mb = rule_choice; mb <= TSB_MAX_MIN_BLOCKS && mb <= rule_choice + 2; ++mb) {
+        tsb_opts o = o_auto; o.min_blocks = mb;
+        KernelModule* m = nullptr;
+        int rc = get_module(b, o, -1, &m);
+        if (rc != TSB_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        float ms = 0.f;
+        for (int rep = 0; rep < 2; ++rep) {              // rep 0 loads the module and warms the clocks
+            TsbArgsHost a = a_full; a.n_run = n_sub;
+            CU(ctx, cudaEventRecord(e0, ctx->stream));
+            if ((rc = launch(b, o, m->optran, a, persistent, m->min_blocks)) != TSB_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+            CU(ctx, cudaEventRecord(e1, ctx->stream));
+            CU(ctx, cudaEventSynchronize(e1));
+            CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        }
+        if (mb == rule_choice || ms < best_ms * 0.98f) { best = mb; best_ms = ms; }     // a later candidate must win by 2 %
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->auto_choice[autokey] = best;
+    ctx->tuned[autokey] = best;
+    std::ofstream f(ctx->cache_dir + "/" + autokey + ".tuned");
+    f << best << "\n";
+    return TSB_OK;
+}
+
 int check_batch(tsb_batch* b) {
     if (!b || !b->plan) return TSB_E_INVALID;
     if (!b->ctx) return fail(nullptr, TSB_E_CUDA, "batch has no GPU context (host-only plan): analyses run on the GPU only");
@@ -427,7 +484,7 @@ extern "C" {
 void tsb_default_opts(tsb_opts* o) {
     if (!o) return;
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
-    o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0;
+    o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0; o->grid_dt = 0.0;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -700,22 +757,48 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
     if (!(tstop > 0) || !(tstep > 0)) return fail(ctx, TSB_E_INVALID, "tstop and tstep must be positive");
-    if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
+    if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS | TSB_OUT_GRID))) return fail(ctx, TSB_E_INVALID, "no output selected");
+    if ((out_flags & TSB_OUT_WAVE) && (out_flags & TSB_OUT_GRID)) return fail(ctx, TSB_E_INVALID, "TSB_OUT_WAVE and TSB_OUT_GRID share the waveform buffer: select one");
     if ((out_flags & TSB_OUT_WAVE) && wave_cap_rows <= 0) return fail(ctx, TSB_E_INVALID, "wave_cap_rows must be positive");
     tsb_opts o = resolve(opts, b->plan->p);
-    CU(ctx, cudaSetDevice(ctx->device));
-    KernelModule* m = nullptr;
-    if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
-    if ((rc = alloc_results(b, TSB_AN_TRAN, out_flags, (out_flags & TSB_OUT_WAVE) ? wave_cap_rows : 0, 0)) != TSB_OK) return rc;
-    TsbArgsHost a;
-    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
     // NewTransient (tran.go:29-55)
     if (tstep > tstop / 300) tstep = tstop / 300;
     double minstep = tstep / 50.0;
     if (tmax == 0) tmax = tstep;
+    double grid_dt = 0.0; int64_t n_grid = 0;
+    if (out_flags & TSB_OUT_GRID) {
+        out_flags |= TSB_OUT_STATS;          // the previous stored row lives in the statistics' `last` slots
+        grid_dt = o.grid_dt > 0 ? o.grid_dt : tstep;
+        double span = tstop - tstart;
+        if (!(span > 0) || !(grid_dt > 0)) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID needs tstart < tstop and a positive grid spacing");
+        double q = span / grid_dt;
+        if (q > 1e7) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID: more than 1e7 grid points");
+        n_grid = (int64_t)floor(q * (1.0 + 1e-12) + 1e-9);
+        if (n_grid < 1) n_grid = 1;
+        wave_cap_rows = n_grid;
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    KernelModule* m = nullptr;
+    b->grid_kernel = (out_flags & TSB_OUT_GRID) != 0;
+    std::string autokey;
+    rc = get_module(b, o, -1, &m, &autokey);
+    if (rc != TSB_OK) { b->grid_kernel = false; return rc; }
+    if ((rc = alloc_results(b, TSB_AN_TRAN, out_flags, (out_flags & (TSB_OUT_WAVE | TSB_OUT_GRID)) ? wave_cap_rows : 0, 0)) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
     a.analysis = TSB_AN_TRAN; a.uic = uic;
     a.tstart = tstart; a.tstop = tstop; a.tstep = tstep; a.maxstep = tmax; a.minstep = minstep;
-    return launch(b, o, m->optran, a, b->plan->p.has_nonlinear && o.lane_refill != 0, m->min_blocks);
+    a.grid_dt = grid_dt; a.n_grid = (int)n_grid;
+    const bool persistent = b->plan->p.has_nonlinear && o.lane_refill != 0;
+    const char* tune_env = getenv("TSB_AUTOTUNE");
+    if (o.min_blocks <= 0 && !autokey.empty() && b->n_inst >= TSB_TUNE_MIN_INSTANCES && !ctx->tuned.count(autokey) &&
+        !(tune_env && *tune_env == '0')) {
+        rc = autotune_min_blocks(b, o, autokey, m->min_blocks, a, persistent);
+        if (rc == TSB_OK) rc = get_module(b, o, -1, &m);
+        if (rc != TSB_OK) { b->grid_kernel = false; return rc; }
+    }
+    b->grid_kernel = false;
+    return launch(b, o, m->optran, a, persistent, m->min_blocks);
 }
 
 int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts) {
@@ -725,6 +808,7 @@ int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc,
     if (src_dev < 0 || src_dev >= (int)p.devs.size() || p.devs[src_dev].kind != TSB_V)
         return fail(ctx, TSB_E_INVALID, "source not found");                       // dc.go:47-68
     if (!(inc > 0)) return fail(ctx, TSB_E_INVALID, "sweep increment must be positive");
+    if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID applies to transient analysis only");
     if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
     std::vector<double> sweep;
     for (double v = start; v <= stop; v += inc) { sweep.push_back(v); if (sweep.size() > (1u << 24)) break; }   // dc.go:36-42
