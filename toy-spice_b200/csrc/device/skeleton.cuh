@@ -261,14 +261,14 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     double time = 0.0, dt = a.minstep;
     double last_key = -1.0;
     TsbTimeKeyer keyer; keyer.reset();
-    int n_acc = 0, n_rej = 0, n_skip = 0, n_bad = 0;   // accepted, rejected, rejected without executing the solve, failed solves
+    int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves
     while (time < a.tstop) {
         double next_time = time + dt;
         if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
         __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
         const double rdt = TSB_X_NB ? tsb_rcp_dt(dt) : 1.0 / dt;
         const double lte = c.lte(dt, rdt);
-        if (TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; ++n_skip; continue; }
+        if (TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
         bool solved;
         if (TSB_X_NB) {
             const bool in_range = c.eval_sources_nb(time);
@@ -293,7 +293,9 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     }
     n_acc_out += n_acc; n_rej_out += n_rej;
     const int failed = status == TSB_ST_TRAN_FAILED ? 1 : 0;
-    n_exec_out += n_acc + n_rej - n_skip + failed;
+    // rejected attempts whose solve WAS executed: those rejected for a failing solve (n_bad - failed), or all of
+    // them when the truncation-error test runs after the solve
+    n_exec_out += n_acc + (TSB_X_PRELTE ? n_bad - failed : n_rej) + failed;
     n_sol_tran_out += 2LL * (n_acc + n_rej) - n_bad + 2 * failed;      // the reference stops at a failing solve, else runs two
 }
 

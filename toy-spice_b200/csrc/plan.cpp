@@ -30,7 +30,8 @@ int device_num_outputs(const Dev& d) {
 
 static int state_size(int kind) {
     switch (kind) {
-    case TSB_C: case TSB_L: return 4;
+    case TSB_C: return 2;      // V0, V1 (the charges q0 = C*V0, q1 = C*V1 are recomputed, models.cuh)
+    case TSB_L: return 4;
     case TSB_D: return 1;
     case TSB_Q: return 3;
     case TSB_M: return 9;
