@@ -213,6 +213,24 @@ int tsb_result_stats_all(tsb_batch* batch, double* out /*[4][n_columns][n_inst]*
  * OP solves (reference-equivalent counts) and executed factor+solve passes. */
 int tsb_result_totals(tsb_batch* batch, int64_t totals[5]);
 
+/* ---- operator level: batched factor + solve -------------------------------------------------------
+ * Drop-in for the reference's matrix OPERATOR (pkg/matrix/circuit.go:126-150 Solve() = sparse Factor + Solve, fed by
+ * AddElement / AddRHS, matrix/device.go:3-8) for hosts that stamp themselves: n_inst systems A x = b of one order
+ * n <= 32 that share one pivot order.  One circuit per warp (8 / 16 / 32 lanes per system), matrix in registers,
+ * pivot-row broadcast by warp shuffles (csrc/lu_warp.cu).  Layout: instance-major, A[inst][row][col] row-major
+ * (0-based), b[inst][row], x[inst][col]; status[inst] = 0, or 1 for a zero pivot ("matrix factorization failed").
+ * pivot_row[k] / pivot_col[k] (k = 0..n-1): 1-based external row / column eliminated at step k+1.
+ * strict_fp = 1 reproduces Sparse 1.3's rounding (no FMA contraction, IEEE reciprocals, spSolve's summation order). */
+/* The reference's symbolic pass on a nominal matrix: the order its first Factor() picks (Markowitz products over the
+ * structurally dense matrix, relative threshold 1e-3, diagonal preference), Translate numbering =
+ * row-major first touch.  Host only (ctx not needed). */
+int tsb_lu_order(int n, const double* A_nominal, int* pivot_row, int* pivot_col);
+int tsb_lu_solve_batched(tsb_ctx* ctx, int n, const int* pivot_row, const int* pivot_col, const double* A, const double* b,
+                         double* x, int32_t* status, int64_t n_inst, int strict_fp);
+/* Same with every array already in HBM (device pointers); asynchronous on the context's stream. */
+int tsb_lu_solve_batched_dev(tsb_ctx* ctx, int n, const int* pivot_row, const int* pivot_col, uint64_t A_dev, uint64_t b_dev,
+                             uint64_t x_dev, uint64_t status_dev, int64_t n_inst, int strict_fp);
+
 /* ---- introspection / build-time support -------------------------------------------------------*/
 /* CUDA source of the kernels specialised for this batch configuration (which parameters vary). */
 int tsb_batch_kernel_source(tsb_batch* batch, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed);

@@ -49,6 +49,8 @@ def lib():
         L.orc_go_sin.restype = C.c_double
         L.orc_go_sin.argtypes = [C.c_double]
         L.orc_format_value_factor.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        L.orc_lu_batch.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -150,3 +152,20 @@ def format_value_factor(v: float) -> str:
     buf = C.create_string_buffer(64)
     lib().orc_format_value_factor(v, buf, 64)
     return buf.value.decode()
+
+
+def lu_batch(A_nominal: np.ndarray, A: np.ndarray, b: np.ndarray):
+    """Sparse 1.3 restatement on a batch of dense systems, order frozen on `A_nominal` (orc_lu_batch).
+    Returns x [n_inst, n], status [n_inst], (pivot_row, pivot_col) 1-based."""
+    n = A_nominal.shape[0]
+    A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    An = np.ascontiguousarray(A_nominal, dtype=np.float64)
+    n_inst = A.shape[0]
+    x = np.zeros((n_inst, n)); st = np.zeros(n_inst, dtype=np.int32)
+    pr = (C.c_int * n)(); pc = (C.c_int * n)()
+    dp = C.POINTER(C.c_double)
+    rc = lib().orc_lu_batch(n, An.ctypes.data_as(dp), n_inst, A.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp),
+                            st.ctypes.data_as(C.POINTER(C.c_int32)), pr, pc)
+    if rc != 0:
+        raise RuntimeError("oracle: nominal matrix is singular")
+    return x, st, (np.array(pr[:]), np.array(pc[:]))

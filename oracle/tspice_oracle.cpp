@@ -249,4 +249,32 @@ int orc_format_value_factor(double v, char* buf, int cap) {
 }
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
+// The reference's matrix operator on a batch of dense systems (pkg/matrix/circuit.go:57-63 SetupElements creates every
+// element; :126-150 Solve = Factor + Solve).  The first Factor() — order-and-factor — runs on A_nominal and freezes the
+// order (the product's contract: the order of the NOMINAL instance); every instance is then Clear / AddElement /
+// Factor (re-use) / Solve.  prow / pcol (n entries, 1-based external) return the chosen order.  Checker for
+// tsb_lu_solve_batched (tests/test_lu_operator.py).
+int orc_lu_batch(int n, const double* A_nominal, int64_t n_inst, const double* A, const double* b, double* x, int32_t* status,
+                 int* prow, int* pcol) {
+    Sparse13 m(n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) m.get_element(i + 1, j + 1) += A_nominal[i * n + j];
+    if (m.factor() >= SP_ZERO_DIAG) return -1;
+    for (int k = 1; k <= n; ++k) { prow[k - 1] = m.pivot_ext_row(k); pcol[k - 1] = m.pivot_ext_col(k); }
+    std::vector<double> rhs(n + 1), sol(n + 1);
+    for (int64_t q = 0; q < n_inst; ++q) {
+        m.clear();
+        const double* Aq = A + q * n * n;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) m.get_element(i + 1, j + 1) += Aq[i * n + j];
+        if (m.factor() >= SP_ZERO_DIAG) { status[q] = 1; for (int i = 0; i < n; ++i) x[q * n + i] = 0.0; continue; }
+        rhs[0] = 0.0;
+        for (int i = 0; i < n; ++i) rhs[i + 1] = b[q * n + i];
+        m.solve(rhs, sol);
+        for (int i = 0; i < n; ++i) x[q * n + i] = sol[i + 1];
+        status[q] = 0;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,110 @@
+"""Operator-level drop-in (tsb_lu_order / tsb_lu_solve_batched, csrc/lu_warp.cu): the reference's matrix operator
+(pkg/matrix/circuit.go:126-150 Solve = sparse Factor + Solve on the dense structure SetupElements leaves) over a batch,
+one circuit per warp.  Checker: the oracle's Sparse 1.3 restatement (orc_lu_batch)."""
+import numpy as np
+import pytest
+
+import parity_util as PU
+
+T, O = PU.T, PU.O
+
+
+def mna_like(n, n_inst, seed, zero_diag_rows=2):
+    """Synthetic MNA-shaped systems: a diagonally dominant conductance block plus `zero_diag_rows` voltage-source
+    style rows / columns (+-1 off the diagonal, 0 on it) so the order cannot be the identity."""
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(-1e-3, 0.0, (n, n)) * (rng.random((n, n)) < 0.35)
+    base = base + base.T
+    np.fill_diagonal(base, 0.0)
+    np.fill_diagonal(base, -base.sum(axis=1) + 1e-4)
+    k = min(zero_diag_rows, n // 3)
+    for q in range(k):
+        r, c = n - 1 - q, q
+        base[r, :] = 0.0; base[:, r] = 0.0
+        base[r, c] = 1.0; base[c, r] = 1.0
+    scale = np.exp(rng.uniform(np.log(0.5), np.log(2.0), (n_inst, n, n)))
+    A = base[None] * scale
+    if k:
+        for q in range(k):
+            r, c = n - 1 - q, q
+            A[:, r, c] = 1.0; A[:, c, r] = 1.0
+    b = rng.normal(size=(n_inst, n))
+    b[:, : max(1, n // 4)] = 0.0          # structural zeros in the right-hand side (spSolve skips them)
+    return base, A, b
+
+
+@pytest.mark.parametrize("n", [3, 8, 13, 32])
+def test_symbolic_pass_on_a_dense_matrix_matches_the_oracle(built, n):
+    base, A, b = mna_like(n, 1, 100 + n)
+    pr, pc = T.lu_order(base)
+    _, _, (opr, opc) = O.lu_batch(base, A, b)
+    assert sorted(pr) == list(range(1, n + 1)) and sorted(pc) == list(range(1, n + 1))
+    assert np.array_equal(pr, opr) and np.array_equal(pc, opc)
+
+
+def test_order_rejects_singular_and_oversize(built):
+    with pytest.raises(T.TsbError):
+        T.lu_order(np.zeros((4, 4)))
+    with pytest.raises(T.TsbError):
+        T.lu_order(np.eye(33))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 3, 5, 8, 10, 16, 21, 32])
+def test_strict_build_is_bit_identical_to_sparse13(ctx, n):
+    n_inst = 257                                   # not a multiple of the systems-per-block of any lane width
+    base, A, b = mna_like(n, n_inst, 7 * n)
+    order = T.lu_order(base)
+    x, st = ctx.lu_solve_batched(A, b, order, strict=True)
+    xo, sto, _ = O.lu_batch(base, A, b)
+    assert np.array_equal(st, sto) and np.all(st == 0)
+    assert np.array_equal(x, xo), float(np.max(np.abs(x - xo)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [5, 16, 32])
+def test_fast_build_within_tolerance_and_zero_pivot_is_data(ctx, n):
+    n_inst = 1000
+    base, A, b = mna_like(n, n_inst, 11 * n)
+    A[17] = 0.0                                    # a singular instance: status 1, never a call failure
+    order = T.lu_order(base)
+    x, st = ctx.lu_solve_batched(A, b, order, strict=False)
+    xo, sto, _ = O.lu_batch(base, A, b)
+    assert np.array_equal(st, sto) and st[17] == 1 and st.sum() == 1
+    ok = st == 0
+    # the fast build re-associates the elimination (multipliers instead of a scaled pivot row), so it is held to the
+    # normwise backward error of a stable LU, and to the 1e-9 contract against the oracle where the system is
+    # well-conditioned enough for that to be meaningful (forward error <= cond * backward error)
+    Aok, xok, bok = A[ok], x[ok], b[ok]
+    res = np.einsum("qij,qj->qi", Aok, xok) - bok
+    den = np.abs(Aok).sum(axis=2).max(axis=1) * np.abs(xok).max(axis=1) + np.abs(bok).max(axis=1)
+    berr = np.abs(res).max(axis=1) / den
+    # the frozen (nominal) pivot order costs some instances a few digits in BOTH implementations: compare with the
+    # backward error of the oracle's own solution
+    berr_o = np.abs(np.einsum("qij,qj->qi", Aok, xo[ok]) - bok).max(axis=1) / den
+    assert berr.max() <= 8 * berr_o.max() + 1e-15 and np.median(berr) <= 8 * np.median(berr_o) + 1e-16, \
+        (float(berr.max()), float(berr_o.max()), float(np.median(berr)), float(np.median(berr_o)))
+    cond = np.linalg.cond(Aok[:64])
+    ferr = np.abs(xok[:64] - xo[ok][:64]).max(axis=1) / np.abs(xo[ok][:64]).max(axis=1)
+    assert np.all(ferr <= 1e-15 * cond + 1e-13), (float(ferr.max()), float(cond.max()))
+    well = cond < 1e5
+    assert np.all(ferr[well] <= 1e-9)
+
+
+@pytest.mark.gpu
+def test_device_pointer_entry_and_permutation_equivariance(ctx):
+    import torch
+    n, n_inst = 16, 1 << 16
+    base, A, b = mna_like(n, n_inst, 5)
+    order = T.lu_order(base)
+    dA, db = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    dx = torch.empty_like(db); dst = torch.empty(n_inst, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.lu_solve_batched_dev(n, n_inst, dA.data_ptr(), db.data_ptr(), dx.data_ptr(), dst.data_ptr(), order, strict=True)
+    import importlib
+    importlib.import_module("toy-spice_b200")   # noqa
+    torch.cuda.synchronize()
+    x1 = dx.cpu().numpy()
+    perm = np.random.default_rng(1).permutation(n_inst)
+    x2, st2 = ctx.lu_solve_batched(A[perm], b[perm], order, strict=True)
+    assert np.array_equal(x2, x1[perm]) and np.all(st2 == 0) and int(dst.sum()) == 0

@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "tsb_batch_sync", "tsb_result_dims", "tsb_result_dev_ptrs", "tsb_result_rows", "tsb_result_status",
     "tsb_result_counters", "tsb_result_waveform", "tsb_result_wave_all", "tsb_result_stats_all",
     "tsb_result_totals", "tsb_batch_kernel_source", "tsb_batch_kernel_key", "tsb_ctx_launch_count",
+    "tsb_lu_order", "tsb_lu_solve_batched", "tsb_lu_solve_batched_dev",
 ]
 
 
@@ -116,6 +117,9 @@ def lib():
             "tsb_result_totals": (i32, [vp, P(i64)]),
             "tsb_batch_kernel_source": (i32, [vp, P(Opts), C.c_char_p, i64, P(i64)]),
             "tsb_batch_kernel_key": (i32, [vp, P(Opts), C.c_char_p, i32]),
+            "tsb_lu_order": (i32, [i32, P(dbl), P(i32), P(i32)]),
+            "tsb_lu_solve_batched": (i32, [vp, i32, P(i32), P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int32), i64, i32]),
+            "tsb_lu_solve_batched_dev": (i32, [vp, i32, P(i32), P(i32), u64, u64, u64, u64, i64, i32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -123,6 +127,19 @@ def lib():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def lu_order(A_nominal: np.ndarray):
+    """tsb_lu_order: the reference's first-factorisation pivot order on a nominal dense matrix (host only).
+    Returns (pivot_row, pivot_col), 1-based external indices per elimination step."""
+    A = np.ascontiguousarray(A_nominal, dtype=np.float64)
+    n = A.shape[0]
+    pr = np.zeros(n, dtype=np.int32); pc = np.zeros(n, dtype=np.int32)
+    rc = lib().tsb_lu_order(n, A.ctypes.data_as(C.POINTER(C.c_double)), pr.ctypes.data_as(C.POINTER(C.c_int)),
+                            pc.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise TsbError("tsb_lu_order: singular nominal matrix or order outside 1..32")
+    return pr, pc
 
 
 def default_opts(**kw) -> Opts:
@@ -168,6 +185,26 @@ class Context:
     @property
     def launch_count(self) -> int:
         return lib().tsb_ctx_launch_count(self.h)
+
+    # -- operator level: the reference's matrix operator over a batch (tsb_lu_solve_batched) ---------------------
+    def lu_solve_batched(self, A: np.ndarray, b: np.ndarray, order, strict: bool = False):
+        """A [n_inst, n, n], b [n_inst, n] host arrays -> (x [n_inst, n], status [n_inst])."""
+        A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        n_inst, n = b.shape
+        pr = np.ascontiguousarray(order[0], dtype=np.int32); pc = np.ascontiguousarray(order[1], dtype=np.int32)
+        x = np.zeros((n_inst, n)); st = np.zeros(n_inst, dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        self._check(lib().tsb_lu_solve_batched(self.h, n, pr.ctypes.data_as(ip), pc.ctypes.data_as(ip), A.ctypes.data_as(dp),
+                                               b.ctypes.data_as(dp), x.ctypes.data_as(dp), st.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               n_inst, int(strict)), "tsb_lu_solve_batched")
+        return x, st
+
+    def lu_solve_batched_dev(self, n: int, n_inst: int, A_ptr: int, b_ptr: int, x_ptr: int, status_ptr: int, order, strict: bool = False):
+        """Same with device pointers (e.g. torch tensors' data_ptr()); asynchronous on the context's stream."""
+        pr = np.ascontiguousarray(order[0], dtype=np.int32); pc = np.ascontiguousarray(order[1], dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        self._check(lib().tsb_lu_solve_batched_dev(self.h, n, pr.ctypes.data_as(ip), pc.ctypes.data_as(ip), A_ptr, b_ptr, x_ptr,
+                                                   status_ptr, n_inst, int(strict)), "tsb_lu_solve_batched_dev")
 
     def close(self):
         if self.h:

@@ -17,11 +17,14 @@
 #include <mutex>
 #include <sstream>
 #include "tsb_internal.hpp"
+#include "hostlu.hpp"
 
 namespace tsb {
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t launch_totals(const long long* counters, long long n_inst, unsigned long long* totals, int sms, cudaStream_t s);
 cudaError_t launch_fill_i64(long long* p, long long n, long long v, int sms, cudaStream_t s);
+cudaError_t launch_lu_warp(const double* A, const double* b, double* x, int* status, long long n_inst, int n, const int* prow,
+                           const int* pcol, int strict, int sms, cudaStream_t s);
 }
 
 using namespace tsb;
@@ -901,6 +904,76 @@ int tsb_result_totals(tsb_batch* b, int64_t totals[5]) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < 5; ++k) totals[k] = (int64_t)h[k];
     return TSB_OK;
+}
+
+// ---- operator level: batched factor + solve (lu_warp.cu) -------------------------------------------
+int tsb_lu_order(int n, const double* A_nominal, int* pivot_row, int* pivot_col) {
+    if (n < 1 || n > 32 || !A_nominal || !pivot_row || !pivot_col) return TSB_E_INVALID;
+    MarkowitzLU lu(n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) lu.add(i + 1, j + 1, A_nominal[i * n + j]);      // dense structure, as SetupElements leaves it
+    if (!lu.order_and_factor()) return TSB_E_INVALID;
+    for (int k = 1; k <= n; ++k) { pivot_row[k - 1] = lu.pivot_row(k); pivot_col[k - 1] = lu.pivot_col(k); }
+    return TSB_OK;
+}
+
+static int lu_check_order(tsb_ctx* ctx, int n, const int* pr, const int* pc, int* prow0, int* pcol0) {
+    if (n < 1 || n > 32) return fail(ctx, TSB_E_UNSUPPORTED, "tsb_lu_solve_batched: order must be 1..32 (one row per lane)");
+    unsigned seen_r = 0, seen_c = 0;
+    for (int k = 0; k < n; ++k) {
+        if (pr[k] < 1 || pr[k] > n || pc[k] < 1 || pc[k] > n) return fail(ctx, TSB_E_INVALID, "pivot order: index out of range");
+        seen_r |= 1u << (pr[k] - 1); seen_c |= 1u << (pc[k] - 1);
+        prow0[k] = pr[k] - 1; pcol0[k] = pc[k] - 1;
+    }
+    const unsigned full = n == 32 ? 0xffffffffu : ((1u << n) - 1);
+    if (seen_r != full || seen_c != full) return fail(ctx, TSB_E_INVALID, "pivot order: not a permutation");
+    return TSB_OK;
+}
+
+int tsb_lu_solve_batched_dev(tsb_ctx* ctx, int n, const int* pivot_row, const int* pivot_col, uint64_t A_dev, uint64_t b_dev,
+                             uint64_t x_dev, uint64_t status_dev, int64_t n_inst, int strict_fp) {
+    if (!ctx) return TSB_E_CUDA;
+    if (!pivot_row || !pivot_col || !A_dev || !b_dev || !x_dev || !status_dev || n_inst < 0) return TSB_E_INVALID;
+    int h[64];
+    int rc = lu_check_order(ctx, n, pivot_row, pivot_col, h, h + 32);
+    if (rc != TSB_OK) return rc;
+    if (n_inst == 0) return TSB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int* d_perm = nullptr;
+    CU(ctx, cudaMallocAsync(&d_perm, sizeof h, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_perm, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_lu_warp((const double*)(uintptr_t)A_dev, (const double*)(uintptr_t)b_dev, (double*)(uintptr_t)x_dev,
+                                   (int*)(uintptr_t)status_dev, n_inst, n, d_perm, d_perm + 32, strict_fp != 0, ctx->sms, ctx->stream);
+    ++ctx->launches;
+    cudaFreeAsync(d_perm, ctx->stream);
+    CU(ctx, e);
+    return TSB_OK;
+}
+
+int tsb_lu_solve_batched(tsb_ctx* ctx, int n, const int* pivot_row, const int* pivot_col, const double* A, const double* b,
+                         double* x, int32_t* status, int64_t n_inst, int strict_fp) {
+    if (!ctx) return TSB_E_CUDA;
+    if (!A || !b || !x || !status || n_inst < 0 || n < 1 || n > 32) return TSB_E_INVALID;
+    if (n_inst == 0) return TSB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t na = (size_t)n_inst * n * n * sizeof(double), nb = (size_t)n_inst * n * sizeof(double);
+    double *dA = nullptr, *db = nullptr, *dx = nullptr; int* dst = nullptr;
+    CU(ctx, cudaMalloc(&dA, na));
+    if (cudaMalloc(&db, nb) != cudaSuccess || cudaMalloc(&dx, nb) != cudaSuccess || cudaMalloc(&dst, (size_t)n_inst * sizeof(int)) != cudaSuccess) {
+        cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dst); cudaGetLastError();
+        return fail(ctx, TSB_E_NOMEM, "tsb_lu_solve_batched: out of device memory");
+    }
+    int rc = TSB_OK;
+    if (cudaMemcpyAsync(dA, A, na, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(db, b, nb, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = fail(ctx, TSB_E_CUDA, "H2D copy failed");
+    if (rc == TSB_OK) rc = tsb_lu_solve_batched_dev(ctx, n, pivot_row, pivot_col, (uint64_t)(uintptr_t)dA, (uint64_t)(uintptr_t)db,
+                                                    (uint64_t)(uintptr_t)dx, (uint64_t)(uintptr_t)dst, n_inst, strict_fp);
+    if (rc == TSB_OK && (cudaMemcpyAsync(x, dx, nb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                         cudaMemcpyAsync(status, dst, (size_t)n_inst * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(ctx->stream) != cudaSuccess))
+        rc = fail(ctx, TSB_E_CUDA, std::string("tsb_lu_solve_batched: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dst);
+    return rc;
 }
 
 // ---- introspection -------------------------------------------------------------------------------
