@@ -1,5 +1,5 @@
 """Development driver (not a pytest file): throughput of the operator-level batched LU (csrc/lu_warp.cu), device
-pointers, CUDA events.  Usage: python tests/gpu_lu_perf.py [bytes_of_A, default 2e9]"""
+pointers, CUDA events.  Usage: python tests/gpu_lu_perf.py [bytes_of_A, default 2e9] [n,n,...]"""
 import sys
 
 import numpy as np
@@ -22,7 +22,8 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     peak = ctx.measure_fp64_peak()
     print(f"fp64 peak {peak:.1f} TFLOP/s")
-    for n in (3, 5, 8, 10, 16, 24, 32):
+    ns = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (3, 5, 8, 10, 16, 24, 32)
+    for n in ns:
         n_inst = int(min(1 << 24, budget // (n * n * 8)))
         base, A1, b1 = mna_like(n, 4096, n)
         order = T.lu_order(base)

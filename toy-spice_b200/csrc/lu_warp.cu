@@ -49,9 +49,9 @@ constexpr int LU_THREADS = 128;
 
 // A: [n_inst][n][n] row-major, b / x: [n_inst][n]  (instance-major: what a per-instance stamper produces)
 template <int W, bool STRICT>
-__global__ void __launch_bounds__(LU_THREADS) tsb_k_lu_warp(const double* __restrict__ A, const double* __restrict__ b,
+__global__ void __launch_bounds__(LU_THREADS, 4) tsb_k_lu_warp(const double* __restrict__ A, const double* __restrict__ b,
                                                             double* __restrict__ x, int* __restrict__ status, long long n_inst,
-                                                            int n, const int* __restrict__ prow, const int* __restrict__ pcol) {
+                                                            int n, const int* __restrict__ prow, const int* __restrict__ pcol, int fence) {
     constexpr int GROUPS = LU_THREADS / W;          // systems per block and pass
     constexpr int LD = W + 1;                       // padded row stride of the staging tile (bank-conflict-free columns)
     extern __shared__ double smem[];
@@ -135,13 +135,17 @@ __global__ void __launch_bounds__(LU_THREADS) tsb_k_lu_warp(const double* __rest
             // (no `k < n` tests: the identity padding makes the steps beyond n exact no-ops, and they are the short ones)
 #pragma unroll
             for (int k = 0; k < W; ++k) {
-                const double piv = shfl_d(a[k], k, W);
-                ok = ok && (piv != 0.0);
-                const double rp = rcp_fast(piv);
-                const double m = lane > k ? a[k] * rp : 0.0;          // 0 for rows that are finished: their update is a no-op
-                a[k] = lane == k ? rp : (lane > k ? m : a[k]);        // rows above k keep U_ik for the back-substitution
+                // `fence` is the lane width passed at run time, i.e. always true: the uniform branch keeps ptxas from
+                // hoisting the shuffles of later steps across this one (255 registers and spills without it)
+                if (k < fence) {
+                    const double piv = shfl_d(a[k], k, W);
+                    ok = ok && (piv != 0.0);
+                    const double rp = rcp_fast(piv);
+                    const double m = lane > k ? a[k] * rp : 0.0;      // 0 for rows that are finished: their update is a no-op
+                    a[k] = lane == k ? rp : (lane > k ? m : a[k]);    // rows above k keep U_ik for the back-substitution
 #pragma unroll
-                for (int j = k + 1; j < W; ++j) a[j] = fma(-shfl_d(a[j], k, W), m, a[j]);
+                    for (int j = k + 1; j < W; ++j) a[j] = fma(-shfl_d(a[j], k, W), m, a[j]);
+                }
             }
             // ---- forward: y_i = b_i - sum_k m_ik y_k  (a[k] of the rows <= k is rp or 0-multiplier: masked) -----
 #pragma unroll
@@ -172,7 +176,7 @@ cudaError_t launch_lu(const double* A, const double* b, double* x, int* status, 
     long long want = (n_inst + GROUPS - 1) / GROUPS;
     long long resident = (long long)sms * 16;                // grid-stride over systems: SM count x max resident blocks
     int blocks = (int)(want < resident ? (want > 0 ? want : 1) : resident);
-    kern<<<blocks, LU_THREADS, smem, s>>>(A, b, x, status, n_inst, n, prow, pcol);
+    kern<<<blocks, LU_THREADS, smem, s>>>(A, b, x, status, n_inst, n, prow, pcol, W);
     return cudaGetLastError();
 }
 
