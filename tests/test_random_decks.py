@@ -1,0 +1,46 @@
+"""Random decks (tests/random_decks.py): front-end, numbering and symbolic pass of the product against the oracle's
+independent restatement on CPU; full analysis parity on the GPU."""
+import numpy as np
+import pytest
+
+import parity_util as PU
+from random_decks import random_deck
+
+T, O, onl = PU.T, PU.O, PU.onl
+SEEDS = list(range(40))
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_front_end_and_symbolic_pass_on_random_decks(built, seed):
+    text, _ = random_deck(seed)
+    ckt = T.Circuit.from_netlist(text)
+    oc = O.OracleCircuit(text)
+    assert ckt.GetNodeMap() == oc.plan.node_map and ckt.GetBranchMap() == oc.plan.branch_map
+    dv = ckt.devices()
+    assert len(dv) == len(oc.plan.devices)
+    for a, b in zip(dv, oc.plan.devices):
+        assert (a["kind"], a["name"], a["nodes"], a["branch"], a["p"], a["ip"]) == (b.kind, b.name, list(b.nodes), b.branch, list(b.p), list(b.ip)), text
+    card, nl = ckt.analysis_card(), oc.netlist
+    assert (card["analysis"], card["tstart"], card["tstop"], card["tstep"], card["tmax"]) == (
+        nl.analysis, nl.tran["tstart"], nl.tran["tstop"], nl.tran["tstep"], nl.tran["tmax"])
+    st, so = ckt.structure(), oc.structure()
+    assert st["ext2int"] == so["ext2int"], text
+    assert st["pivot_row"] == so["pivot_row"] and st["pivot_col"] == so["pivot_col"], text
+    # the generated kernel source exists for every deck (specialisation never refuses a netlist of supported devices)
+    assert "tsb_optran" in ckt.batch(2).kernel_source(T.default_opts(min_blocks=2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [-1, 1], ids=["auto", "strict"])
+@pytest.mark.parametrize("seed", SEEDS[:24])
+def test_random_deck_matches_oracle(ctx, seed, mode):
+    text, info = random_deck(seed)
+    n = 6
+    ov = PU.draws("random", T.Circuit.from_netlist(text), n, seed=1000 + seed)
+    cap = 24000 if info["has_inductor"] else 2048
+    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=cap, opts=T.default_opts(strict_fp=mode))
+    _, ores = PU.run_oracle(text, n, ov, cap_rows=cap)
+    rep = PU.compare_waves(batch, ores, n)
+    assert PU.report_ok(rep), (rep, text)
+    assert rep["compared_points"] > 0
+    assert rep["counter_mismatch"] <= 1, (rep, text)
