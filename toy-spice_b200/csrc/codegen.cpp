@@ -485,11 +485,12 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK, TSB_MIN_BLOCKS) tsb_optran(TsbArgs a) {");
     e.line("    if (Ckt::HAS_NL && TSB_LANE_REFILL) {   // persistent lanes: finished lanes refill themselves from a.work_counter");
     e.line("        long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;");
-    e.line("        if (inst < a.n_run) tsb_run_optran_instance<Ckt>(a, inst);");
+    e.line("        tsb_run_optran_instance<Ckt>(a, inst, inst < a.n_run);");
     e.line("        return;");
     e.line("    }");
-    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_run; inst += (long long)gridDim.x * blockDim.x)");
-    e.line("        tsb_run_optran_instance<Ckt>(a, inst);");
+    e.line("    // block-uniform trip count: every lane of a warp enters the driver (its Newton loops are warp-synchronous)");
+    e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
+    e.line("        tsb_run_optran_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
     e.line("}");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
     e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_run; inst += (long long)gridDim.x * blockDim.x)");

@@ -300,9 +300,81 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Transient loop of a circuit WITH nonlinear devices, warp-synchronous: the time loop and the Newton loop of
+// tran.go:96-151 / 157-216 as two nested loops whose trip counts are decided by warp votes — every lane of the warp
+// starts a step attempt together, iterates until the slowest live lane's Newton loop has returned (lanes that are
+// through idle, a ballot per trip), then the whole warp does truncation error / accept / store together.  The
+// analysis mode is a compile-time constant here (mode selects and the LoadGmin branch fold away), and there is no
+// phase / continuation state machine in the hot loop.  `active` = this lane has an instance that reached the
+// transient; every lane of the warp must call (the votes use the full mask).
+#ifndef TSB_X_NLLOOP
+#define TSB_X_NLLOOP 1
+#endif
+template <class Ckt, class Sink>
+__device__ __forceinline__ void tsb_tran_nonlinear(const TsbArgs& a, Ckt& c, Sink& sink, bool active, long long& n_acc_out,
+                                                   long long& n_rej_out, long long& n_sol_tran_out, long long& n_exec_out,
+                                                   int& status, double& fail_at) {
+    constexpr int N = Ckt::N;
+    double time = 0.0, dt = a.minstep;                  // tran.go:93
+    double last_key = -1.0;
+    TsbTimeKeyer keyer; keyer.reset();
+    int n_acc = 0, n_rej = 0, n_sol = 0;
+    bool live = active && time < a.tstop;
+    while (__any_sync(0xffffffffu, live)) {
+        // ---- top of `for tr.time < tr.stopTime` (tran.go:96-111) ------------------------------------------
+        double next_time = time + dt;
+        if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+        double rdt = 0.0;
+        if (live) {
+            c.eval_sources(time, 1.0);                   // sources are evaluated at the START of the step
+            rdt = 1.0 / dt;                              // the one division by the time step of this attempt
+        }
+        // ---- doNRiter (tran.go:157-216) ---------------------------------------------------------------------
+        int iter = 0;
+        bool conv = false, fail = false, iterating = live;
+        while (__any_sync(0xffffffffu, iterating)) {
+            if (iterating) {
+                if (iter > 0) c.update_nl(c.xo);
+                const bool solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+                ++n_sol;
+                if (!solved) fail = true;
+                else {
+                    if (iter > 0) conv = tsb_converged<N>(c.x, c.xo, a.reltol, a.abstol);
+                    if (!conv) {
+#pragma unroll
+                        for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+                        if (++iter >= a.max_iter) fail = true;
+                    }
+                }
+                iterating = !(conv || fail);
+            }
+        }
+        // ---- tran.go:113-151 ------------------------------------------------------------------------------------
+        if (live) {
+            if (fail) {
+                if (dt > a.minstep) { dt /= 2; ++n_rej; }
+                else { status = TSB_ST_TRAN_FAILED; fail_at = time; live = false; }
+            } else {
+                const double lte = c.lte(dt, rdt);
+                if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; }
+                else {
+                    tsb_accept_step(a, c, sink, time, dt, next_time, lte, keyer, last_key);
+                    ++n_acc;
+                    live = time < a.tstop;
+                }
+            }
+        }
+    }
+    n_acc_out += n_acc; n_rej_out += n_rej; n_sol_tran_out += n_sol; n_exec_out += n_sol;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Operating point + transient (analysis == TSB_AN_OP stops after the first operating point).
+#ifndef TSB_X_WSYNC
+#define TSB_X_WSYNC 1
+#endif
 template <class Ckt>
-__device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long long inst) {
+__device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long long inst, bool valid) {
     constexpr int N = Ckt::N;
     constexpr bool LINEAR_LOOP = !Ckt::HAS_NL && (TSB_SKIP_LINEAR_RESOLVE != 0);
     // Lane refill (the "compaction of finished lanes" of the north star): lanes of a NONLINEAR circuit finish
@@ -314,6 +386,17 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     // phase-specific code (OP start, initial estimate, accept) once per distinct phase, so on sweeps whose lanes
     // all take similar trip counts refill LOSES 3-17 % (profiles/r01_notes.md) and is off by default.
     constexpr bool REFILL = Ckt::HAS_NL && (TSB_LANE_REFILL != 0);
+    // Warp-synchronous Newton loops (nonlinear circuits).  Each trip of the loop below is one Newton iteration for every
+    // lane, but the code that runs when a Newton loop RETURNS (truncation error, accept, result store, source
+    // evaluation of the next step: ~2x the instructions of an iteration) is executed once per group of lanes that
+    // return in the same trip.  Left alone, lanes drift apart and that code runs almost every trip for a handful of
+    // lanes: the first profile of diode2 showed 15 of 32 threads active per instruction and 3 800 warp instructions
+    // per accepted step.  With WSYNC a lane whose Newton loop has returned waits (one ballot per trip) until every
+    // live lane of its warp has returned as well, then the whole warp runs the post-Newton code together: the trip
+    // count becomes the per-step maximum over the warp, the expensive code runs once per step.
+    constexpr bool WSYNC = Ckt::HAS_NL && !REFILL && (TSB_X_WSYNC != 0);
+    constexpr bool NL_LOOP = WSYNC && (TSB_X_NLLOOP != 0);     // transient in tsb_tran_nonlinear, entered by the whole warp
+    if (!WSYNC && !valid) return;
     Ckt c;
     TsbSink<Ckt::NCOL_MAX> sink(a, inst);   // NCOL_MAX = transient column count (>= OP column count)
 
@@ -329,7 +412,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     double time, dt, next_time, rdt;
     double last_key;
     TsbTimeKeyer keyer;
-    bool linear_tran;                          // hand the transient over to tsb_tran_linear
+    bool linear_tran;                          // hand the transient over to tsb_tran_linear / tsb_tran_nonlinear
 
     auto begin_instance = [&]() {
         c.load(a, inst);
@@ -344,7 +427,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         last_key = -1.0; keyer.reset();
         linear_tran = false;
         if (phase == PH_TRAN_BEGIN && !(time < a.tstop)) phase = PH_DONE;
-        if (LINEAR_LOOP && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
+        if ((LINEAR_LOOP || NL_LOOP) && phase == PH_TRAN_BEGIN) { linear_tran = true; phase = PH_DONE; }
     };
     auto finish_instance = [&]() {
         if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
@@ -359,18 +442,21 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         a.counters[6 * a.n_inst + inst] = n_exec;
         a.counters[7 * a.n_inst + inst] = sink.n_rows;
     };
-    begin_instance();
+    bool done = !valid;                 // lanes without an instance only take part in the ballots
+    bool pend = false;                  // this lane's Newton loop has returned (conv / fail hold how)
+    bool conv = false, fail = false;
+    phase = PH_DONE;
+    if (valid) begin_instance();
 
     for (;;) {
-        if (phase == PH_DONE) {
-            if (LINEAR_LOOP && linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
-            finish_instance();
-            if (!REFILL) break;
-            inst = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
-            if (inst >= a.n_run) break;
-            begin_instance();
-            continue;
-        }
+        if (!done && !pend && phase == PH_DONE) {
+            if (!LINEAR_LOOP && !NL_LOOP) finish_instance();       // (else: transient + finish follow the loop, below)
+            done = true;
+            if (REFILL) {
+                inst = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
+                if (inst < a.n_run) { done = false; begin_instance(); }
+            }
+        } else if (!done && !pend) {
         if (phase == PH_OP_START) {
             // OperatingPoint.Execute(): linear-only initial estimate from a separate sparse matrix
             c.eval_sources(0.0, 1.0);
@@ -381,7 +467,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
                 for (int i = 1; i <= N; ++i) c.xo[i] = 0.0;
             }
             gmin = 0.0; cont = C_MAIN; iter = 0; mode = TSB_MODE_OP; phase = PH_NR;
-        } else if (!LINEAR_LOOP && phase == PH_TRAN_BEGIN) {
+        } else if (!LINEAR_LOOP && !NL_LOOP && phase == PH_TRAN_BEGIN) {
             // top of the `for tr.time < tr.stopTime` loop (tran.go:96-111)
             next_time = time + dt;
             if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
@@ -396,7 +482,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         bool solved = c.template assemble_solve<-1>(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
         if (is_tran) ++n_sol_tran; else ++n_sol_op;
         ++n_exec;
-        bool conv = false, fail = !solved;
+        conv = false; fail = !solved;
         if (solved) {
             if (!Ckt::HAS_NL && TSB_SKIP_LINEAR_RESOLVE) {
                 // A circuit without NonLinear devices re-stamps identical values in iteration 1, so the
@@ -411,7 +497,17 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
                 if (++iter >= a.max_iter) fail = true;
             }
         }
-        if (!conv && !fail) continue;
+        pend = conv || fail;
+        }
+        if (WSYNC) {
+            if (__all_sync(0xffffffffu, done)) break;
+            if (!__all_sync(0xffffffffu, done || pend)) continue;      // somebody is still iterating: wait for them
+            if (!pend) continue;                                       // (a finished lane)
+        } else {
+            if (done) break;
+            if (!pend) continue;
+        }
+        pend = false;
 
         // ---------------- the Newton loop returned: decide what runs next -----------------------
         bool op_done = false, op_failed = false;
@@ -465,7 +561,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             if (conv) op_done = true; else op_failed = true;
             break;
         case C_TRAN:
-            if (LINEAR_LOOP) break;               // linear circuits run their transient in tsb_tran_linear
+            if (LINEAR_LOOP || NL_LOOP) break;    // these run their transient in tsb_tran_linear / tsb_tran_nonlinear
             if (fail) {
                 // tran.go:113-120
                 if (dt > a.minstep) { dt /= 2; ++n_rej; phase = PH_TRAN_BEGIN; }
@@ -503,9 +599,20 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             } else {
                 time = 0.0; dt = a.minstep;                        // tran.go:93
                 phase = time < a.tstop ? PH_TRAN_BEGIN : PH_DONE;
-                if (LINEAR_LOOP) { linear_tran = true; phase = PH_DONE; }
+                if (LINEAR_LOOP || NL_LOOP) { linear_tran = true; phase = PH_DONE; }
             }
         }
+    }
+    if (LINEAR_LOOP) {
+        // the operating point(s) ran in the loop above; the transient of a linear circuit has its own loop, kept
+        // outside so that its register allocation is not entangled with the Newton state machine
+        if (linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
+        finish_instance();
+    }
+    if (NL_LOOP) {
+        // every lane of the warp arrives here together (the loop above ends on a full-warp vote)
+        tsb_tran_nonlinear(a, c, sink, valid && linear_tran, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
+        if (valid) finish_instance();
     }
 }
 
