@@ -305,7 +305,7 @@ struct Diode : Device {
         double vt = thermalVoltage(temp);
         double ratio = temp / ktemp;
         double egfact = -Eg / (2 * vt) * (temp / ktemp - 1.0);
-        return Is * std::pow(ratio, Xti / N) * std::exp(egfact);
+        return Is * go_pow(ratio, Xti / N) * std::exp(egfact);
     }
     double calculateCurrent(double v, double temp) const {       // :119-135
         double vt = thermalVoltage(temp);
@@ -404,7 +404,7 @@ struct Bjt : Device {
         if (Vaf > 0) qb = 1.0 / (1 - vbc / Vaf);
         gm = AlphaF * dIes_dVbe / qb;
         if (vt != 0) gpi = std::fabs(ib) / vt; else gpi = 1e-12;
-        if (Vaf != 0) gout = AlphaF * Ies * (expVbe - 1) * (1 / Vaf) * std::pow(1 + vce / Vaf, -2);
+        if (Vaf != 0) gout = AlphaF * Ies * (expVbe - 1) * (1 / Vaf) * go_pow(1 + vce / Vaf, -2);
         else gout = 1e-12;
     }
     void UpdateVoltages(const std::vector<double>& v) override { // :283-313
@@ -481,7 +481,7 @@ struct Mosfet : Device {
         double cox = epsox / TOX;
         double eeff = vgst / (TOX * 100);
         double ueff = UO;
-        if (UCRIT > 0 && eeff > 0) ueff /= (1.0 + std::pow(eeff / UCRIT, UEXP));
+        if (UCRIT > 0 && eeff > 0) ueff /= (1.0 + go_pow(eeff / UCRIT, UEXP));
         double vdsat = vgst;
         if (VMAX > 0) {
             double ecrit = VMAX / ueff * 100;
@@ -583,8 +583,8 @@ struct Mosfet : Device {
         default: qgs = cgs * vgs; qgd = cgd * vgd; qgb = cgb * (vgs - vbs); break;
         }
         double cbs, cbd;
-        if (vbs < 0) cbs = CBS / std::pow(1.0 - vbs / PB, MJ); else cbs = CBS * (1.0 + MJ * vbs / PB);
-        if (vbd < 0) cbd = CBD / std::pow(1.0 - vbd / PB, MJ); else cbd = CBD * (1.0 + MJ * vbd / PB);
+        if (vbs < 0) cbs = CBS / go_pow(1.0 - vbs / PB, MJ); else cbs = CBS * (1.0 + MJ * vbs / PB);
+        if (vbd < 0) cbd = CBD / go_pow(1.0 - vbd / PB, MJ); else cbd = CBD * (1.0 + MJ * vbd / PB);
         qbs = cbs * vbs;
         qbd = cbd * vbd;
     }
@@ -863,7 +863,7 @@ struct OperatingPoint {
         path = OP_GMIN;
         int numGminSteps = 10;
         double startGmin = (double)mat.Size * 0.001;
-        double gmin = startGmin * std::pow(10, (double)numGminSteps);
+        double gmin = startGmin * go_pow(10, (double)numGminSteps);
         std::vector<double> cur = mat.Solution();
         for (int i = 0; i <= numGminSteps; ++i) {
             if (!doNRiter(gmin, conv.maxIter, &cur)) break;

@@ -64,4 +64,62 @@ inline double go_min(double x, double y) {
     return x < y ? x : y;
 }
 
+// math.Pow (src/math/pow.go), restated: special cases, Sqrt for y = +-0.5, and the general path
+// x**y = Exp(yf*Log(x)) * x**yi with the integer power by repeated squaring of the Frexp mantissa and one Ldexp at
+// the end.  For integer y this is a fixed sequence of IEEE multiplications (and one division for y < 0), i.e.
+// reproducible bit for bit — unlike libm's pow, which rounds the exact power once.  Exp / Log of the fractional part
+// come from libm (<= 1 ulp from Go's).
+inline double go_pow(double x, double y) {
+    if (y == 0 || x == 1) return 1;
+    if (y == 1) return x;
+    if (std::isnan(x) || std::isnan(y)) return std::nan("");
+    if (x == 0) {
+        bool odd = std::fabs(y) < 9007199254740992.0 && std::fmod(std::fabs(y), 2.0) == 1.0;
+        if (y < 0) return (odd && std::signbit(x)) ? -INFINITY : INFINITY;
+        return odd ? x : 0.0;
+    }
+    if (std::isinf(y)) {
+        if (x == -1) return 1;
+        if ((std::fabs(x) < 1) == (y > 0)) return 0;
+        return INFINITY;
+    }
+    if (std::isinf(x)) {
+        if (x < 0) {
+            bool odd = std::fabs(y) < 9007199254740992.0 && std::fmod(std::fabs(y), 2.0) == 1.0;
+            if (y < 0) return odd ? -0.0 : 0.0;
+            return odd ? -INFINITY : INFINITY;
+        }
+        return y < 0 ? 0.0 : INFINITY;
+    }
+    if (y == 0.5) return std::sqrt(x);
+    if (y == -0.5) return 1 / std::sqrt(x);
+    double yi, yf = std::modf(std::fabs(y), &yi);
+    if (yf != 0 && x < 0) return std::nan("");
+    if (yi >= 9.223372036854775808e18) {
+        if (x == -1) return 1;
+        if ((std::fabs(x) < 1) == (y > 0)) return 0;
+        return INFINITY;
+    }
+    double a1 = 1.0;
+    int ae = 0;
+    if (yf != 0) {
+        if (yf > 0.5) { yf--; yi++; }
+        a1 = std::exp(yf * std::log(x));
+    }
+    int xe;
+    double x1 = std::frexp(x, &xe);
+    for (int64_t i = (int64_t)yi; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) {
+            ae += xe;                                  // overflow / underflow: let Ldexp decide
+            break;
+        }
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < .5) { x1 += x1; xe--; }
+    }
+    if (y < 0) { a1 = 1 / a1; ae = -ae; }
+    return std::ldexp(a1, ae);
+}
+
 }  // namespace orc
