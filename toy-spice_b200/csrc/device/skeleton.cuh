@@ -326,8 +326,10 @@ __device__ __forceinline__ void tsb_tran_nonlinear(const TsbArgs& a, Ckt& c, Sin
         if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
         double rdt = 0.0;
         if (live) {
-            c.eval_sources(time, 1.0);                   // sources are evaluated at the START of the step
-            rdt = 1.0 / dt;                              // the one division by the time step of this attempt
+            // sources are evaluated at the START of the step; branch-free sine core, general routine only
+            // for an argument beyond its range
+            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
+            rdt = tsb_rcp_dt(dt);                        // the one division by the time step of this attempt
         }
         // ---- doNRiter (tran.go:157-216) ---------------------------------------------------------------------
         int iter = 0;
