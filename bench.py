@@ -275,6 +275,7 @@ def main():
     fp64_peak = ctx.measure_fp64_peak()
 
     # ---- warm-up (also loads / compiles the specialised kernels) --------------------------------
+    step_resident()             # priming pass (not one of the W warm-up steps): loads the kernels, runs the launch-bounds autotuner
     for _ in range(max(args.warmup, 3 if args.warmup > 0 else 0)):
         step_resident()
     torch.cuda.synchronize()
