@@ -46,6 +46,12 @@ template <bool STRICT> __device__ __forceinline__ double nmuladd(double a, doubl
 }
 
 constexpr int LU_THREADS = 128;
+// 1: pivot-row broadcast through shared memory (one lane stores the row with STS.128, all lanes read it back with
+// broadcast LDS.128: 2 instead of 3 instructions per (k, j) pair).  Measured SLOWER than the shuffles on B200
+// (n = 32: 1.18e8 vs 1.30e8 systems/s; profiles/r01_lu_operator.txt), so the shuffles stay.
+#ifndef TSB_LU_SMEM_BCAST
+#define TSB_LU_SMEM_BCAST 0
+#endif
 
 // A: [n_inst][n][n] row-major, b / x: [n_inst][n]  (instance-major: what a per-instance stamper produces)
 template <int W, bool STRICT>
@@ -138,13 +144,30 @@ __global__ void __launch_bounds__(LU_THREADS, 4) tsb_k_lu_warp(const double* __r
                 // `fence` is the lane width passed at run time, i.e. always true: the uniform branch keeps ptxas from
                 // hoisting the shuffles of later steps across this one (255 registers and spills without it)
                 if (k < fence) {
+#if TSB_LU_SMEM_BCAST
+                    // pivot-row broadcast through shared memory (the staging tile is free by now): one lane stores the
+                    // row, every lane reads it back with broadcast loads — 1 load per element instead of 2 shuffles
+                    if (lane == k) {
+#pragma unroll
+                        for (int j = k; j < W; ++j) tile[j] = a[j];
+                    }
+                    __syncwarp();
+                    const double piv = tile[k];
+#else
                     const double piv = shfl_d(a[k], k, W);
+#endif
                     ok = ok && (piv != 0.0);
                     const double rp = rcp_fast(piv);
                     const double m = lane > k ? a[k] * rp : 0.0;      // 0 for rows that are finished: their update is a no-op
                     a[k] = lane == k ? rp : (lane > k ? m : a[k]);    // rows above k keep U_ik for the back-substitution
+#if TSB_LU_SMEM_BCAST
+#pragma unroll
+                    for (int j = k + 1; j < W; ++j) a[j] = fma(-tile[j], m, a[j]);
+                    __syncwarp();
+#else
 #pragma unroll
                     for (int j = k + 1; j < W; ++j) a[j] = fma(-shfl_d(a[j], k, W), m, a[j]);
+#endif
                 }
             }
             // ---- forward: y_i = b_i - sum_k m_ik y_k  (a[k] of the rows <= k is rp or 0-multiplier: masked) -----
