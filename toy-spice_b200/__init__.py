@@ -4,6 +4,7 @@ the analysis API of edp1096/toy-spice.  See DESIGN.md.  The CUDA extension
 from .api import (AN_AC, AN_DC, AN_OP, AN_TRAN, OUT_GRID, OUT_STATS, OUT_WAVE, Batch, Circuit, Context, DCSweep, NewDCSweep,
                   NewOP, NewTransient, OperatingPoint, Opts, Transient, TsbError, analysis_from_card, default_opts,
                   lib, lib_path, lu_order)
+from .report import format_results, format_value_factor, write_raw
 from .workloads import BUNDLED
 
 __all__ = [n for n in dir() if not n.startswith("_")]
