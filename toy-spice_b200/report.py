@@ -5,7 +5,7 @@
                         (same headers, same column order: V(...) then I(...), each sorted by name; AC is out of scope)
   write_raw             ASCII "rawfile" as SPICE3 / ngspice write it (not in the reference; for waveform viewers)
 
-Host-side presentation only: nothing here touches the GPU or the oracle."""
+Host-side presentation only: no computation happens here."""
 from __future__ import annotations
 
 import datetime as _dt
