@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -260,10 +261,16 @@ int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, c
     }
     std::string err;
     mkdir(ctx->cache_dir.c_str(), 0755);
-    { std::ofstream f(base + ".cu"); f << src; }
+    // Several ranks of one job share this directory: every file is written under a private name and renamed into
+    // place (atomic on POSIX), so a reader sees either nothing (and compiles for itself) or a complete file.
+    const std::string tmp = base + ".tmp" + std::to_string((long long)getpid());
+    { std::ofstream f(tmp + ".cu"); f << src; }
+    rename((tmp + ".cu").c_str(), (base + ".cu").c_str());
     if (!nvrtc_compile(src, base + ".cu", o, cubin, info, err)) return fail(ctx, TSB_E_COMPILE, err);
-    { std::ofstream f(base + ".cubin", std::ios::binary); f.write(cubin.data(), (std::streamsize)cubin.size()); }
-    { std::ofstream f(base + ".info"); f << info.regs << " " << info.spill_st << " " << info.spill_ld << "\n"; }
+    { std::ofstream f(tmp + ".info"); f << info.regs << " " << info.spill_st << " " << info.spill_ld << "\n"; }
+    rename((tmp + ".info").c_str(), (base + ".info").c_str());
+    { std::ofstream f(tmp + ".cubin", std::ios::binary); f.write(cubin.data(), (std::streamsize)cubin.size()); }
+    rename((tmp + ".cubin").c_str(), (base + ".cubin").c_str());
     return TSB_OK;
 }
 
