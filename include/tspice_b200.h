@@ -93,11 +93,14 @@ typedef struct tsb_opts {
                            0: fast build (FMA, one reciprocal of dt per step, reciprocal-seed pivots; each
                               substituted operation within 1 ulp); -1 (default): 1 for circuits with mutual
                               couplings (condition numbers ~1e7 make 1-ulp differences visible at 1e-9), else 0 */
-    int block_size;     /* 0: default (128) */
+    int block_size;     /* 0: default (128); rounded up to a multiple of 32 (whole warps), at most 1024 */
     int skip_linear_resolve; /* 1 (default): circuits without nonlinear devices do not execute the reference's
                            second Newton solve per step — it re-stamps identical values, returns identical bits and
                            always passes the convergence test; counters still report it (reference-equivalent) */
-    int min_blocks;     /* __launch_bounds__ min resident blocks per SM for the specialised kernels (0: default) */
+    int min_blocks;     /* __launch_bounds__ min resident blocks per SM for the specialised kernels.  0 (default): chosen
+                           by a spill rule and, on the first transient run of a batch of >= 32768 instances, by timing the
+                           candidates on a sub-batch (that first call then blocks for a fraction of a second;
+                           $TSB_AUTOTUNE=0 disables; results never depend on the choice) */
     int lane_refill;    /* 1: circuits with nonlinear devices run on a resident grid whose lanes, once their instance has
                            finished, take the next unprocessed instance from a work counter (finished lanes never idle
                            beside slow neighbours) — for sweeps whose instances need very different numbers of steps;

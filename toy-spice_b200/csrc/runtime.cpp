@@ -428,6 +428,9 @@ tsb_opts resolve(const tsb_opts* o, const Plan& plan) {
         r = *o;
         if (r.max_iter <= 0) r.max_iter = 100;
         if (r.block_size <= 0) r.block_size = 128;
+        // whole warps only: the Newton loops of nonlinear circuits are warp-synchronous (full-mask votes)
+        r.block_size = (r.block_size + 31) / 32 * 32;
+        if (r.block_size > 1024) r.block_size = 1024;
     }
     const char* env = getenv("TSB_STRICT_FP");
     if (env && *env) r.strict_fp = *env != '0';
