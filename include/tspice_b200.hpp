@@ -151,10 +151,12 @@ class Transient : public Analysis {
 public:
     Transient(double tStart, double tStop, double tStep, double tMax, bool uic)
         : tStart_(tStart), tStop_(tStop), tStep_(tStep), tMax_(tMax), uic_(uic) {}
-    int out = TSB_OUT_WAVE;
+    int out = TSB_OUT_WAVE;      // TSB_OUT_WAVE | TSB_OUT_STATS | TSB_OUT_GRID (results resampled onto a fixed time grid)
     int64_t cap_rows = 16384;
+    double grid_dt = 0.0;        // TSB_OUT_GRID: grid spacing (0: the clamped tStep)
     void Execute() override {
         require();
+        if (out & TSB_OUT_GRID) opts.grid_dt = grid_dt;
         check(tsb_run_tran(batch_->get(), tStart_, tStop_, tStep_, tMax_, uic_ ? 1 : 0, out, cap_rows, &opts));
         check(tsb_batch_sync(batch_->get()));
         raise_single_instance_failure("failed to converge at t");                      // tran.go:119
@@ -197,4 +199,25 @@ inline DCSweep NewDCSweep(std::vector<std::string> s, std::vector<double> a, std
 }
 
 }  // namespace analysis
+
+// Operator level (pkg/matrix: Clear / AddElement / AddRHS / Solve over a batch of stamped systems).
+struct PivotOrder { std::vector<int> row, col; };
+inline PivotOrder LuOrder(int n, const std::vector<double>& A_nominal) {
+    if ((int)A_nominal.size() != n * n) throw std::invalid_argument("A_nominal must be n*n");
+    PivotOrder o; o.row.resize(n); o.col.resize(n);
+    if (tsb_lu_order(n, A_nominal.data(), o.row.data(), o.col.data()) != TSB_OK) throw Error("matrix factorization failed (nominal matrix is singular)");
+    return o;
+}
+// A: [n_inst][n][n] row-major, b: [n_inst][n]; returns x [n_inst][n]; status[inst] = 1 marks a zero pivot.
+inline std::vector<double> LuSolveBatched(Context& ctx, int n, const PivotOrder& o, const std::vector<double>& A,
+                                          const std::vector<double>& b, std::vector<int32_t>& status, bool strict = false) {
+    const int64_t n_inst = (int64_t)b.size() / n;
+    if ((int64_t)A.size() != n_inst * n * n) throw std::invalid_argument("A must be n_inst*n*n");
+    std::vector<double> x((size_t)n_inst * n);
+    status.assign((size_t)n_inst, 0);
+    if (tsb_lu_solve_batched(ctx.get(), n, o.row.data(), o.col.data(), A.data(), b.data(), x.data(), status.data(), n_inst, strict ? 1 : 0) != TSB_OK)
+        throw Error(ctx.last_error());
+    return x;
+}
+
 }  // namespace tsb

@@ -45,6 +45,30 @@ int main(int argc, char** argv) {
         }
         for (int32_t st : tb.Status()) CHECK(st == TSB_ST_OK);
 
+        // results on a fixed grid (TSB_OUT_GRID): 300 points at the clamped tStep, constant for this resistive divider
+        auto tg = analysis::NewTransient(0.0, 3e-3, 1e-4, 1e-4, false);
+        tg.out = TSB_OUT_GRID;
+        tg.Setup(batch);
+        tg.Execute();
+        auto g2 = tg.GetResults(2);
+        CHECK(g2["TIME"].size() == 300 && std::fabs(g2["TIME"].front() - 1e-5) < 1e-18 && g2["TIME"].back() == 0.003);
+        for (double v : g2["V(2)"]) CHECK(std::fabs(v - expect[2]) < 1e-12);
+
+        // operator level: the rr.cir MNA system itself through the batched LU, strict build
+        {
+            const std::vector<double> A0 = {1e-3, -1e-3, 1, -1e-3, 2e-3, 0, 1, 0, 0};
+            PivotOrder ord = LuOrder(3, A0);
+            std::vector<double> A, b;
+            for (int q = 0; q < 5; ++q) { A.insert(A.end(), A0.begin(), A0.end()); b.insert(b.end(), {0.0, 0.0, 5.0 + q}); }
+            std::vector<int32_t> st;
+            auto x = LuSolveBatched(ctx, 3, ord, A, b, st, true);
+            for (int q = 0; q < 5; ++q) {
+                CHECK(st[q] == 0);
+                CHECK(std::fabs(x[3 * q] - (5.0 + q)) < 1e-12 && std::fabs(x[3 * q + 1] - (5.0 + q) / 2) < 1e-12 &&
+                      std::fabs(x[3 * q + 2] + (5.0 + q) / 2 * 1e-3) < 1e-15);
+            }
+        }
+
         // error behaviour: DC sweep over a source that does not exist (dc.go:64-66), inconsistent lengths (dc.go:21-23)
         bool threw = false;
         try { auto dc = analysis::NewDCSweep({"Vx"}, {0.0}, {1.0}, {0.1}); dc.Setup(ckt); dc.Execute(); } catch (const Error&) { threw = true; }

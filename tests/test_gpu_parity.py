@@ -300,3 +300,47 @@ def test_fixed_grid_is_what_lets_inductor_waveforms_fit(ctx):
         g = batch.waveform(int(i))
         scale = np.maximum(np.abs(ref), np.max(np.abs(ref), axis=0, keepdims=True) * 1e-3)
         assert np.all(np.abs(g - ref) <= PU.RELTOL * scale + PU.ABSTOL)
+
+
+def test_fixed_grid_with_tstart_and_coarse_grid(ctx):
+    """Grid coarser than the steps and finer than the steps, with a start time > 0 (rows before tstart are not part of
+    the reference series, so the first grid points see constant extrapolation from the first stored row)."""
+    text = T.BUNDLED["rc"]
+    n = 8
+    ov = PU.draws("rc", T.Circuit.from_netlist(text), n)
+    for grid_dt, tstart in ((2.3e-4, 0.0), (1.7e-6, 1e-3), (1e-5, 5e-4)):
+        tran = {"tstart": tstart}
+        ckt, batch, an = PU.run_gpu(ctx, text, n, ov, out=T.OUT_GRID, grid_dt=grid_dt, tran=tran)
+        _, ores = PU.run_oracle(text, n, ov, cap_rows=4096, tran=tran)
+        tg = an.grid_times()
+        w = batch.wave_all()
+        assert w.shape[0] == len(tg) and np.all(batch.rows() == len(tg))
+        for i in range(n):
+            ref = PU.resample_reference(ores["wave"][i], int(ores["n_rows"][i]), ores["ncol"], tg)
+            scale = np.maximum(np.abs(ref), np.max(np.abs(ref), axis=0, keepdims=True) * 1e-3)
+            assert np.all(np.abs(w[:, :, i] - ref) <= PU.RELTOL * scale + PU.ABSTOL), (grid_dt, tstart, i)
+
+
+def test_launch_bounds_autotuner_is_result_neutral(ctx, tmp_path):
+    """min_blocks = 0 on a large batch times the candidates on a sub-batch first (runtime.cpp: autotune_min_blocks),
+    records the choice in <cache>/<key>.tuned, and must not change a single bit of the results."""
+    import shutil
+    cache = tmp_path / "kc"
+    shutil.copytree(os.path.join(PU.ROOT, "toy-spice_b200", "_kcache"), cache, ignore=shutil.ignore_patterns("*.tuned"))
+    ctx = T.Context(0)                  # a fresh context: no in-memory record of earlier choices
+    ctx.set_cache_dir(str(cache))
+    try:
+        n = 1 << 16
+        for name in ("rc", "diode4"):
+            ov = PU.draws(name, T.Circuit.from_netlist(T.BUNDLED[name]), n)
+            res = []
+            for mb in (0, 2):
+                _, b, _ = PU.run_gpu(ctx, T.BUNDLED[name], n, ov, out=T.OUT_STATS, opts=T.default_opts(min_blocks=mb))
+                res.append((b.stats_all(), b.rows(), b.status(), b.counters()))
+                del b
+            for x, y in zip(*res):
+                assert np.array_equal(x, y, equal_nan=True), name
+        tuned = [f for f in os.listdir(cache) if f.endswith(".tuned")]
+        assert len(tuned) >= 2 and all(1 <= int(open(cache / f).read()) <= 6 for f in tuned)
+    finally:
+        ctx.close()

@@ -277,7 +277,7 @@ int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, c
 // Launch bounds of the transient kernel.  One circuit per thread keeps everything in registers, so
 // occupancy is bought with the register cap: the kernels are latency-bound (dependent FP64 chains),
 // more resident warps help until the cap forces spills into the Newton loop.  Rule (measured on B200,
-// profiles/r01_notes.md): the largest min-blocks-per-SM in {4,3,2,1} whose ptxas report shows at most
+// profiles/r01_notes.md): the largest min-blocks-per-SM in {6..1} whose ptxas report shows at most
 // TSB_SPILL_OK bytes of spill stores; __graft_entry__.build() applies the same rule with nvcc.
 const int TSB_SPILL_OK = 100;
 const int TSB_MAX_MIN_BLOCKS = 6;
