@@ -20,7 +20,8 @@
  *   - every function returns TSB_OK (0) or a negative TSB_E_* code; tsb_last_error() gives text.
  *   - per-instance failures (no convergence, singular matrix, NaN) are DATA (status array),
  *     never a call failure.  No C++ exception crosses this boundary.
- *   - handles are opaque and owned by the library; every create has a destroy.
+ *   - handles are opaque and owned by the library; every create has a destroy.  Plans keep their context alive and
+ *     batches their plan, so the destroy calls may come in any order (garbage-collected hosts).
  *   - buffers passed in/out are caller-owned HOST memory unless the name says `_dev`.
  *   - indices: nodes and branches are 1-based MNA unknown numbers, 0 = ground
  *     (pkg/matrix/device.go:3-8); devices are numbered 0.. in tsb_plan_add_device call order,

@@ -344,3 +344,15 @@ def test_launch_bounds_autotuner_is_result_neutral(ctx, tmp_path):
         assert len(tuned) >= 2 and all(1 <= int(open(cache / f).read()) <= 6 for f in tuned)
     finally:
         ctx.close()
+
+
+def test_context_may_be_destroyed_before_its_batches():
+    c2 = T.Context(0)
+    ckt = T.Circuit.from_netlist(T.BUNDLED["rc"], c2)
+    b = ckt.batch(64)
+    b.run_tran(0.0, 3e-3, 1e-5, 0.0, out=T.OUT_STATS)
+    b.sync()
+    s0 = b.stats_all().copy()
+    c2.close()                                     # handle released; the library keeps the context until b and ckt are gone
+    assert np.array_equal(b.stats_all(), s0)       # device buffers still valid
+    del b, ckt

@@ -173,3 +173,23 @@ def test_generated_kernel_compiles_for_sm100a(built, tmp_path):
     assert "0 bytes spill stores, 0 bytes spill loads" in r.stderr
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(tmp_path / "k.cubin")], capture_output=True, text=True).stdout
     assert "DFMA" in sass and "sm_100" in sass
+
+
+def test_destroy_order_is_free(built):
+    """Plans keep their context alive and batches their plan (reference counts inside the library): a host whose
+    garbage collector releases handles in arbitrary order must not crash.  Host-only here (no context); the GPU
+    variant is in test_gpu_parity.py."""
+    import ctypes as C
+    L = T.lib()
+    plan = C.c_void_p()
+    assert L.tsb_plan_from_netlist(None, T.BUNDLED["rlc"].encode(), C.byref(plan)) == 0
+    batches = []
+    for _ in range(3):
+        b = C.c_void_p()
+        assert L.tsb_batch_create(plan, 16, C.byref(b)) == 0
+        batches.append(b)
+    L.tsb_plan_destroy(plan)                       # the batches still refer to it
+    buf = C.create_string_buffer(64)
+    assert L.tsb_batch_kernel_key(batches[0], None, buf, 64) == 0 and len(buf.value) == 32      # plan data still readable
+    for b in batches:
+        L.tsb_batch_destroy(b)

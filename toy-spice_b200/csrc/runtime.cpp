@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -75,12 +76,17 @@ struct tsb_ctx {
     std::map<std::string, int> auto_choice;            // key of the min_blocks=auto source -> chosen min blocks
     std::map<std::string, int> tuned;                  // ... -> choice confirmed by timing (autotune_min_blocks)
     int64_t launches = 0;
+    // Lifetime: plans hold a reference to their context, batches to their plan, so the destroy calls may come in any
+    // order (a garbage-collected host language releases them in no particular one): an object is torn down when its
+    // owner has destroyed it AND nothing refers to it any more.
+    std::atomic<int> refs{1};
 };
 
 struct tsb_plan {
     Plan p;
     tsb_ctx* ctx = nullptr;
     std::string err;
+    std::atomic<int> refs{1};
 };
 
 struct tsb_batch {
@@ -521,13 +527,19 @@ int tsb_ctx_create(int device_ordinal, tsb_ctx** out) {
     *out = ctx.release();
     return TSB_OK;
 }
-void tsb_ctx_destroy(tsb_ctx* ctx) {
-    if (!ctx) return;
+static void ctx_release(tsb_ctx* ctx) {
+    if (!ctx || ctx->refs.fetch_sub(1) != 1) return;
     cudaSetDevice(ctx->device);
     for (auto& kv : ctx->modules) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
+static void plan_release(tsb_plan* plan) {
+    if (!plan || plan->refs.fetch_sub(1) != 1) return;
+    ctx_release(plan->ctx);
+    delete plan;
+}
+void tsb_ctx_destroy(tsb_ctx* ctx) { ctx_release(ctx); }
 const char* tsb_last_error(tsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
 int tsb_ctx_set_stream(tsb_ctx* ctx, uint64_t stream) {
     if (!ctx) return TSB_E_INVALID;
@@ -571,6 +583,7 @@ int tsb_ctx_measure_fp64_peak(tsb_ctx* ctx, double* tflops) {
 int tsb_plan_create(tsb_ctx* ctx, int n_nodes, int n_branches, tsb_plan** out) {
     if (!out || n_nodes < 0 || n_branches < 0) return TSB_E_INVALID;
     tsb_plan* p = new tsb_plan; p->ctx = ctx; p->p.ctx = ctx;
+    if (ctx) ctx->refs.fetch_add(1);
     p->p.n_nodes = n_nodes; p->p.n_branches = n_branches;
     *out = p;
     return TSB_OK;
@@ -584,6 +597,7 @@ int tsb_plan_from_netlist(tsb_ctx* ctx, const char* text, tsb_plan** out) {
     if (rc != TSB_OK) return fail(ctx, rc, err);
     rc = plan_finalize(p->p);
     if (rc != TSB_OK) return fail(ctx, rc, p->p.error);
+    if (ctx) ctx->refs.fetch_add(1);
     *out = p.release();
     return TSB_OK;
 }
@@ -603,7 +617,7 @@ int tsb_plan_finalize(tsb_plan* plan) {
     if (rc != TSB_OK) { plan->err = plan->p.error; return fail(plan->ctx, rc, plan->p.error); }
     return TSB_OK;
 }
-void tsb_plan_destroy(tsb_plan* plan) { delete plan; }
+void tsb_plan_destroy(tsb_plan* plan) { plan_release(plan); }
 const char* tsb_plan_error(tsb_plan* plan) { return plan ? plan->p.error.c_str() : ""; }
 
 int tsb_plan_size(const tsb_plan* plan, int* n_nodes, int* n_branches) {
@@ -681,6 +695,7 @@ int tsb_batch_create(tsb_plan* plan, int64_t n_inst, tsb_batch** out) {
     if (!plan->p.finalized) return fail(plan->ctx, TSB_E_INVALID, "plan is not finalized");
     tsb_batch* b = new tsb_batch;
     b->plan = plan; b->ctx = plan->ctx; b->n_inst = n_inst;
+    plan->refs.fetch_add(1);
     b->uniform = plan->p.nominal;
     b->varying.assign(plan->p.n_params, 0);
     b->var_slot.assign(plan->p.n_params, -1);
@@ -695,6 +710,7 @@ void tsb_batch_destroy(tsb_batch* b) {
         cudaFree(b->d_uniform);
         free_results(b);
     }
+    plan_release(b->plan);
     delete b;
 }
 
