@@ -65,3 +65,13 @@ def random_deck(seed: int, allow_inductor=True, allow_diode=True):
         tstop, tstep = 4e-4, 4e-6                   # inductor decks take ~50 x 300 steps whatever the span
     lines.append(f".tran {tstep:g} {tstop:g}")
     return "\n".join(lines) + "\n", dict(nodes=m, has_inductor=has_l, source=str(src))
+
+
+def rc_ladder(sections: int) -> str:
+    """Vin - (R - C to ground) x sections: n = sections + 2 unknowns, tridiagonal conductance block (no fill)."""
+    lines = [f"* RC ladder, {sections} sections", "Vin 1 0 SIN(0 5 1k)"]
+    for k in range(1, sections + 1):
+        lines.append(f"R{k} {k} {k + 1} 100")
+        lines.append(f"C{k} {k + 1} 0 100n")
+    lines.append(".tran 0.01ms 3ms")
+    return "\n".join(lines) + "\n"

@@ -44,3 +44,20 @@ def test_random_deck_matches_oracle(ctx, seed, mode):
     assert PU.report_ok(rep), (rep, text)
     assert rep["compared_points"] > 0
     assert rep["counter_mismatch"] <= 1, (rep, text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sections", [12, 24])
+def test_rc_ladder_beyond_the_bundled_sizes(ctx, sections):
+    """n = 14 and 26 unknowns: past the point where a circuit fits in one thread's registers (the generated kernel
+    spills to local memory) the thread-per-circuit path must still be CORRECT — it is the fallback until analysis
+    drivers exist on top of the warp-per-circuit LU."""
+    from random_decks import rc_ladder
+    text = rc_ladder(sections)
+    n = 6
+    ov = PU.draws("ladder", T.Circuit.from_netlist(text), n, seed=77)
+    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=1024)
+    _, ores = PU.run_oracle(text, n, ov, cap_rows=1024)
+    rep = PU.compare_waves(batch, ores, n)
+    assert PU.report_ok(rep), rep
+    assert rep["compared_points"] > 0 and rep["counter_mismatch"] == 0
