@@ -356,3 +356,28 @@ def test_context_may_be_destroyed_before_its_batches():
     c2.close()                                     # handle released; the library keeps the context until b and ckt are gone
     assert np.array_equal(b.stats_all(), s0)       # device buffers still valid
     del b, ckt
+
+
+def test_guard_bands_around_every_result_buffer(monkeypatch):
+    """compute-sanitizer is closed on this pool; TSB_GUARD=1 puts 256-byte guard bands around every result buffer and
+    tsb_batch_sync() fails if a kernel wrote into one.  With 1-, 3- and 33-instance batches the structure-of-arrays
+    strides (8, 24, 264 bytes) are inside or next to a band, so an off-by-one in a row / column / instance count of
+    any output mode (waveform, statistics, fixed grid, OP, DC sweep, lane refill) is caught."""
+    monkeypatch.setenv("TSB_GUARD", "1")
+    c2 = T.Context(0)
+    try:
+        for name in ("rc", "rlc", "diode2", "diode3", "diode1", "bjt2", "mosfet1", "transformer1", "vpwl"):
+            text = T.BUNDLED[name]
+            is_tran = T.Circuit.from_netlist(text).analysis_card()["analysis"] == T.AN_TRAN
+            for n in (1, 3, 33):
+                ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+                modes = [(T.OUT_WAVE, {"cap_rows": 7}), (T.OUT_STATS, {})]      # cap 7: overflow handling writes nothing past row 6
+                if is_tran:
+                    modes += [(T.OUT_GRID, {"grid_dt": 0.0}), (T.OUT_WAVE, {"cap_rows": 24000 if "rlc" in name or "transformer" in name else 512})]
+                for out, kw in modes:
+                    for refill in ((0, 1) if name in ("diode2", "bjt2") else (0,)):
+                        _, b, _ = PU.run_gpu(c2, text, n, ov, out=out, opts=T.default_opts(lane_refill=refill), **kw)   # Execute() syncs -> guard check
+                        b.sync()
+                        del b
+    finally:
+        c2.close()

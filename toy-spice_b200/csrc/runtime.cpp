@@ -80,6 +80,7 @@ struct tsb_ctx {
     // order (a garbage-collected host language releases them in no particular one): an object is torn down when its
     // owner has destroyed it AND nothing refers to it any more.
     std::atomic<int> refs{1};
+    bool guard = false;                                // $TSB_GUARD=1: result buffers carry guard bands checked at every sync
 };
 
 struct tsb_plan {
@@ -108,6 +109,7 @@ struct tsb_batch {
     unsigned long long* d_totals = nullptr;
     unsigned long long* d_work = nullptr;              // lane-refill work counter
     bool grid_kernel = false;                          // the next module request wants the TSB_OUT_GRID specialisation
+    std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -343,9 +345,55 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     return TSB_OK;
 }
 
+// Debug aid ($TSB_GUARD=1; compute-sanitizer is not available on every pool): every result buffer is allocated with a
+// 256-byte band of 0xA5 on each side; tsb_batch_sync() reads the bands back and fails with the name of the buffer
+// whose neighbourhood a kernel wrote to.  With small batches the structure-of-arrays strides are within a band, so
+// an off-by-one in a row / column / instance count is caught.
+const size_t TSB_GUARD_BYTES = 256;
+
+cudaError_t galloc(tsb_batch* b, void** p, size_t bytes) {
+    if (!b->ctx->guard) return cudaMalloc(p, bytes);
+    char* base = nullptr;
+    const size_t payload = (bytes + 15) / 16 * 16;
+    cudaError_t e = cudaMalloc((void**)&base, payload + 2 * TSB_GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(base, 0xA5, payload + 2 * TSB_GUARD_BYTES, b->ctx->stream);
+    *p = base + TSB_GUARD_BYTES;
+    b->guarded[*p] = payload;
+    return cudaSuccess;
+}
+template <class P> void gfree(tsb_batch* b, P*& p) {
+    if (!p) return;
+    auto it = b->guarded.find((void*)p);
+    if (it != b->guarded.end()) { cudaFree((char*)p - TSB_GUARD_BYTES); b->guarded.erase(it); }
+    else cudaFree(p);
+    p = nullptr;
+}
+int guard_check(tsb_batch* b) {
+    tsb_ctx* ctx = b->ctx;
+    if (!ctx->guard) return TSB_OK;
+    std::vector<unsigned char> h(TSB_GUARD_BYTES);
+    auto name_of = [&](void* p) -> const char* {
+        if (p == b->d_wave) return "wave"; if (p == b->d_stats) return "stats"; if (p == b->d_rows) return "rows";
+        if (p == b->d_status) return "status"; if (p == b->d_counters) return "counters"; if (p == b->d_scratch) return "scratch";
+        if (p == b->d_sweep) return "sweep"; return "buffer";
+    };
+    for (auto& kv : b->guarded) {
+        for (int side = 0; side < 2; ++side) {
+            const char* src = side == 0 ? (char*)kv.first - TSB_GUARD_BYTES : (char*)kv.first + kv.second;
+            CU(ctx, cudaMemcpy(h.data(), src, TSB_GUARD_BYTES, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < TSB_GUARD_BYTES; ++i)
+                if (h[i] != 0xA5)
+                    return fail(ctx, TSB_E_CUDA, std::string("TSB_GUARD: a kernel wrote ") + (side ? "past the end of" : "before the start of") +
+                                " the `" + name_of(kv.first) + "` buffer (offset " + std::to_string(side ? (long long)i : (long long)i - (long long)TSB_GUARD_BYTES) + ")");
+        }
+    }
+    return TSB_OK;
+}
+
 void free_results(tsb_batch* b) {
-    cudaFree(b->d_wave); cudaFree(b->d_stats); cudaFree(b->d_rows); cudaFree(b->d_status);
-    cudaFree(b->d_counters); cudaFree(b->d_scratch); cudaFree(b->d_sweep); cudaFree(b->d_totals); cudaFree(b->d_work);
+    gfree(b, b->d_wave); gfree(b, b->d_stats); gfree(b, b->d_rows); gfree(b, b->d_status);
+    gfree(b, b->d_counters); gfree(b, b->d_scratch); gfree(b, b->d_sweep); cudaFree(b->d_totals); cudaFree(b->d_work);
     b->d_work = nullptr;
     b->d_wave = b->d_stats = b->d_scratch = b->d_sweep = nullptr;
     b->d_rows = b->d_counters = nullptr; b->d_status = nullptr; b->d_totals = nullptr;
@@ -360,20 +408,20 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     size_t wave_bytes = (out_flags & (TSB_OUT_WAVE | TSB_OUT_GRID)) ? (size_t)cap_rows * ncol * N * sizeof(double) : 0;
     size_t stats_bytes = (out_flags & TSB_OUT_STATS) ? (size_t)4 * ncol * N * sizeof(double) : 0;
     if (wave_bytes != b->wave_bytes) {
-        cudaFree(b->d_wave); b->d_wave = nullptr; b->wave_bytes = 0;
-        if (wave_bytes) { CU(ctx, cudaMalloc(&b->d_wave, wave_bytes)); b->wave_bytes = wave_bytes; }
+        gfree(b, b->d_wave); b->wave_bytes = 0;
+        if (wave_bytes) { CU(ctx, galloc(b, (void**)&b->d_wave, wave_bytes)); b->wave_bytes = wave_bytes; }
     }
     if (stats_bytes != b->stats_bytes) {
-        cudaFree(b->d_stats); b->d_stats = nullptr; b->stats_bytes = 0;
-        if (stats_bytes) { CU(ctx, cudaMalloc(&b->d_stats, stats_bytes)); b->stats_bytes = stats_bytes; }
+        gfree(b, b->d_stats); b->stats_bytes = 0;
+        if (stats_bytes) { CU(ctx, galloc(b, (void**)&b->d_stats, stats_bytes)); b->stats_bytes = stats_bytes; }
     }
-    if (!b->d_rows) CU(ctx, cudaMalloc(&b->d_rows, N * sizeof(long long)));
-    if (!b->d_status) CU(ctx, cudaMalloc(&b->d_status, N * sizeof(int)));
-    if (!b->d_counters) CU(ctx, cudaMalloc(&b->d_counters, 8 * N * sizeof(long long)));
-    if (!b->d_scratch) CU(ctx, cudaMalloc(&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
+    if (!b->d_rows) CU(ctx, galloc(b, (void**)&b->d_rows, N * sizeof(long long)));
+    if (!b->d_status) CU(ctx, galloc(b, (void**)&b->d_status, N * sizeof(int)));
+    if (!b->d_counters) CU(ctx, galloc(b, (void**)&b->d_counters, 8 * N * sizeof(long long)));
+    if (!b->d_scratch) CU(ctx, galloc(b, (void**)&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
     if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 5 * sizeof(unsigned long long)));
     if (!b->d_work) CU(ctx, cudaMalloc(&b->d_work, sizeof(unsigned long long)));
-    if (n_sweep > 0) { cudaFree(b->d_sweep); b->d_sweep = nullptr; CU(ctx, cudaMalloc(&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
+    if (n_sweep > 0) { gfree(b, b->d_sweep); CU(ctx, galloc(b, (void**)&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
     b->analysis = analysis; b->ncol = ncol; b->out_flags = out_flags; b->cap_rows = cap_rows;
     return TSB_OK;
 }
@@ -524,6 +572,8 @@ int tsb_ctx_create(int device_ordinal, tsb_ctx** out) {
     ctx->stream = ctx->own_stream;
     const char* env = getenv("TSB_KCACHE");
     ctx->cache_dir = env && *env ? env : lib_dir() + "/_kcache";
+    const char* g = getenv("TSB_GUARD");
+    ctx->guard = g && *g && *g != '0';
     *out = ctx.release();
     return TSB_OK;
 }
@@ -861,7 +911,7 @@ int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc,
 int tsb_batch_sync(tsb_batch* b) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
-    return TSB_OK;
+    return guard_check(b);
 }
 
 // ---- results -----------------------------------------------------------------------------------
