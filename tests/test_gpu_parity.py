@@ -381,3 +381,19 @@ def test_guard_bands_around_every_result_buffer(monkeypatch):
                         del b
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("name", ["rc", "rlc", "diode2", "mosfet1"])
+def test_uic_and_start_time(ctx, name):
+    """`.tran ... uic` skips both operating points (tran.go:57-75, 82-91) and a start time > 0 suppresses the rows
+    before it (tran.go:140-142): the linear and the nonlinear transient loops entered without the OP state machine."""
+    text = T.BUNDLED[name]
+    n = 12
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    card = T.Circuit.from_netlist(text).analysis_card()
+    for tran in ({"uic": True}, {"tstart": 0.4 * card["tstop"]}, {"uic": True, "tstart": 0.25 * card["tstop"]}):
+        ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=24000, tran=tran)
+        _, ores = PU.run_oracle(text, n, ov, cap_rows=24000, tran=tran)
+        rep = PU.compare_waves(batch, ores, n)
+        assert PU.report_ok(rep), (tran, rep)
+        assert rep["compared_points"] > 0 and rep["counter_mismatch"] == 0, (tran, rep)
