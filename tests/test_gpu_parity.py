@@ -397,3 +397,23 @@ def test_uic_and_start_time(ctx, name):
         rep = PU.compare_waves(batch, ores, n)
         assert PU.report_ok(rep), (tran, rep)
         assert rep["compared_points"] > 0 and rep["counter_mismatch"] == 0, (tran, rep)
+
+
+def test_dc_sweep_statistics_and_descending_axis(ctx):
+    """Statistics of a DC sweep (column 0 = the sweep value: first / last row give its extremes) equal the reduction of
+    the waveform of the same run; every instance shares the sweep axis; nonlinear state continues from point to point
+    exactly as in the oracle (dc.go:88-140) for a 1000-instance batch that spans several warps and a tail."""
+    text = T.BUNDLED["diode3"]
+    n = 1000
+    ov = PU.draws("diode3", T.Circuit.from_netlist(text), n)
+    ckt, b, an = PU.run_gpu(ctx, text, n, ov, out=T.OUT_WAVE | T.OUT_STATS)
+    w, s, rows = b.wave_all(), b.stats_all(), b.rows()
+    npts = int(rows[0])             # -1 .. 3 by repeated += 0.1 (dc.go:36-42): 40 points, the last one falls just past 3
+    assert np.all(b.status() == 0) and np.all(rows == npts) and npts in (40, 41) and w.shape[0] == npts
+    assert np.array_equal(s[0], w.min(axis=0)) and np.array_equal(s[1], w.max(axis=0)) and np.array_equal(s[3], w[-1])
+    idx = np.random.default_rng(4).choice(n, 40, replace=False)
+    _, ores = PU.run_oracle(text, 40, {k: v[idx] for k, v in ov.items()})
+    assert np.all(ores["n_rows"] == npts)
+    ref = ores["wave"][:, :npts, :ores["ncol"]].transpose(1, 2, 0)
+    assert np.all(np.abs(w[:, :, idx] - ref) <= PU.RELTOL * np.abs(ref) + PU.ABSTOL)
+    assert np.array_equal(b.counters()[3, idx], ores["counters"][:, 3])            # Newton solves per instance, as the reference counts

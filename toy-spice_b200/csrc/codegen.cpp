@@ -399,7 +399,8 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("// MODE >= 0 fixes the analysis mode at compile time (the dedicated transient loop): mode selects fold away.");
     e.line("// EARLY = false (the dedicated linear transient loop): a zero pivot does not return before the solve — the body");
     e.line("// stays one basic block; the caller discards x when the result is false.");
-    e.line("template <int MODE, bool EARLY = true>");
+    e.line("// SOLVE = false: stamps only, for their side effects on device state (the DC sweep's discarded pass, dc.go:119-125).");
+    e.line("template <int MODE, bool EARLY = true, bool SOLVE = true>");
     e.line("__device__ __forceinline__ bool assemble_solve(int mode_rt, double time, double dt, double rdt, double gmin) {");
     ++e.ind;
     e.line("const int mode = MODE >= 0 ? MODE : mode_rt;");
@@ -413,6 +414,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
         emit_clear(e, pl.lu_main, n, fa ? &tg : nullptr);
         emit_stamps(e, pl, pl.lu_main, false, false, fa);
+        e.line("if (!SOLVE) return true;");
         e.line("double xt[" + std::to_string(n + 1) + "];");
         emit_lu(e, pl.lu_main, true, "xt", fa ? &bz : nullptr, "EARLY && !lu_ok");
     }
@@ -493,8 +495,8 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("        tsb_run_optran_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
     e.line("}");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
-    e.line("    for (long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x; inst < a.n_run; inst += (long long)gridDim.x * blockDim.x)");
-    e.line("        tsb_run_dc_instance<Ckt>(a, inst);");
+    e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
+    e.line("        tsb_run_dc_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
     e.line("}");
     return e.os.str();
 }

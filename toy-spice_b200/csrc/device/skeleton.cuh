@@ -619,43 +619,60 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
 }
 
 // ------------------------------------------------------------------------------------------------
-// DC sweep (dc.go:88-187): per sweep value one "wasted" stamp, then Newton with state continuation.
+// DC sweep (dc.go:88-187): per sweep value one stamp whose solution is never used, then Newton with state continuation.
+// The sweep values are the same for every instance, so the outer loop is warp-uniform; the Newton loop is
+// vote-controlled like the transient one (lanes that have converged wait for the slowest live lane, then the whole
+// warp stores the point together).  The discarded pass (dc.go:119-125: Stamp + LoadGmin + Solve before doNRiter)
+// keeps only what has an effect — the side effects of Stamp() on device state; its factor + solve, whose result the
+// first Newton iteration overwrites before anything reads it, are not executed.  `valid`: this lane has an instance
+// (every lane of a warp must call: full-mask votes).
 template <class Ckt>
-__device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long inst) {
+__device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long inst, bool valid) {
     constexpr int N = Ckt::N;
     Ckt c;
-    c.load(a, inst);
-    c.init();
     TsbSink<Ckt::NCOL_MAX> sink(a, inst);
-    long long n_sol = 0;
+    if (valid) { c.load(a, inst); c.init(); sink.begin(inst); }
+    int n_sol = 0, n_pts = 0;
     int status = TSB_ST_OK;
     double fail_at = 0.0;
-    int k = 0;
-    int iter = -1;                 // -1: the stamp before doNRiter whose solution is never used (dc.go:119-125)
-    if (a.n_sweep > 0) { c.set_dc(a.sweep[0]); c.eval_sources(0.0, 1.0); }
-    while (k < a.n_sweep) {
-        if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
-        bool solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, 0.0, iter < 0 ? 1e-12 : 0.0);
-        if (iter < 0) { iter = 0; continue; }
-        ++n_sol;
-        bool conv = false, fail = !solved;
-        if (solved) {
-            if (iter > 0) conv = tsb_converged_dc<N>(c.x, c.xo, a.reltol, a.abstol);
-            if (!conv) {
+    bool live = valid;
+    for (int k = 0; k < a.n_sweep && __any_sync(0xffffffffu, live); ++k) {
+        if (live) {
+            c.set_dc(a.sweep[k]);
+            c.eval_sources(0.0, 1.0);
+            (void)c.template assemble_solve<TSB_MODE_OP, true, false>(TSB_MODE_OP, 0.0, 0.0, 0.0, 1e-12);
+            ++n_pts;
+        }
+        int iter = 0;
+        bool conv = false, fail = false, iterating = live;
+        while (__any_sync(0xffffffffu, iterating)) {
+            if (iterating) {
+                if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
+                const bool solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, 0.0, 0.0);
+                ++n_sol;
+                if (!solved) fail = true;
+                else {
+                    if (iter > 0) conv = tsb_converged_dc<N>(c.x, c.xo, a.reltol, a.abstol);
+                    if (!conv) {
 #pragma unroll
-                for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
-                if (++iter >= a.max_iter) fail = true;
+                        for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+                        if (++iter >= a.max_iter) fail = true;
+                    }
+                }
+                iterating = !(conv || fail);
             }
         }
-        if (!conv && !fail) continue;
-        if (fail) { status = TSB_ST_DC_FAILED; fail_at = a.sweep[k]; break; }
-        double row[Ckt::NCOL_MAX];
-        row[0] = a.sweep[k];
-        c.signals(row + 1);
-        sink.push(row);
-        ++k;
-        if (k < a.n_sweep) { c.set_dc(a.sweep[k]); c.eval_sources(0.0, 1.0); iter = -1; }
+        if (live) {
+            if (fail) { status = TSB_ST_DC_FAILED; fail_at = a.sweep[k]; live = false; }
+            else {
+                double row[Ckt::NCOL_MAX];
+                row[0] = a.sweep[k];
+                c.signals(row + 1);
+                sink.push(row);
+            }
+        }
     }
+    if (!valid) return;
     if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
     sink.finish();
     a.status[inst] = status;
@@ -665,7 +682,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     a.counters[3 * a.n_inst + inst] = n_sol;
     a.counters[4 * a.n_inst + inst] = 0;
     a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
-    a.counters[6 * a.n_inst + inst] = n_sol + a.n_sweep;      // + the discarded stamp pass per sweep value
+    a.counters[6 * a.n_inst + inst] = n_sol;                  // factor + solve passes executed (the discarded pass solves nothing)
     a.counters[7 * a.n_inst + inst] = sink.n_rows;
 }
 
