@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(LU_THREADS, 4) tsb_k_lu_warp(const double* __r
     __syncthreads();
     double* tile = tile_all + group * W * LD;
     const int my_row = perm[lane];
+    const unsigned magic = (unsigned)((0x100000000ULL + (unsigned)n - 1) / (unsigned)n);   // ceil(2^32 / n), n >= 1
 
     for (long long base = (long long)blockIdx.x * GROUPS; base < n_inst; base += (long long)gridDim.x * GROUPS) {
         const long long inst = base + group;
@@ -80,7 +81,11 @@ __global__ void __launch_bounds__(LU_THREADS, 4) tsb_k_lu_warp(const double* __r
         // ---- stage the system: coalesced within the group ------------------------------------------
         if (live) {
             const double* Ai = A + inst * (long long)n * n;
-            for (int e = lane; e < n * n; e += W) tile[(e / n) * LD + (e % n)] = __ldcs(Ai + e);
+            // row = e / n by multiplication with ceil(2^32 / n) (exact for e < 2^16), not an integer division per element
+            for (int e = lane; e < n * n; e += W) {
+                const int r = (int)__umulhi((unsigned)e, magic);
+                tile[r * LD + (e - r * n)] = __ldcs(Ai + e);
+            }
         }
         __syncwarp();
         double a[W];
