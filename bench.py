@@ -388,6 +388,46 @@ def main():
     except Exception as ex:       # the FP64-bound headline must not depend on this extra measurement
         roofline_hbm = {"error": str(ex)[:200]}
 
+    # ---- the operator-level device-stamp kernel (HBM-write-bound: (n^2 + n) * 8 bytes per instance) -----------------
+    # rlc.cir transient companion stamps of 2^22 instances, coalesced through shared memory (tsb_stamp_staged); not part
+    # of `value` (the analysis kernels never materialise the matrix), reported as the stamp stage's own roofline
+    roofline_stamp = None
+    try:
+        ns = 1 << 22
+        rl = decks[-1]
+        nn = rl["ckt"].n
+        ovs = W.sweep_draws(rl["ckt"].devices(), ns, 99)
+        bs = rl["ckt"].batch(ns)
+        keep = []
+        for (d, p), v in ovs.items():
+            t = torch.from_numpy(v).to(f"cuda:{local}"); keep.append(t)
+            bs.set_param(d, p, t)
+        dA = torch.empty((ns, nn, nn), dtype=torch.float64, device=f"cuda:{local}")
+        dB = torch.empty((ns, nn), dtype=torch.float64, device=f"cuda:{local}")
+        ms_s = []
+        for i in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            bs.stamp_dev(T.AN_TRAN, 1e-4, 1e-6, 0.0, dA.data_ptr(), dB.data_ptr(), opts=opts)
+            e1.record(stream)
+            stream.synchronize()
+            if i > 0:
+                ms_s.append(e0.elapsed_time(e1))
+        sbytes = ns * ((nn * nn + nn) * 8 + len(ovs) * 8)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hp, hsrc = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            hp, hsrc = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        ach_s = sbytes / (min(ms_s) * 1e-3) / 1e9
+        roofline_stamp = {"bound": "hbm", "kernel": "tsb_stamp_staged (rlc.cir transient stamps, operator level)", "achieved": ach_s, "peak": hp,
+                          "unit": "GB/s", "frac": ach_s / hp, "traffic": None, "peak_source": hsrc, "algorithmic_bytes_per_launch": sbytes,
+                          "ms_per_launch": min(ms_s), "instances": ns}
+        del bs, dA, dB, keep
+    except Exception as ex:
+        roofline_stamp = {"error": str(ex)[:200]}
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,7 +449,7 @@ def main():
             "executed_solves_per_step": exec_job,
             "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world},
             "gpu_launches": int(launches), "failed_instances": bad_status,
-            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

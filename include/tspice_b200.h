@@ -229,6 +229,13 @@ int tsb_result_totals(tsb_batch* batch, int64_t totals[5]);
  * structurally dense matrix, relative threshold 1e-3, diagonal preference), Translate numbering =
  * row-major first touch.  Host only (ctx not needed). */
 int tsb_lu_order(int n, const double* A_nominal, int* pivot_row, int* pivot_col);
+/* The device-stamp kernel on its own (pkg/device Stamp of every device of every instance, circuit.go:165-176): the
+ * dense system after mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin) on a freshly set-up circuit, status =
+ * {Mode = mode (TSB_AN_OP or TSB_AN_TRAN), Time = time, TimeStep = dt, Gmin = gmin}, written to device memory as
+ * A[inst][n][n] (row-major) and b[inst][n], 0-based = MNA index - 1.  With tsb_lu_solve_batched_dev and the plan's
+ * own pivot order (tsb_plan_structure) it forms the two-kernel version of one Newton iteration.  Asynchronous. */
+int tsb_batch_stamp_dev(tsb_batch* batch, int mode, double time, double dt, double gmin, uint64_t A_dev, uint64_t b_dev,
+                        const tsb_opts* opts);
 int tsb_lu_solve_batched(tsb_ctx* ctx, int n, const int* pivot_row, const int* pivot_col, const double* A, const double* b,
                          double* x, int32_t* status, int64_t n_inst, int strict_fp);
 /* Same with every array already in HBM (device pointers); asynchronous on the context's stream. */

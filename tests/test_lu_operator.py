@@ -108,3 +108,59 @@ def test_device_pointer_entry_and_permutation_equivariance(ctx):
     perm = np.random.default_rng(1).permutation(n_inst)
     x2, st2 = ctx.lu_solve_batched(A[perm], b[perm], order, strict=True)
     assert np.array_equal(x2, x1[perm]) and np.all(st2 == 0) and int(dst.sum()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rr", "rc", "rlc", "transformer1", "transformer2"])
+def test_two_kernel_newton_iteration_equals_the_fused_kernel(ctx, name):
+    """Operator-level pipeline: device-stamp kernel (tsb_batch_stamp_dev) -> warp-per-circuit LU (strict, the plan's own
+    pivot order) reproduces, bit for bit, the operating point the fused thread-per-circuit analysis kernel computes
+    for a linear circuit (its Newton loop solves exactly this system)."""
+    import torch
+    text = T.BUNDLED[name]
+    n_inst = 1000
+    ckt = T.Circuit.from_netlist(text, ctx)
+    n = ckt.n
+    ov = PU.draws(name, ckt, n_inst)
+    b = ckt.batch(n_inst)
+    for (d, p), v in ov.items():
+        b.set_param(d, p, v)
+    strict = T.default_opts(strict_fp=1)
+    dA = torch.full((n_inst, n, n), float("nan"), dtype=torch.float64, device="cuda")
+    db = torch.full((n_inst, n), float("nan"), dtype=torch.float64, device="cuda")
+    dx = torch.empty_like(db); dst = torch.empty(n_inst, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    b.stamp_dev(T.AN_OP, 0.0, 0.0, 0.0, dA.data_ptr(), db.data_ptr(), opts=strict)
+    st = ckt.structure()
+    ctx.lu_solve_batched_dev(n, n_inst, dA.data_ptr(), db.data_ptr(), dx.data_ptr(), dst.data_ptr(), (st["pivot_row"], st["pivot_col"]), strict=True)
+    b.sync()
+    torch.cuda.synchronize()
+    assert not torch.isnan(dA).any() and not torch.isnan(db).any() and int(dst.sum()) == 0
+    b.run_op(strict)
+    b.sync()
+    x_fused = b.wave_all()[0].T                            # OP row: [n columns = x[1..n]][n_inst] -> [n_inst, n]
+    assert np.array_equal(dx.cpu().numpy(), x_fused), name
+
+
+@pytest.mark.gpu
+def test_stamp_kernel_transient_companion_models(ctx):
+    """rc.cir in transient mode at (t, dt): G + C/dt and the source value, written by the stamp kernel."""
+    import torch
+    n_inst = 257
+    ckt = T.Circuit.from_netlist(T.BUNDLED["rc"], ctx)
+    ov = PU.draws("rc", ckt, n_inst)
+    b = ckt.batch(n_inst)
+    for (d, p), v in ov.items():
+        b.set_param(d, p, v)
+    dA = torch.zeros((n_inst, 3, 3), dtype=torch.float64, device="cuda"); db = torch.zeros((n_inst, 3), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    t, dt = 1.25e-4, 2e-7
+    b.stamp_dev(T.AN_TRAN, t, dt, 0.0, dA.data_ptr(), db.data_ptr(), opts=T.default_opts(strict_fp=1))
+    b.sync(); torch.cuda.synchronize()
+    A, rhs = dA.cpu().numpy(), db.cpu().numpy()
+    g = 1.0 / ov[("r1", 0)]; geq = ov[("c1", 0)] / dt
+    ref = np.zeros((n_inst, 3, 3))
+    ref[:, 0, 0] = g; ref[:, 0, 1] = -g; ref[:, 1, 0] = -g; ref[:, 1, 1] = g + geq; ref[:, 2, 0] = 1.0; ref[:, 0, 2] = 1.0
+    assert np.array_equal(A, ref)
+    assert np.array_equal(rhs[:, :2], np.zeros((n_inst, 2)))                      # fresh capacitor: charge1 = 0
+    assert np.allclose(rhs[:, 2], 5.0 * np.sin(2 * np.pi * 1000.0 * t), rtol=4e-16, atol=0)

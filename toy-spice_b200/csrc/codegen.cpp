@@ -423,6 +423,32 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     --e.ind;
     e.line("}");
 
+    // ---- operator level: the stamped system itself -----------------------------------------------------
+    // mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin) as a DENSE n x n matrix + right-hand side written to
+    // global memory, instance-major (A[inst][row][col], b[inst][row], 0-based = external index - 1): what a
+    // host that keeps its own Solve() — or the warp-per-circuit LU operator — consumes.
+    {
+        LuProgram dn;                       // index map of the dense layout (no elimination program needed)
+        dn.n = n;
+        for (int r = 1; r <= n; ++r)
+            for (int c2 = 1; c2 <= n; ++c2) { dn.index[{r, c2}] = (int)dn.pos.size(); dn.pos.push_back({r, c2}); }
+        e.line("__device__ __forceinline__ void stamp_dense(int mode, double time, double dt, double rdt, double gmin, double* __restrict__ Aout, double* __restrict__ bout) {");
+        ++e.ind;
+        e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin; e.rdt = rdt;");
+        e.line("double A[" + std::to_string(n * n) + "];");
+        e.line("double b[" + std::to_string(n + 1) + "];");
+        emit_clear(e, dn, n, nullptr);
+        emit_stamps(e, pl, dn, false, false, false);
+        e.line("if (gmin != 0.0) {   // LoadGmin: onto the pivot positions of the frozen order (SURVEY Q17)");
+        for (int k = 1; k <= n; ++k)
+            e.line("    A[" + std::to_string(dn.index[{pl.lu_main.prow[k], pl.lu_main.pcol[k]}]) + "] += gmin;");
+        e.line("}");
+        for (int k = 0; k < n * n; ++k) e.line("Aout[" + std::to_string(k) + "] = A[" + std::to_string(k) + "];");
+        for (int i = 1; i <= n; ++i) e.line("bout[" + std::to_string(i - 1) + "] = b[" + std::to_string(i) + "];");
+        --e.ind;
+        e.line("}");
+    }
+
     // ---- time-dependent device state -------------------------------------------------------------
     auto vd_expr = [&](const Dev& d) {
         return "(x[" + std::to_string(d.nodes[0]) + "] - x[" + std::to_string(d.nodes[1]) + "])";
@@ -494,6 +520,40 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_optran_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
     e.line("}");
+    e.line("// Operator level: stamp every instance (fresh device state, sources at a.tstart) -> a.wave = A, a.stats = b.");
+    e.line("// tsb_stamp: every thread stores its own system straight to HBM (instances are (N*N+N)*8 bytes apart: 32 scattered");
+    e.line("// 8-byte words per store instruction).  tsb_stamp_staged: the block's systems are contiguous in the instance-major");
+    e.line("// layout, so they are assembled in shared memory (odd row stride: conflict-free) and written out with coalesced");
+    e.line("// stores — the HBM-bound form; used whenever blockDim.x * ((N*N+N)|1) doubles fit in shared memory.");
+    e.line("template <bool STAGED> __device__ __forceinline__ void tsb_stamp_body(const TsbArgs& a) {");
+    e.line("    constexpr int NA = Ckt::N * Ckt::N, NB = Ckt::N, LD = (NA + NB) | 1;");
+    e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x) {");
+    e.line("        const long long inst = base + threadIdx.x;");
+    e.line("        const bool valid = inst < a.n_run;");
+    e.line("        double* mine = STAGED ? tsb_smem + (long long)threadIdx.x * LD : a.wave + inst * (long long)NA;");
+    e.line("        double* mine_b = STAGED ? mine + NA : a.stats + inst * (long long)NB;");
+    e.line("        if (valid) {");
+    e.line("            Ckt c;");
+    e.line("            c.load(a, inst);");
+    e.line("            c.init();");
+    e.line("            c.eval_sources(a.tstart, 1.0);");
+    e.line("            const double dt = a.tstep;");
+    e.line("            c.stamp_dense(a.analysis, a.tstart, dt, dt > 0 ? 1.0 / dt : 0.0, a.minstep, mine, mine_b);   // status.Gmin travels in `minstep`");
+    e.line("        }");
+    e.line("        if (STAGED) {");
+    e.line("            __syncthreads();");
+    e.line("            const long long left = a.n_run - base;");
+    e.line("            const int nvalid = left < (long long)blockDim.x ? (int)left : (int)blockDim.x;");
+    e.line("            double* ga = a.wave + base * (long long)NA;");
+    e.line("            for (int q = threadIdx.x; q < nvalid * NA; q += blockDim.x) { const int t = q / NA; __stcs(ga + q, tsb_smem[t * LD + (q - t * NA)]); }");
+    e.line("            double* gb = a.stats + base * (long long)NB;");
+    e.line("            for (int q = threadIdx.x; q < nvalid * NB; q += blockDim.x) { const int t = q / NB; __stcs(gb + q, tsb_smem[t * LD + NA + (q - t * NB)]); }");
+    e.line("            __syncthreads();");
+    e.line("        }");
+    e.line("    }");
+    e.line("}");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_stamp(TsbArgs a) { tsb_stamp_body<false>(a); }");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_stamp_staged(TsbArgs a) { tsb_stamp_body<true>(a); }");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
     e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_dc_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");

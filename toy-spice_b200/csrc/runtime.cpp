@@ -62,7 +62,7 @@ struct TsbArgsHost {
 
 struct KernelModule {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t optran = nullptr, dc = nullptr;
+    cudaKernel_t optran = nullptr, dc = nullptr, stamp = nullptr, stamp_staged = nullptr;
     int info_regs = -1, info_spill = -1, min_blocks = 0;
 };
 
@@ -81,6 +81,7 @@ struct tsb_ctx {
     // owner has destroyed it AND nothing refers to it any more.
     std::atomic<int> refs{1};
     bool guard = false;                                // $TSB_GUARD=1: result buffers carry guard bands checked at every sync
+    long long choice_epoch = 0;                        // bumped whenever auto_choice changes (invalidates batch memos)
 };
 
 struct tsb_plan {
@@ -110,6 +111,10 @@ struct tsb_batch {
     unsigned long long* d_work = nullptr;              // lane-refill work counter
     bool grid_kernel = false;                          // the next module request wants the TSB_OUT_GRID specialisation
     std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
+    // memo of the last module request: generating the kernel source to derive its cache key costs ~0.3 ms of host
+    // time, which is the length of a short launch (the stamp kernel); identical requests skip it
+    std::string memo_sig, memo_autokey;
+    KernelModule* memo_module = nullptr;
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -290,7 +295,35 @@ int obtain_cubin(tsb_ctx* ctx, const std::string& src, const std::string& key, c
 const int TSB_SPILL_OK = 100;
 const int TSB_MAX_MIN_BLOCKS = 6;
 
+int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::string* autokey_out);
+
 int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::string* autokey_out = nullptr) {
+    tsb_ctx* ctx = b->ctx;
+    std::string sig;
+    sig.reserve(b->varying.size() + 96);
+    sig.append(b->varying.begin(), b->varying.end());
+    const char* xd = getenv("TSB_EXTRA_DEFINES");
+    char tail[160];
+    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
+             (int)b->grid_kernel, dc_param, ctx->choice_epoch, (void*)ctx);
+    sig += tail;
+    if (xd) sig += xd;
+    if (b->memo_module && sig == b->memo_sig) {
+        *out = b->memo_module;
+        if (autokey_out) *autokey_out = b->memo_autokey;
+        return TSB_OK;
+    }
+    std::string autokey;
+    const long long epoch0 = ctx->choice_epoch;
+    int rc = get_module_uncached(b, o, dc_param, out, &autokey);
+    if (rc != TSB_OK) return rc;
+    if (autokey_out) *autokey_out = autokey;
+    if (ctx->choice_epoch == epoch0) { b->memo_sig = sig; b->memo_autokey = autokey; b->memo_module = *out; }   // pointers into ctx->modules are stable (std::map)
+    else b->memo_module = nullptr;
+    return TSB_OK;
+}
+
+int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::string* autokey_out) {
     tsb_ctx* ctx = b->ctx;
     std::vector<char> cubin;
     KernelInfo info;
@@ -326,7 +359,7 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
             std::ofstream f(ctx->cache_dir + "/" + autokey + ".auto");
             f << chosen << "\n";
         }
-        ctx->auto_choice[autokey] = chosen;
+        if (!ctx->auto_choice.count(autokey) || ctx->auto_choice[autokey] != chosen) { ctx->auto_choice[autokey] = chosen; ++ctx->choice_epoch; }
         o.min_blocks = chosen;
     }
     src = generate_source(b->plan->p, make_config(b, o, dc_param));
@@ -339,6 +372,8 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     CU(ctx, cudaLibraryLoadData(&m.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     CU(ctx, cudaLibraryGetKernel(&m.optran, m.lib, "tsb_optran"));
     CU(ctx, cudaLibraryGetKernel(&m.dc, m.lib, "tsb_dc"));
+    CU(ctx, cudaLibraryGetKernel(&m.stamp, m.lib, "tsb_stamp"));
+    CU(ctx, cudaLibraryGetKernel(&m.stamp_staged, m.lib, "tsb_stamp_staged"));
     m.info_regs = info.regs; m.info_spill = info.spill_st; m.min_blocks = o.min_blocks;
     ctx->modules[key] = m;
     *out = &ctx->modules[key];
@@ -531,6 +566,7 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->auto_choice[autokey] = best;
+    ++ctx->choice_epoch;
     ctx->tuned[autokey] = best;
     std::ofstream f(ctx->cache_dir + "/" + autokey + ".tuned");
     f << best << "\n";
@@ -906,6 +942,50 @@ int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc,
     CU(ctx, cudaStreamSynchronize(ctx->stream));     // `sweep` is a stack vector
     a.analysis = TSB_AN_DC; a.sweep = b->d_sweep; a.n_sweep = (int)sweep.size();
     return launch(b, o, m->dc, a);
+}
+
+// Operator level: the device-stamp kernel on its own.  Writes, for every instance, the dense MNA system the reference
+// holds after mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin) on a freshly set-up circuit (device state as
+// SetupDevices leaves it), with status = {Mode, Time, TimeStep = dt, Gmin}: A[inst][n][n] row-major and b[inst][n]
+// (0-based = MNA index - 1), device pointers.  Together with tsb_lu_solve_batched_dev (pivot order from
+// tsb_plan_structure) this is the two-kernel form of one Newton iteration: an HBM-bound stamp kernel and a
+// compute-bound factor + solve kernel.
+int tsb_batch_stamp_dev(tsb_batch* b, int mode, double time, double dt, double gmin, uint64_t A_dev, uint64_t b_dev, const tsb_opts* opts) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    if (!A_dev || !b_dev || (mode != 0 && mode != 1)) return fail(ctx, TSB_E_INVALID, "tsb_batch_stamp_dev: mode must be 0 (OP) or 1 (transient), outputs non-null");
+    tsb_opts o = resolve(opts, b->plan->p);
+    CU(ctx, cudaSetDevice(ctx->device));
+    KernelModule* m = nullptr;
+    if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;       // parameters only: no result buffers are needed here
+    a.analysis = mode; a.tstart = time; a.tstep = dt; a.minstep = gmin;    // tsb_stamp reads status.Gmin from `minstep`
+    a.wave = (double*)(uintptr_t)A_dev; a.stats = (double*)(uintptr_t)b_dev;
+    a.out_flags = 0;
+    // Staged (coalesced) form whenever the block's systems fit in shared memory: threads per block = the largest
+    // multiple of 32 (<= the configured block size) with threads * ((n*n+n)|1) doubles <= 200 KB.
+    const int n = b->plan->p.n();
+    const size_t per_thread = (size_t)(((n * n + n) | 1)) * sizeof(double);
+    int block = o.block_size > 0 ? o.block_size : 128;
+    int staged_threads = (int)(200 * 1024 / per_thread) / 32 * 32;
+    if (staged_threads > block) staged_threads = block;
+    const char* env = getenv("TSB_STAMP_DIRECT");
+    const bool staged = staged_threads >= 32 && !(env && *env == '1');
+    cudaKernel_t kern = staged ? m->stamp_staged : m->stamp;
+    size_t smem = 0;
+    if (staged) {
+        block = staged_threads;
+        smem = (size_t)block * per_thread;
+        if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    long long blocks = (b->n_inst + block - 1) / block;
+    long long resident = (long long)ctx->sms * 32;             // grid-stride over blocks of instances
+    if (blocks > resident) blocks = resident;
+    void* kargs[] = {&a};
+    CU(ctx, cudaLaunchKernel((const void*)kern, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
+    ++ctx->launches;
+    return TSB_OK;
 }
 
 int tsb_batch_sync(tsb_batch* b) {
