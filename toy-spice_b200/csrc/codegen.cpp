@@ -100,7 +100,10 @@ std::set<std::string> stamp_targets(const Plan& pl, const LuProgram& lu, bool li
 
 // Zero-initialisation of A[] and b[] (mat.Clear()).  With `first_assign` only the entries no stamp writes are
 // zeroed: the first stamp into an entry then ASSIGNS instead of accumulating onto 0.0 (emit_stamps) — ptxas cannot
-// fold 0.0 + x (it is not x for x = -0.0) and the first profile showed one DADD RZ per stamped entry.
+// fold 0.0 + x (it is not x for x = -0.0) and the first profile showed one DADD RZ per stamped entry.  Values are
+// unchanged (0.0 + x == x for every x but -0.0, whose sign no later operation of the solve can turn into a
+// different number short of a division by that zero, i.e. a zero pivot, which is a failure either way), so the
+// strict build uses it too; dense (BJT) builds keep the literal accumulate for their NaN / Inf bookkeeping.
 void emit_clear(Emitter& e, const LuProgram& lu, int n, const std::set<std::string>* assigned) {
     for (size_t k = 0; k < lu.pos.size(); ++k) {
         std::string t = "A[" + std::to_string(k) + "]";
@@ -379,7 +382,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         e.line("double A[" + std::to_string(pl.lu_init.pos.size()) + "];");
         e.line("double b[" + std::to_string(n + 1) + "];");
         {
-            const bool fa = cfg.fast_div && !pl.lu_init.dense;
+            const bool fa = !pl.lu_init.dense;      // also in the strict build: only the sign of a zero can differ
             std::set<std::string> tg = stamp_targets(pl, pl.lu_init, true, true);
             std::set<int> bz;
             for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
@@ -408,7 +411,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("double A[" + std::to_string(pl.lu_main.pos.size()) + "];");
     e.line("double b[" + std::to_string(n + 1) + "];");
     {
-        const bool fa = cfg.fast_div && !pl.lu_main.dense;
+        const bool fa = !pl.lu_main.dense;      // also in the strict build: only the sign of a zero can differ
         std::set<std::string> tg = stamp_targets(pl, pl.lu_main, false, false);
         std::set<int> bz;
         for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
