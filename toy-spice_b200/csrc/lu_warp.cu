@@ -62,40 +62,39 @@ __global__ void __launch_bounds__(LU_THREADS, 4) tsb_k_lu_warp(const double* __r
     constexpr int LD = W + 1;                       // padded row stride of the staging tile (bank-conflict-free columns)
     extern __shared__ double smem[];
     double* tile_all = smem;                        // GROUPS * W * LD doubles
-    int* perm = reinterpret_cast<int*>(smem + GROUPS * W * LD);   // prow[W], pcol[W] (0-based; identity beyond n)
+    int* perm = reinterpret_cast<int*>(smem + GROUPS * W * LD);   // 4 * W ints, see below
     const int lane = threadIdx.x % W;
     const int group = threadIdx.x / W;
+    // perm[0..W): prow, perm[W..2W): pcol (identity beyond n); perm[2W..3W): inverse of prow, perm[3W..4W): inverse of pcol
     if (threadIdx.x < 2 * W) {
         const int k = threadIdx.x % W;
         const int* src = threadIdx.x < W ? prow : pcol;
-        perm[threadIdx.x] = k < n ? src[k] : k;
+        const int v = k < n ? src[k] : k;
+        perm[threadIdx.x] = v;
+        perm[(threadIdx.x < W ? 2 * W : 3 * W) + v] = k;
     }
-    __syncthreads();
     double* tile = tile_all + group * W * LD;
-    const int my_row = perm[lane];
-    const unsigned magic = (unsigned)((0x100000000ULL + (unsigned)n - 1) / (unsigned)n);   // ceil(2^32 / n), n >= 1
+    // The tile holds the system in INTERNAL order (row k = pivot row k, column j = pivot column j) inside an identity
+    // matrix of order W: the padding is written once, the n x n part is overwritten for every system, and a lane
+    // reads its row with compile-time offsets — no index arithmetic or selects per element.
+    for (int e = lane; e < W * W; e += W) tile[(e / W) * LD + lane] = (e / W == lane) ? 1.0 : 0.0;
+    __syncthreads();
+    const int my_row = perm[lane];                  // external row owned by this lane (output / right-hand side)
+    const int my_col_int = perm[3 * W + lane];      // internal column of external column `lane` (staging)
 
     for (long long base = (long long)blockIdx.x * GROUPS; base < n_inst; base += (long long)gridDim.x * GROUPS) {
         const long long inst = base + group;
         const bool live = inst < n_inst;
-        // ---- stage the system: coalesced within the group ------------------------------------------
-        if (live) {
+        // ---- stage the system row by row: lanes = external columns (coalesced), scattered into internal order ----
+        if (live && lane < n) {
             const double* Ai = A + inst * (long long)n * n;
-            // row = e / n by multiplication with ceil(2^32 / n) (exact for e < 2^16), not an integer division per element
-            for (int e = lane; e < n * n; e += W) {
-                const int r = (int)__umulhi((unsigned)e, magic);
-                tile[r * LD + (e - r * n)] = __ldcs(Ai + e);
-            }
+            for (int r = 0; r < n; ++r) tile[perm[2 * W + r] * LD + my_col_int] = __ldcs(Ai + r * n + lane);   // (unrolling by 8 measured slower)
         }
         __syncwarp();
         double a[W];
         double c = 0.0;
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            double v = (j == lane) ? 1.0 : 0.0;                   // identity padding beyond n
-            if (live && lane < n && j < n) v = tile[my_row * LD + perm[W + j]];
-            a[j] = v;
-        }
+        for (int j = 0; j < W; ++j) a[j] = tile[lane * LD + j];
         if (live && lane < n) c = __ldcs(b + inst * (long long)n + my_row);
         __syncwarp();
         bool ok = true;
@@ -198,7 +197,7 @@ template <int W, bool STRICT>
 cudaError_t launch_lu(const double* A, const double* b, double* x, int* status, long long n_inst, int n, const int* prow,
                       const int* pcol, int sms, cudaStream_t s) {
     constexpr int GROUPS = LU_THREADS / W;
-    const size_t smem = (size_t)GROUPS * W * (W + 1) * sizeof(double) + 2 * W * sizeof(int);
+    const size_t smem = (size_t)GROUPS * W * (W + 1) * sizeof(double) + 4 * W * sizeof(int);
     auto kern = tsb_k_lu_warp<W, STRICT>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long want = (n_inst + GROUPS - 1) / GROUPS;
