@@ -417,3 +417,34 @@ def test_dc_sweep_statistics_and_descending_axis(ctx):
     ref = ores["wave"][:, :npts, :ores["ncol"]].transpose(1, 2, 0)
     assert np.all(np.abs(w[:, :, idx] - ref) <= PU.RELTOL * np.abs(ref) + PU.ABSTOL)
     assert np.array_equal(b.counters()[3, idx], ores["counters"][:, 3])            # Newton solves per instance, as the reference counts
+
+
+def test_diode_solutions_satisfy_kirchhoff_independently_of_the_oracle(ctx):
+    """Physics pin that does not go through the oracle: diode1.cir operating points and every point of the diode3.cir DC
+    sweep satisfy (V1 - V2)/R = Is*(exp(vd/(N*Vt)) - 1) (+ the model's 1e-12 S leakage inside the Jacobian only) to the
+    accuracy the reference's own Newton tolerance implies."""
+    vt = 1.3806226e-23 * 300.15 / 1.6021918e-19
+    n = 4096
+    # diode1: vin - r1 - d1 to ground
+    text = T.BUNDLED["diode1"]
+    ov = PU.draws("diode1", T.Circuit.from_netlist(text), n)
+    ckt, b, an = PU.run_gpu(ctx, text, n, ov)
+    w = b.wave_all()[0]                                     # [ncol, n]: V(1), V(2), I(vin)
+    cols = ckt.columns(T.AN_OP)
+    v1, v2 = w[cols.index("V(1)")], w[cols.index("V(2)")]
+    i_r = (v1 - v2) / ov[("r1", 0)]
+    i_d = ov[("d1", 0)] * (np.exp(v2 / (ov[("d1", 1)] * vt)) - 1.0)
+    assert np.all(b.status() == 0) and np.all(np.abs(i_r - i_d) <= 2e-5 * np.abs(i_r))
+    # diode3: Vin swept -1 .. 3, d1 between nodes 1 and 2, r1 to ground
+    text = T.BUNDLED["diode3"]
+    ov = PU.draws("diode3", T.Circuit.from_netlist(text), n)
+    ckt, b, an = PU.run_gpu(ctx, text, n, ov)
+    w = b.wave_all()                                        # [points, ncol, n]
+    cols = ckt.columns(T.AN_DC)
+    v1, v2 = w[:, cols.index("V(1)")], w[:, cols.index("V(2)")]
+    vd = v1 - v2
+    nvt = ov[("d1", 1)] * vt
+    i_d = np.where(vd > -3.0 * nvt, ov[("d1", 0)] * (np.exp(np.minimum(vd / nvt, 40.0)) - 1.0), -ov[("d1", 0)])   # diode.go:119-135
+    i_r = v2 / ov[("r1", 0)]
+    assert np.all(b.status() == 0)
+    assert np.all(np.abs(i_r - i_d) <= 2e-5 * np.abs(i_d) + 1e-11)

@@ -185,3 +185,25 @@ def test_threaded_runner_is_deterministic():
     a = oc.run(64, overrides=ov, threads=1, cap_rows=320)
     b = oc.run(64, overrides=ov, threads=4, cap_rows=320)
     assert np.array_equal(a["wave"], b["wave"], equal_nan=True) and np.array_equal(a["counters"], b["counters"])
+
+
+def test_diode_operating_point_satisfies_kirchhoff():
+    """Oracle-independent pin of the nonlinear path: at the converged operating point of diode1.cir the resistor current
+    equals the diode current of the model equation (diode.go:119-135: Is*(exp(vd/(N*Vt)) - 1), Vt = k*300.15/q), for a
+    spread of Is / N draws.  (The reference's Newton test is relative 1e-6 on the solution, so the residual is ~1e-6.)"""
+    import parity_util as PU
+    T, O = PU.T, PU.O
+    text = T.BUNDLED["diode1"]
+    n = 64
+    ckt = T.Circuit.from_netlist(text)
+    ov = PU.draws("diode1", ckt, n)
+    res = O.OracleCircuit(text).run(n, overrides=ov)
+    names = res["signals"]
+    v1 = res["wave"][:, 0, names.index("V(1)")]; v2 = res["wave"][:, 0, names.index("V(2)")]
+    Is, N = ov[("d1", 0)], ov[("d1", 1)]
+    vt = 1.3806226e-23 * 300.15 / 1.6021918e-19
+    i_r = (v1 - v2) / ov[("r1", 0)]
+    i_d = Is * (np.exp(v2 / (N * vt)) - 1.0)
+    assert np.all(res["status"] == 0)
+    assert np.all(np.abs(i_r - i_d) <= 2e-5 * np.abs(i_r)), float(np.max(np.abs(i_r - i_d) / np.abs(i_r)))
+    assert np.all((v2 > 0.3) & (v2 < 1.6)) and np.allclose(v1, 5.0)
