@@ -5,12 +5,17 @@
 // The drivers are templated on a generated struct `Ckt` (codegen.cpp) that provides the
 // netlist-specific straight-line code (stamps, LU in the frozen pivot order, state updates).
 //
-// The drivers are written as ONE loop around ONE Newton-iteration body: every trip through
-// the loop performs exactly one "stamp + factor + solve + convergence test" for every live lane,
-// whatever phase that lane is in (operating point, Gmin stepping, source stepping, transient
-// step k, a rejected step being retried).  Lanes of a warp therefore never wait for each other
-// at step boundaries — a lane that needs 5 Newton iterations and its neighbour that needs 2 both
-// do useful work on every trip; only lanes that have finished idle until the warp's slowest lane is done.
+// Drivers in this file (each entered by WHOLE warps: lanes without an instance only take part in the votes):
+//   tsb_run_optran_instance  operating point(s) as one loop around one Newton-iteration body (a small state machine:
+//                            main loop, Gmin stepping, source stepping), then hands the transient to
+//   tsb_tran_linear          circuits without nonlinear devices: one solve per step, LTE test before the solve,
+//                            branch-free step body;
+//   tsb_tran_nonlinear       circuits with nonlinear devices: time loop and Newton loop as two nested loops whose
+//                            trip counts are decided by warp votes (per-lane convergence predicate; converged lanes
+//                            wait for the slowest live lane, post-Newton work runs once per step for the warp);
+//   tsb_run_dc_instance      DC sweep: warp-uniform sweep loop, vote-controlled Newton loop.
+// With lane refill (TSB_LANE_REFILL) the state machine also runs the transient, free-running per lane.
+// Compile-time A/B switches (TSB_X_*) keep every measured alternative buildable; profiles/r01_notes.md has the numbers.
 //
 // Reference behaviour reproduced (statement by statement; see SURVEY.md §3.6 for the quirks):
 //   OperatingPoint.Execute / doNRiter / calculateInitialEstimate / performSourceStepping   op.go:25-233
