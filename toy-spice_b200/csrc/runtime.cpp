@@ -409,9 +409,12 @@ int guard_check(tsb_batch* b) {
     if (!ctx->guard) return TSB_OK;
     std::vector<unsigned char> h(TSB_GUARD_BYTES);
     auto name_of = [&](void* p) -> const char* {
-        if (p == b->d_wave) return "wave"; if (p == b->d_stats) return "stats"; if (p == b->d_rows) return "rows";
-        if (p == b->d_status) return "status"; if (p == b->d_counters) return "counters"; if (p == b->d_scratch) return "scratch";
-        if (p == b->d_sweep) return "sweep"; return "buffer";
+        const std::pair<const void*, const char*> known[] = {
+            {b->d_wave, "wave"}, {b->d_stats, "stats"}, {b->d_rows, "rows"}, {b->d_status, "status"},
+            {b->d_counters, "counters"}, {b->d_scratch, "scratch"}, {b->d_sweep, "sweep"}};
+        for (const auto& kn : known)
+            if (p == kn.first) return kn.second;
+        return "buffer";
     };
     for (auto& kv : b->guarded) {
         for (int side = 0; side < 2; ++side) {
