@@ -381,7 +381,7 @@ def main():
             hbm_peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
         ach = alg_bytes / (min(ms_w) * 1e-3) / 1e9
         roofline_hbm = {"bound": "hbm", "kernel": "tsb_optran (rc.cir, TSB_OUT_WAVE)", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": src,
+                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("rc", n, "wave"), "peak_source": src,
                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": min(ms_w),
                         "circuit_timesteps_per_sec": rows_total / (min(ms_w) * 1e-3)}
         del bw
