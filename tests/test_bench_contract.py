@@ -1,0 +1,58 @@
+"""The JSON line bench.py prints (the driver's contract), checked on the lines recorded on B200s under profiles/ and —
+on a GPU box — on a short live run."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check_line(d, reference=False):
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"):
+        assert k in d, k
+    assert d["unit"] == "circuit-timesteps/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None      # BASELINE.md publishes no number
+    assert "workload" in d["config"] and "model" not in d["config"] and "l2" in d["config"]
+    e = d["e2e"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(e) and e["value"] > 0
+    if reference:
+        assert d["impl"] == "reference" and d["gpu_launches"] == 0 and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+        c = d["cpu_baseline"]
+        assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] == d["value"] and c["sample"]
+        return
+    assert d["gpu_launches"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    assert d["value"] > 1e9 and d["steps"] >= 1 and d["warmup"] >= 3
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1.2
+    cl = d["clocks"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(cl)
+    assert not set(cl["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if d["n_gpus"] == 1:
+        c = d["cpu_baseline"]
+        assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+
+
+@pytest.mark.parametrize("name", ["bench_r01_final_1m.json", "bench_r01_final_2gpu.json", "bench_r01_final_8gpu.json"])
+def test_recorded_bench_lines_follow_the_contract(name):
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
+    check_line(d)
+
+
+def test_recorded_reference_arm_line():
+    check_line(json.load(open(os.path.join(ROOT, "profiles", "bench_r01_final_reference_arm.json"))), reference=True)
+
+
+@pytest.mark.gpu
+def test_live_bench_line(built):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--instances", "65536", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    d["cpu_baseline"] = d["cpu_baseline"] or {"value": 1.0, "unit": "", "cores": 1, "kind": "port", "sample": "skipped"}
+    check_line(d)
