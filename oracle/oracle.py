@@ -49,6 +49,9 @@ def lib():
         L.orc_go_sin.restype = C.c_double
         L.orc_go_sin.argtypes = [C.c_double]
         L.orc_format_value_factor.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        for fn in ("orc_go_max", "orc_go_min", "orc_go_pow"):
+            getattr(L, fn).restype = C.c_double
+            getattr(L, fn).argtypes = [C.c_double, C.c_double]
         L.orc_lu_batch.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L

@@ -242,6 +242,9 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
 
 // Exposed helpers for unit tests.
 double orc_go_sin(double x) { return go_sin(x); }
+double orc_go_max(double x, double y) { return go_max(x, y); }
+double orc_go_min(double x, double y) { return go_min(x, y); }
+double orc_go_pow(double x, double y) { return go_pow(x, y); }
 int orc_format_value_factor(double v, char* buf, int cap) {
     std::string s = format_value_factor(v);
     snprintf(buf, cap, "%s", s.c_str());

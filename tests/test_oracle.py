@@ -207,3 +207,31 @@ def test_diode_operating_point_satisfies_kirchhoff():
     assert np.all(res["status"] == 0)
     assert np.all(np.abs(i_r - i_d) <= 2e-5 * np.abs(i_r)), float(np.max(np.abs(i_r - i_d) / np.abs(i_r)))
     assert np.all((v2 > 0.3) & (v2 < 1.6)) and np.allclose(v1, 5.0)
+
+
+def test_go_runtime_semantics_restated_in_the_oracle():
+    """math.Max / math.Min / math.Pow as the Go specification documents them (src/math/dim.go, pow.go special cases) —
+    where C's fmax / fmin / pow differ, the oracle follows Go."""
+    import math
+    import parity_util as PU
+    L = PU.O.lib()
+    nan, inf = float("nan"), float("inf")
+    # Max / Min: NaN propagates unless an infinity of the winning sign is present; signed zeros are ordered
+    assert math.isnan(L.orc_go_max(nan, 1.0)) and math.isnan(L.orc_go_max(1.0, nan)) and math.isnan(L.orc_go_min(nan, 1.0))
+    assert L.orc_go_max(inf, nan) == inf and L.orc_go_max(nan, inf) == inf and L.orc_go_min(nan, -inf) == -inf
+    assert math.copysign(1.0, L.orc_go_max(0.0, -0.0)) == 1.0 and math.copysign(1.0, L.orc_go_max(-0.0, -0.0)) == -1.0
+    assert math.copysign(1.0, L.orc_go_min(0.0, -0.0)) == -1.0 and math.copysign(1.0, L.orc_go_min(0.0, 0.0)) == 1.0
+    assert L.orc_go_max(2.0, 3.0) == 3.0 and L.orc_go_min(2.0, 3.0) == 2.0 and L.orc_go_max(-inf, 1.0) == 1.0
+    # Pow: documented special cases
+    assert L.orc_go_pow(3.7, 0.0) == 1.0 and L.orc_go_pow(1.0, nan) == 1.0 and L.orc_go_pow(nan, 0.0) == 1.0 and L.orc_go_pow(5.5, 1.0) == 5.5
+    assert math.isnan(L.orc_go_pow(nan, 2.0)) and math.isnan(L.orc_go_pow(-8.0, 1.0 / 3.0))
+    assert L.orc_go_pow(0.0, -2.0) == inf and L.orc_go_pow(-0.0, -3.0) == -inf and L.orc_go_pow(-0.0, 3.0) == 0.0 and L.orc_go_pow(0.0, 2.5) == 0.0
+    assert L.orc_go_pow(2.0, inf) == inf and L.orc_go_pow(0.5, inf) == 0.0 and L.orc_go_pow(-1.0, inf) == 1.0 and L.orc_go_pow(2.0, -inf) == 0.0
+    assert L.orc_go_pow(inf, -2.0) == 0.0 and L.orc_go_pow(-inf, 3.0) == -inf and L.orc_go_pow(-inf, 2.0) == inf
+    assert L.orc_go_pow(2.25, 0.5) == 1.5 and L.orc_go_pow(4.0, -0.5) == 0.5
+    # integer exponents: the repeated-squaring sequence — exactly 1 / (x*x) for y = -2 (bjt.go:275), x*x*x for 3
+    rng = np.random.default_rng(9)
+    for x in rng.uniform(0.1, 50.0, 200):
+        assert L.orc_go_pow(float(x), -2.0) == 1.0 / (float(x) * float(x))
+        assert L.orc_go_pow(float(x), 3.0) == float(x) * (float(x) * float(x)) or L.orc_go_pow(float(x), 3.0) == (float(x) * float(x)) * float(x)
+        assert abs(L.orc_go_pow(float(x), 1.7) - float(x) ** 1.7) <= 4e-16 * float(x) ** 1.7
