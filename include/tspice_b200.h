@@ -185,6 +185,12 @@ int tsb_batch_set_param_dev(tsb_batch* batch, int dev, int param, uint64_t dev_p
 /* One value for all instances (replaces the netlist value). */
 int tsb_batch_set_param_uniform(tsb_batch* batch, int dev, int param, double value);
 
+/* Optional processing order: slot s of the launch works on instance perm[s] (a permutation of 0..n_inst-1, host
+ * memory, copied).  Lanes of a warp advance together, so grouping instances that need similar Newton iteration counts
+ * (e.g. sorted by the parameter that drives them) removes waiting; parameters and results keep the caller's order and
+ * do not change by a bit.  NULL removes the order. */
+int tsb_batch_set_order(tsb_batch* batch, const int64_t* perm);
+
 /* Analyses — the batch equivalents of analysis.NewOP / NewTransient / NewDCSweep + Setup + Execute. */
 int tsb_run_op(tsb_batch* batch, const tsb_opts* opts);
 int tsb_run_tran(tsb_batch* batch, double tstart, double tstop, double tstep, double tmax, int uic,

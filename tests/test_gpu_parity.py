@@ -448,3 +448,37 @@ def test_diode_solutions_satisfy_kirchhoff_independently_of_the_oracle(ctx):
     i_r = v2 / ov[("r1", 0)]
     assert np.all(b.status() == 0)
     assert np.all(np.abs(i_r - i_d) <= 2e-5 * np.abs(i_d) + 1e-11)
+
+
+@pytest.mark.parametrize("name", ["diode2", "rlc", "diode3", "bjt2"])
+def test_processing_order_changes_no_bit(ctx, name):
+    """tsb_batch_set_order: the lanes of a warp can be given instances that behave alike; parameters and results stay in
+    the caller's order and every result is bit-identical to the unordered run (transient, DC sweep, lane refill)."""
+    n = 5000
+    text = T.BUNDLED[name]
+    ckt = T.Circuit.from_netlist(text, ctx)
+    ov = PU.draws(name, ckt, n)
+    card = ckt.analysis_card()
+    res = []
+    rng = np.random.default_rng(3)
+    for perm, refill in ((None, 0), (rng.permutation(n), 0), (np.argsort(next(iter(ov.values()))), 1)):
+        b = ckt.batch(n)
+        for (d, p), v in ov.items():
+            b.set_param(d, p, v)
+        b.set_order(perm)
+        o = T.default_opts(lane_refill=refill)
+        if card["analysis"] == T.AN_TRAN:
+            b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=o)
+        else:
+            b.run_dc(card["dc_src_dev"], card["dc_start"], card["dc_stop"], card["dc_inc"], out=T.OUT_STATS, opts=o)
+        b.sync()
+        res.append((b.stats_all(), b.rows(), b.status(), b.counters()))
+        if perm is not None:
+            b.set_order(None)
+        del b
+    for other in res[1:]:
+        for x, y in zip(res[0], other):
+            assert np.array_equal(x, y, equal_nan=True), name
+    b = ckt.batch(4)
+    with pytest.raises(T.TsbError):
+        b.set_order([0, 1, 1, 3])

@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "tsb_batch_sync", "tsb_result_dims", "tsb_result_dev_ptrs", "tsb_result_rows", "tsb_result_status",
     "tsb_result_counters", "tsb_result_waveform", "tsb_result_wave_all", "tsb_result_stats_all",
     "tsb_result_totals", "tsb_batch_kernel_source", "tsb_batch_kernel_key", "tsb_ctx_launch_count",
-    "tsb_lu_order", "tsb_lu_solve_batched", "tsb_lu_solve_batched_dev", "tsb_batch_stamp_dev",
+    "tsb_lu_order", "tsb_lu_solve_batched", "tsb_lu_solve_batched_dev", "tsb_batch_stamp_dev", "tsb_batch_set_order",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
             "tsb_batch_kernel_source": (i32, [vp, P(Opts), C.c_char_p, i64, P(i64)]),
             "tsb_batch_kernel_key": (i32, [vp, P(Opts), C.c_char_p, i32]),
             "tsb_batch_stamp_dev": (i32, [vp, i32, dbl, dbl, dbl, u64, u64, P(Opts)]),
+            "tsb_batch_set_order": (i32, [vp, P(i64)]),
             "tsb_lu_order": (i32, [i32, P(dbl), P(i32), P(i32)]),
             "tsb_lu_solve_batched": (i32, [vp, i32, P(i32), P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int32), i64, i32]),
             "tsb_lu_solve_batched_dev": (i32, [vp, i32, P(i32), P(i32), u64, u64, u64, u64, i64, i32]),
@@ -415,6 +416,14 @@ class Batch:
     def run_dc(self, src, start, stop, inc, out=OUT_WAVE, opts: Opts | None = None):
         self._check(lib().tsb_run_dc(self.h, self._dev(src), start, stop, inc, out,
                                      C.byref(opts) if opts is not None else None), "tsb_run_dc")
+
+    def set_order(self, perm):
+        """Processing order (tsb_batch_set_order): slot s works on instance perm[s]; None removes it."""
+        if perm is None:
+            self._check(lib().tsb_batch_set_order(self.h, None), "tsb_batch_set_order")
+            return
+        p = np.ascontiguousarray(perm, dtype=np.int64)
+        self._check(lib().tsb_batch_set_order(self.h, p.ctypes.data_as(C.POINTER(C.c_int64))), "tsb_batch_set_order")
 
     def stamp_dev(self, mode: int, time: float, dt: float, gmin: float, A_ptr: int, b_ptr: int, opts: Opts | None = None):
         """Operator level: the dense stamped system of every instance into device memory (tsb_batch_stamp_dev)."""

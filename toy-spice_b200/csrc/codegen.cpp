@@ -231,6 +231,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("#define TSB_SKIP_LINEAR_RESOLVE " + std::to_string(cfg.skip_linear ? 1 : 0));
     e.line("#define TSB_LANE_REFILL " + std::to_string(cfg.lane_refill && pl.has_nonlinear ? 1 : 0));
     e.line("#define TSB_GRID " + std::to_string(cfg.grid ? 1 : 0));
+    e.line("#define TSB_ORDER " + std::to_string(cfg.order ? 1 : 0));
     if (!cfg.extra_defines.empty()) e.os << cfg.extra_defines << "\n";     // development knob ($TSB_EXTRA_DEFINES)
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
@@ -516,12 +517,12 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK, TSB_MIN_BLOCKS) tsb_optran(TsbArgs a) {");
     e.line("    if (Ckt::HAS_NL && TSB_LANE_REFILL) {   // persistent lanes: finished lanes refill themselves from a.work_counter");
     e.line("        long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;");
-    e.line("        tsb_run_optran_instance<Ckt>(a, inst, inst < a.n_run);");
+    e.line("        tsb_run_optran_instance<Ckt>(a, tsb_slot_instance(a, inst, inst < a.n_run), inst < a.n_run);");
     e.line("        return;");
     e.line("    }");
     e.line("    // block-uniform trip count: every lane of a warp enters the driver (its Newton loops are warp-synchronous)");
     e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
-    e.line("        tsb_run_optran_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
+    e.line("        tsb_run_optran_instance<Ckt>(a, tsb_slot_instance(a, base + threadIdx.x, base + threadIdx.x < a.n_run), base + threadIdx.x < a.n_run);");
     e.line("}");
     e.line("// Operator level: stamp every instance (fresh device state, sources at a.tstart) -> a.wave = A, a.stats = b.");
     e.line("// tsb_stamp: every thread stores its own system straight to HBM (instances are (N*N+N)*8 bytes apart: 32 scattered");
@@ -559,7 +560,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_stamp_staged(TsbArgs a) { tsb_stamp_body<true>(a); }");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
     e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
-    e.line("        tsb_run_dc_instance<Ckt>(a, base + threadIdx.x, base + threadIdx.x < a.n_run);");
+    e.line("        tsb_run_dc_instance<Ckt>(a, tsb_slot_instance(a, base + threadIdx.x, base + threadIdx.x < a.n_run), base + threadIdx.x < a.n_run);");
     e.line("}");
     return e.os.str();
 }

@@ -52,7 +52,14 @@ struct TsbArgs {
     int n_grid;
     long long n_run;           // instances [0, n_run) are processed (n_inst stays the array stride); < n_inst only
                                // while the library times launch-bounds candidates on a sub-batch
+    const long long* order;    // optional processing order (tsb_batch_set_order): slot s works on instance order[s]
 };
+
+// Slot -> instance.  With an order, lanes of a warp can be given instances that behave alike (similar Newton
+// iteration counts) whatever their position in the caller's arrays; parameters and results stay where the caller put them.
+__device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long long slot, bool valid) {
+    return (TSB_ORDER && valid && a.order) ? a.order[slot] : slot;      // TSB_ORDER: kernels specialised for ordered batches
+}
 
 #define TSB_ST_OK 0
 #define TSB_ST_OP_FAILED 1
@@ -460,8 +467,8 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             if (!LINEAR_LOOP && !NL_LOOP) finish_instance();       // (else: transient + finish follow the loop, below)
             done = true;
             if (REFILL) {
-                inst = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
-                if (inst < a.n_run) { done = false; begin_instance(); }
+                const long long slot = a.first_free + (long long)atomicAdd(a.work_counter, 1ULL);
+                if (slot < a.n_run) { inst = tsb_slot_instance(a, slot, true); done = false; begin_instance(); }
             }
         } else if (!done && !pend) {
         if (phase == PH_OP_START) {

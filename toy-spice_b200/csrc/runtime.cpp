@@ -58,6 +58,7 @@ struct TsbArgsHost {
     double grid_dt;
     int n_grid;
     long long n_run;
+    const long long* order;
 };
 
 struct KernelModule {
@@ -115,6 +116,7 @@ struct tsb_batch {
     // time, which is the length of a short launch (the stamp kernel); identical requests skip it
     std::string memo_sig, memo_autokey;
     KernelModule* memo_module = nullptr;
+    long long* d_order = nullptr;                      // tsb_batch_set_order: processing order (device copy)
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -240,6 +242,7 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
     cfg.grid = b->grid_kernel;
+    cfg.order = b->d_order != nullptr;
     if (const char* x = getenv("TSB_EXTRA_DEFINES")) {          // development knob for A/B kernel experiments
         std::string item;
         for (const char* c = x;; ++c) {
@@ -304,8 +307,8 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     sig.append(b->varying.begin(), b->varying.end());
     const char* xd = getenv("TSB_EXTRA_DEFINES");
     char tail[160];
-    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
-             (int)b->grid_kernel, dc_param, ctx->choice_epoch, (void*)ctx);
+    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
+             (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, ctx->choice_epoch, (void*)ctx);
     sig += tail;
     if (xd) sig += xd;
     if (b->memo_module && sig == b->memo_sig) {
@@ -500,6 +503,7 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     memset(&a, 0, sizeof a);
     a.n_inst = b->n_inst;
     a.n_run = b->n_inst;
+    a.order = b->d_order;
     if (b->slot_ptr.size() > TSB_MAX_VARYING) return fail(ctx, TSB_E_UNSUPPORTED, "too many per-instance parameters (max 64)");
     for (size_t s = 0; s < b->slot_ptr.size(); ++s) a.pv[s] = b->slot_ptr[s];
     size_t ub = b->uniform.size() * sizeof(double);
@@ -797,6 +801,7 @@ void tsb_batch_destroy(tsb_batch* b) {
         cudaSetDevice(b->ctx->device);
         for (size_t s = 0; s < b->slot_ptr.size(); ++s) if (b->slot_owned[s]) cudaFree(b->slot_ptr[s]);
         cudaFree(b->d_uniform);
+        cudaFree(b->d_order);
         free_results(b);
     }
     plan_release(b->plan);
@@ -988,6 +993,28 @@ int tsb_batch_stamp_dev(tsb_batch* b, int mode, double time, double dt, double g
     void* kargs[] = {&a};
     CU(ctx, cudaLaunchKernel((const void*)kern, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
     ++ctx->launches;
+    return TSB_OK;
+}
+
+// Processing order.  Instances are independent, so WHICH lane works on which instance is free; what is not free is
+// that the lanes of a warp advance together (warp-synchronous Newton loops): a warp is as slow as its slowest lane.
+// A caller who knows which parameter drives the iteration count can hand over a permutation that puts like with like
+// (e.g. np.argsort of the diode emission coefficient: diode2.cir -20 %).  Parameters and results stay in the
+// caller's order; results are bit-identical with and without an order.  perm == NULL removes it.
+int tsb_batch_set_order(tsb_batch* b, const int64_t* perm) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!perm) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(b->d_order); b->d_order = nullptr; return TSB_OK; }
+    std::vector<char> seen((size_t)b->n_inst, 0);
+    for (int64_t i = 0; i < b->n_inst; ++i) {
+        if (perm[i] < 0 || perm[i] >= b->n_inst || seen[(size_t)perm[i]]) return fail(ctx, TSB_E_INVALID, "tsb_batch_set_order: not a permutation of 0..n_inst-1");
+        seen[(size_t)perm[i]] = 1;
+    }
+    if (!b->d_order) CU(ctx, cudaMalloc(&b->d_order, (size_t)b->n_inst * sizeof(long long)));
+    static_assert(sizeof(long long) == sizeof(int64_t), "order entries are 64-bit");
+    CU(ctx, cudaMemcpyAsync(b->d_order, perm, (size_t)b->n_inst * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return TSB_OK;
 }
 
