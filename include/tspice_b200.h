@@ -72,7 +72,8 @@ enum {
 enum { TSB_SRC_DC = 0, TSB_SRC_SIN = 1, TSB_SRC_PULSE = 2, TSB_SRC_PWL = 3 };
 
 /* Analysis kinds (pkg/analysis/anlysis.go:11-16). */
-enum { TSB_AN_OP = 0, TSB_AN_TRAN = 1, TSB_AN_AC = 2, TSB_AN_DC = 3 };
+enum { TSB_AN_OP = 0, TSB_AN_TRAN = 1, TSB_AN_AC = 2, TSB_AN_DC = 3,
+       TSB_AN_DC2 = 4   /* column layout of a nested DC sweep (SWEEP1, SWEEP2, signals; dc.go:272-288) for tsb_plan_num_columns / _column_name */ };
 
 /* Per-instance status (tsb_result_status). */
 enum {
@@ -100,8 +101,11 @@ typedef struct tsb_opts {
                            always passes the convergence test; counters still report it (reference-equivalent) */
     int min_blocks;     /* __launch_bounds__ min resident blocks per SM for the specialised kernels.  0 (default): chosen
                            by a spill rule and, on the first transient run of a batch of >= 32768 instances, by timing the
-                           candidates on a sub-batch (that first call then blocks for a fraction of a second;
-                           $TSB_AUTOTUNE=0 disables; results never depend on the choice) */
+                           candidates on a sub-batch.  THAT FIRST CALL IS NOT ASYNCHRONOUS: it blocks the host for a
+                           fraction of a second (event synchronisation, possibly NVRTC), so it must not happen under CUDA
+                           graph capture — it is skipped when the stream is capturing, and $TSB_AUTOTUNE=0 or an explicit
+                           min_blocks > 0 disables it; the choice is remembered per process and, in the kernel cache, per
+                           GPU model.  Results never depend on the choice. */
     int lane_refill;    /* 1: circuits with nonlinear devices run on a resident grid whose lanes, once their instance has
                            finished, take the next unprocessed instance from a work counter (finished lanes never idle
                            beside slow neighbours) — for sweeps whose instances need very different numbers of steps;
@@ -133,7 +137,15 @@ void tsb_ctx_destroy(tsb_ctx* ctx);
 const char* tsb_last_error(tsb_ctx* ctx);
 /* Launch on an existing CUDA stream (cudaStream_t / CUstream as an integer); 0 = the context's own. */
 int tsb_ctx_set_stream(tsb_ctx* ctx, uint64_t stream);
-/* Directory of the specialised-kernel cache (cubin files).  Default: $TSB_KCACHE or <lib dir>/../_kcache. */
+/* The stream the context launches on (cudaStream_t as an integer). */
+int tsb_ctx_get_stream(tsb_ctx* ctx, uint64_t* stream);
+/* Stream ordering contract for BORROWED device buffers (tsb_batch_set_param_dev, tsb_batch_stamp_dev,
+ * tsb_lu_solve_batched_dev): the library reads / writes them on the context's stream and knows nothing about the stream
+ * that produced them.  Either launch on that stream (tsb_ctx_set_stream), or record a cudaEvent_t on it after the producer
+ * and hand it to tsb_ctx_wait_event: everything the context launches afterwards waits for the event on the device.  The
+ * caller keeps borrowed buffers alive until the work that uses them has finished (tsb_batch_sync). */
+int tsb_ctx_wait_event(tsb_ctx* ctx, uint64_t event);
+/* Directory of the specialised-kernel cache (cubin files).  Default: $TSB_KCACHE or <lib dir>/_kcache. */
 int tsb_ctx_set_cache_dir(tsb_ctx* ctx, const char* dir);
 /* FP64 DFMA-chain microbenchmark on this GPU: TFLOP/s (the FP64 roof used by bench.py). */
 int tsb_ctx_measure_fp64_peak(tsb_ctx* ctx, double* tflops);
@@ -177,8 +189,12 @@ int tsb_plan_column_name(const tsb_plan* plan, int analysis, int col, char* buf,
 /* ---- batch: N instances of a plan -----------------------------------------------------------*/
 int tsb_batch_create(tsb_plan* plan, int64_t n_inst, tsb_batch** out);
 void tsb_batch_destroy(tsb_batch* batch);
-/* Per-instance parameter values for (dev, param): n_inst doubles, host memory (copied H2D). */
+/* Per-instance parameter values for (dev, param): n_inst doubles, host memory of any kind.  COPY semantics: the values
+ * are staged through a library-owned pinned buffer, the caller's buffer is free again when the call returns. */
 int tsb_batch_set_param(tsb_batch* batch, int dev, int param, const double* values);
+/* Zero-copy variant for pinned host buffers: the H2D DMA reads `values` later, on the context's stream.  The buffer must
+ * stay valid and unmodified until the next tsb_batch_sync() (or any blocking tsb_result_* read). */
+int tsb_batch_set_param_async(tsb_batch* batch, int dev, int param, const double* values);
 /* Same, values already resident in HBM (device pointer, n_inst doubles; borrowed until the batch
  * is destroyed or the parameter is set again). */
 int tsb_batch_set_param_dev(tsb_batch* batch, int dev, int param, uint64_t dev_ptr);
@@ -197,6 +213,13 @@ int tsb_run_tran(tsb_batch* batch, double tstart, double tstop, double tstep, do
                  int out_flags, int64_t wave_cap_rows, const tsb_opts* opts);
 int tsb_run_dc(tsb_batch* batch, int src_dev, double start, double stop, double inc, int out_flags,
                const tsb_opts* opts);
+/* Nested sweep of two voltage sources (DCSweep.nestedSweep, dc.go:205-270): for every value of source 1 (outer loop)
+ * source 2 runs through its whole range (inner loop); device state carries over from point to point exactly as in the
+ * reference.  Rows are [SWEEP1, SWEEP2, signals...] (StoreNestedResult, dc.go:272-288; column names: analysis code
+ * TSB_AN_DC2), n1 * n2 of them per instance.  A failing instance stops at its first non-converging point:
+ * status = TSB_ST_DC_FAILED, rows[inst] = index of that point, counters[5] = the outer source's value there. */
+int tsb_run_dc2(tsb_batch* batch, int src1_dev, double start1, double stop1, double inc1, int src2_dev, double start2,
+                double stop2, double inc2, int out_flags, const tsb_opts* opts);
 /* Block until the last run has finished (runs are asynchronous on the context's stream). */
 int tsb_batch_sync(tsb_batch* batch);
 
@@ -251,6 +274,10 @@ int tsb_lu_solve_batched_dev(tsb_ctx* ctx, int n, const int* pivot_row, const in
 /* ---- introspection / build-time support -------------------------------------------------------*/
 /* CUDA source of the kernels specialised for this batch configuration (which parameters vary). */
 int tsb_batch_kernel_source(tsb_batch* batch, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed);
+/* Which specialisation the two calls below describe: dc_src_dev >= 0 selects the DC-sweep kernel for that source
+ * (dc_src2_dev >= 0: the nested sweep), grid != 0 the TSB_OUT_GRID kernels; (-1, -1, 0) = the default OP / transient
+ * kernels.  A batch used this way is for introspection only (build step), do not run analyses on it. */
+int tsb_batch_kernel_variant(tsb_batch* batch, int dc_src_dev, int dc_src2_dev, int grid);
 /* Cache key (hex) of that source + compile options; the cubin is looked up as <cache_dir>/<key>.cubin. */
 int tsb_batch_kernel_key(tsb_batch* batch, const tsb_opts* opts, char* buf, int cap);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */

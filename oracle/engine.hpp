@@ -1048,6 +1048,36 @@ struct DCSweep {
         source->SetValue(origVal);
         return RUN_OK;
     }
+    // nestedSweep (dc.go:205-270) + StoreNestedResult (dc.go:272-288): rows are [SWEEP1, SWEEP2, signals...]
+    VSource* source2 = nullptr;
+    std::vector<double> sweepVals2;
+    double fail_val2 = 0;
+    void SetSecond(VSource* s2, double start, double stop, double inc) {
+        source2 = s2;
+        for (double v = start; v <= stop; v += inc) sweepVals2.push_back(v);
+    }
+    int ExecuteNested(ResultStore& rs) {
+        origVal = source->GetValue();
+        const double origVal2 = source2->GetValue();
+        for (double val1 : sweepVals) {
+            source->SetValue(val1);
+            for (double val2 : sweepVals2) {
+                source2->SetValue(val2);
+                Status st; st.Mode = OP_MODE; st.Temp = 300.15; st.Gmin = conv.gmin;
+                ckt->Matrix->Clear();
+                ckt->Stamp(st);
+                if (!doNRiter(0, conv.maxIter)) { fail_val = val1; fail_val2 = val2; return RUN_DC_FAILED; }
+                std::vector<double> row(rs.nsig);
+                row[0] = val1;
+                row[1] = val2;
+                ckt->GetSolution(row.data() + 2);
+                rs.push(row.data());
+            }
+        }
+        source->SetValue(origVal);
+        source2->SetValue(origVal2);
+        return RUN_OK;
+    }
 };
 
 }  // namespace orc

@@ -21,7 +21,8 @@ _LIB = None
 class OrcJob(C.Structure):
     _fields_ = [("analysis", C.c_int), ("tstart", C.c_double), ("tstop", C.c_double), ("tstep", C.c_double),
                 ("tmax", C.c_double), ("uic", C.c_int), ("dc_src_dev", C.c_int), ("dc_start", C.c_double),
-                ("dc_stop", C.c_double), ("dc_inc", C.c_double)]
+                ("dc_stop", C.c_double), ("dc_inc", C.c_double), ("dc2_src_dev", C.c_int), ("dc2_start", C.c_double),
+                ("dc2_stop", C.c_double), ("dc2_inc", C.c_double)]
 
 
 def build(force: bool = False) -> str:
@@ -101,13 +102,14 @@ class OracleCircuit:
         return dict(rc=rc, ext2int=list(e2i)[1:], pivot_row=list(pr)[1:], pivot_col=list(pc)[1:])
 
     def run(self, n_inst=1, overrides=None, analysis=None, tran=None, dc=None, threads=1, cap_rows=None,
-            want_wave=True, want_stats=False):
+            want_wave=True, want_stats=False, dc2=None):
         """overrides: {(device_name_or_index, param_index): array[n_inst]}.
         Returns dict(wave [n_inst, cap, ncol], n_rows, status, counters, stats, signals)."""
         nl = self.netlist
         an = nl.analysis if analysis is None else analysis
         job = OrcJob()
         job.analysis = an
+        job.dc2_src_dev = -1
         if an == nlmod.AN_TRAN:
             t = dict(nl.tran)
             if tran:
@@ -119,16 +121,22 @@ class OracleCircuit:
                 d.update(dc)
             job.dc_src_dev = self.dev_index(d["source"])
             job.dc_start, job.dc_stop, job.dc_inc = d["start"], d["stop"], d["inc"]
+            if dc2:         # nested sweep (dc.go:205-270): dict(source, start, stop, inc) of the INNER source
+                job.dc2_src_dev = self.dev_index(dc2["source"])
+                job.dc2_start, job.dc2_stop, job.dc2_inc = dc2["start"], dc2["stop"], dc2["inc"]
         overrides = overrides or {}
         keys = list(overrides.keys())
         ov_dev = [self.dev_index(k[0]) if isinstance(k[0], str) else int(k[0]) for k in keys]
         ov_par = [int(k[1]) for k in keys]
         vals = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(overrides[k], dtype=np.float64), (n_inst,))
                                               for k in keys]) if keys else np.zeros((0, n_inst)))
-        ncol = lib().orc_n_columns(self.h, an)
+        nested = an == nlmod.AN_DC and job.dc2_src_dev >= 0
+        ncol = lib().orc_n_columns(self.h, 4 if nested else an)
         if cap_rows is None:
             cap_rows = 1 if an == nlmod.AN_OP else (int(round((job.dc_stop - job.dc_start) / job.dc_inc)) + 3
                                                      if an == nlmod.AN_DC else 65536)
+            if nested:
+                cap_rows *= int(round((job.dc2_stop - job.dc2_start) / job.dc2_inc)) + 3
         wave = np.full((n_inst, cap_rows, ncol), np.nan) if want_wave else None
         stats = np.zeros((n_inst, 4, ncol)) if want_stats else None
         n_rows = np.zeros(n_inst, dtype=np.int64)
@@ -144,7 +152,7 @@ class OracleCircuit:
         if rc != 0:
             raise RuntimeError(f"orc_run failed rc={rc}")
         return dict(wave=wave, n_rows=n_rows, status=status, counters=counters, stats=stats,
-                    signals=self.signals(an), ncol=ncol)
+                    signals=(["SWEEP1", "SWEEP2"] + self.signals(an)[1:]) if nested else self.signals(an), ncol=ncol)
 
 
 def go_sin(x: float) -> float:

@@ -121,6 +121,8 @@ struct orc_job {
     int uic;
     int dc_src_dev;
     double dc_start, dc_stop, dc_inc;
+    int dc2_src_dev;         // >= 0: nested sweep (dc.go:205-270), this is the inner source
+    double dc2_start, dc2_stop, dc2_inc;
 };
 
 void* orc_circuit_new(int n_nodes, int n_branches) {
@@ -143,7 +145,7 @@ int orc_n_columns(void* h, int analysis) {
     Template* t = static_cast<Template*>(h);
     if (analysis == 0) return t->n_nodes + t->n_branches;
     int nr = 0; for (auto& d : t->devs) if (d.kind == K_R) ++nr;
-    return 1 + t->n_nodes + t->n_branches + nr;
+    return (analysis == 4 ? 2 : 1) + t->n_nodes + t->n_branches + nr;        // 4: nested DC sweep (SWEEP1, SWEEP2)
 }
 
 // Structure introspection of one nominal build (SURVEY Appendix A checks).
@@ -170,7 +172,8 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
             const double* ov_vals, int n_threads, int64_t cap_rows, double* wave, int64_t* n_rows,
             int32_t* status, int64_t* counters, double* stats) {
     Template* t = static_cast<Template*>(h);
-    const int ncol = orc_n_columns(h, job->analysis);
+    const bool nested = job->analysis == 3 && job->dc2_src_dev >= 0;
+    const int ncol = orc_n_columns(h, nested ? 4 : job->analysis);
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
     if ((int64_t)n_threads > n_inst) n_threads = (int)n_inst;
@@ -202,12 +205,16 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
             } else {
                 DCSweep dc(job->dc_start, job->dc_stop, job->dc_inc);
                 dc.ckt = c.get();
-                Device* sd = nullptr;
+                Device* sd = nullptr; Device* sd2 = nullptr;
                 // map template device index -> built device (K devices are moved last)
-                { int pos = 0; for (size_t k = 0; k < devs.size(); ++k) { if (devs[k].kind == K_K) continue; if ((int)k == job->dc_src_dev) sd = c->devices[pos].get(); ++pos; } }
+                { int pos = 0; for (size_t k = 0; k < devs.size(); ++k) { if (devs[k].kind == K_K) continue; if ((int)k == job->dc_src_dev) sd = c->devices[pos].get(); if (nested && (int)k == job->dc2_src_dev) sd2 = c->devices[pos].get(); ++pos; } }
                 if (!sd || sd->type != 'V') { bad = 2; break; }
+                if (nested && (!sd2 || sd2->type != 'V')) { bad = 2; break; }
                 dc.source = static_cast<VSource*>(sd);
-                st = dc.Execute(rs);
+                if (nested) {
+                    dc.SetSecond(static_cast<VSource*>(sd2), job->dc2_start, job->dc2_stop, job->dc2_inc);
+                    st = dc.ExecuteNested(rs);
+                } else st = dc.Execute(rs);
                 cnt.op_solves = c->Matrix->n_solves; fail_at = dc.fail_val;
             }
             if (status) status[i] = st;

@@ -33,8 +33,9 @@ def draws(name: str, ckt, n: int, seed: int | None = None):
     return W.sweep_draws(ckt.devices(), n, W.sweep_seed(name) if seed is None else seed)
 
 
-def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, analysis=None, tran=None, grid_dt=0.0):
-    """Through the reference-shaped API: Circuit -> analysis.Setup(batch) -> Execute."""
+def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, analysis=None, tran=None, grid_dt=0.0, dc=None, dc2=None):
+    """Through the reference-shaped API: Circuit -> analysis.Setup(batch) -> Execute.
+    dc = (source, start, stop, inc) overrides the deck's .dc card; dc2 = (outer, inner) tuples runs the nested sweep."""
     ckt = T.Circuit.from_netlist(text, ctx)
     batch = ckt.batch(n)
     for (dev, par), vals in overrides.items():
@@ -51,7 +52,13 @@ def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, anal
         an.cap_rows = cap_rows
         an.grid_dt = grid_dt
     else:
-        an = T.NewDCSweep([ckt.devices()[card["dc_src_dev"]]["name"]], [card["dc_start"]], [card["dc_stop"]], [card["dc_inc"]])
+        if dc2 is not None:
+            (s1, a1, b1, c1), (s2, a2, b2, c2) = dc2
+            an = T.NewDCSweep([s1, s2], [a1, a2], [b1, b2], [c1, c2])
+        elif dc is not None:
+            an = T.NewDCSweep([dc[0]], [dc[1]], [dc[2]], [dc[3]])
+        else:
+            an = T.NewDCSweep([ckt.devices()[card["dc_src_dev"]]["name"]], [card["dc_start"]], [card["dc_stop"]], [card["dc_inc"]])
         an.out = out
     if opts is not None:
         an.opts = opts
@@ -60,10 +67,17 @@ def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, anal
     return ckt, batch, an
 
 
-def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None, want_wave=True):
+def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None, want_wave=True, dc=None,
+               dc2=None):
     oc = O.OracleCircuit(text)
+    kw = {}
+    if dc2 is not None:
+        (s1, a1, b1, c1), (s2, a2, b2, c2) = dc2
+        kw = dict(dc=dict(source=s1, start=a1, stop=b1, inc=c1), dc2=dict(source=s2, start=a2, stop=b2, inc=c2))
+    elif dc is not None:
+        kw = dict(dc=dict(source=dc[0], start=dc[1], stop=dc[2], inc=dc[3]))
     res = oc.run(n, overrides=overrides, threads=threads, cap_rows=cap_rows, want_stats=want_stats, analysis=analysis, tran=tran,
-                 want_wave=want_wave)
+                 want_wave=want_wave, **kw)
     return oc, res
 
 
@@ -74,8 +88,8 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
     st_g = batch.status()
     cnt_g = batch.counters()
     ncol = ores["ncol"]
-    rep = dict(n=n, row_mismatch=0, status_mismatch=0, max_rel=0.0, max_abs=0.0, worst=None, nan_mismatch=0,
-               compared_points=0, counter_mismatch=0)
+    rep = dict(n=n, row_mismatch=0, status_mismatch=0, max_rel=0.0, max_abs=0.0, worst=None, nan_mismatch=0, inf_mismatch=0,
+               compared_points=0, counter_mismatch=0, counter_flips=[])
     wall = batch.wave_all() if n > 64 else None
     for i in range(n):
         nr_o = int(ores["n_rows"][i])
@@ -87,11 +101,17 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
             continue
         if not np.array_equal(cnt_g[:4, i], ores["counters"][i, :4]):
             rep["counter_mismatch"] += 1
+            rep["counter_flips"].append((i, cnt_g[:4, i].tolist(), ores["counters"][i, :4].tolist()))
         wg = wall[:nr_o, :, i] if wall is not None else batch.waveform(i)
         wo = ores["wave"][i, :nr_o, :ncol]
         nan_g, nan_o = np.isnan(wg), np.isnan(wo)
         if not np.array_equal(nan_g, nan_o):
             rep["nan_mismatch"] += 1
+            continue
+        # infinities are results too (BJT overflow lanes): same places, same signs
+        inf_g, inf_o = np.isinf(wg), np.isinf(wo)
+        if not np.array_equal(inf_g, inf_o) or not np.array_equal(np.sign(wg[inf_g]), np.sign(wo[inf_o])):
+            rep["inf_mismatch"] += 1
             continue
         ok = ~nan_o & np.isfinite(wo) & np.isfinite(wg)
         err = np.abs(wg[ok] - wo[ok])
@@ -108,7 +128,7 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
 
 
 def report_ok(rep) -> bool:
-    return (rep["row_mismatch"] == 0 and rep["status_mismatch"] == 0 and rep["nan_mismatch"] == 0
+    return (rep["row_mismatch"] == 0 and rep["status_mismatch"] == 0 and rep["nan_mismatch"] == 0 and rep["inf_mismatch"] == 0
             and rep["max_rel"] <= 1.0)
 
 

@@ -1,5 +1,5 @@
-"""Seeded generator of small random SPICE decks (R, C, L, D, V, I; DC / SIN / PULSE / PWL sources; mixed-case
-names, engineering suffixes) used to exercise the front-end, the symbolic pass, the code generator and the
+"""Seeded generators of small random SPICE decks: random_deck (R, C, L, D, V, I; DC / SIN / PULSE / PWL sources; mixed-case
+names, engineering suffixes) and random_active_deck (Q, M, K, core inductors) used to exercise the front-end, the symbolic pass, the code generator and the
 analysis kernels beyond the bundled decks.  Every node has a resistive path to ground."""
 import numpy as np
 
@@ -65,6 +65,73 @@ def random_deck(seed: int, allow_inductor=True, allow_diode=True):
         tstop, tstep = 4e-4, 4e-6                   # inductor decks take ~50 x 300 steps whatever the span
     lines.append(f".tran {tstep:g} {tstop:g}")
     return "\n".join(lines) + "\n", dict(nodes=m, has_inductor=has_l, source=str(src))
+
+
+def random_active_deck(seed: int):
+    """Random decks with the device kinds random_deck() never emits: BJT (NPN / PNP), MOSFET (NMOS / PMOS, Level 1-3),
+    coupled inductors (K over 2 or 3 windings) and magnetic-core inductors — on a resistive skeleton, one driven by a
+    source, every node with a resistive path to ground.  The reference's BJT / PMOS models often overflow or fail to
+    converge; those lanes are parity cases too (status, NaN / Inf classes, solve counts)."""
+    rng = np.random.default_rng(10_000 + seed)
+    flavour = ["bjt", "mos", "xfmr", "core"][seed % 4]
+    lines = [f"* random active deck {seed} ({flavour})"]
+    info = dict(flavour=flavour, has_inductor=flavour in ("xfmr",), nodes=0)
+    r = lambda lo, hi: _eng(float(np.exp(rng.uniform(np.log(lo), np.log(hi)))), rng)
+    if flavour == "bjt":
+        pnp = bool(rng.integers(0, 2))
+        vcc = float(rng.uniform(5, 12))
+        lines.append(f"VCC 1 0 DC {vcc:.3f}")
+        hi, lo = (f"{vcc:.3f}", f"{vcc - rng.uniform(0.55, 0.7):.3f}") if pnp else ("0", f"{rng.uniform(0.55, 0.7):.3f}")
+        lines.append(f"VB 4 0 PULSE({hi} {lo} 2u 1u 1u 40u 100u)" if rng.random() < 0.7 else f"VB 4 0 DC {lo}")
+        lines.append(f"RB 4 2 {r(5, 500)}")
+        if pnp:
+            lines += [f"RC 3 0 {r(200, 5e3)}", "Q1 3 2 1 QX"]
+        else:
+            lines += [f"RC 1 3 {r(200, 5e3)}", "Q1 3 2 0 QX"]
+        lines.append(f".model QX {'PNP' if pnp else 'NPN'}(Is={rng.uniform(0.5, 5):.3f}e-14 Bf={int(rng.integers(50, 300))} "
+                     f"Vaf={rng.uniform(40, 150):.1f} Ikf={rng.uniform(5, 50):.1f}m)")
+        if rng.random() < 0.5:
+            lines.append(f"RL 3 0 {r(1e3, 1e5)}")
+        lines.append(".tran 1u 100u")
+        info["nodes"] = 4
+    elif flavour == "mos":
+        level = int(rng.integers(1, 4))
+        pmos = bool(rng.integers(0, 2))
+        lines.append(f"VDD 1 0 DC {rng.uniform(3, 6):.3f}")
+        src = rng.choice(["pulse", "sin"])
+        lines.append("VG 2 0 PULSE(0 5 1u 200n 200n 4u 10u)" if src == "pulse" else f"VG 2 0 SIN(2.5 {rng.uniform(0.5, 2.4):.3f} 200k)")
+        lines.append(f"RD 1 3 {r(80, 200) if pmos else r(1e3, 2e4)}")
+        body = "0"
+        if rng.random() < 0.4 and not pmos:
+            lines += [f"VBB 5 0 DC -{rng.uniform(0.5, 3):.2f}", f"RS 4 0 {r(100, 2e3)}"]
+            lines.append("M1 3 2 4 5 MX L=2u W=20u")
+        else:
+            lines.append(f"M1 3 2 0 {body} MX L={rng.choice(['1u', '2u', '5u'])} W={rng.choice(['10u', '20u', '40u'])}")
+        extra = {1: "", 2: f" TOX=2e-8 UO={int(rng.integers(200, 700))} UCRIT=1e4 UEXP={rng.uniform(0.05, 0.2):.3f} VMAX={rng.uniform(3, 9):.1f}e4",
+                 3: f" THETA={rng.uniform(0.01, 0.1):.3f} KAPPA={rng.uniform(0.1, 0.6):.2f} DELTA={rng.uniform(0, 1):.2f}"}[level]
+        vto = -rng.uniform(0.5, 1.0) if pmos else rng.uniform(0.5, 1.0)
+        lines.append(f".model MX {'PMOS' if pmos else 'NMOS'}(Level={level} VTO={vto:.3f} KP={rng.uniform(10, 60):.1f}u GAMMA={rng.uniform(0.2, 0.7):.2f} "
+                     f"PHI={rng.uniform(0.55, 0.8):.2f} LAMBDA={rng.uniform(0, 0.05):.3f} CGSO=2e-10 CGDO=2e-10{extra})")
+        lines.append(".tran 0.1u 10u")
+        info["nodes"] = 5
+    elif flavour == "xfmr":
+        three = bool(rng.integers(0, 2))
+        lines.append(f"Vin 1 0 SIN(0 {rng.uniform(2, 12):.2f} {rng.choice([500, 1000, 2000])})")
+        lines += [f"Rp 1 2 {r(0.05, 2)}", f"Lp 2 0 {r(5e-2, 4e-1)}", f"Ls1 3 0 {r(1e-2, 1e-1)}", f"Rs1 3 4 {r(0.02, 1)}",
+                  f"Rl1 4 0 {r(50, 2e4)}"]
+        if three:
+            lines += [f"Ls2 5 0 {r(1e-2, 1e-1)}", f"Rs2 5 6 {r(0.02, 1)}", f"Rl2 6 0 {r(50, 2e4)}"]
+        lines.append(f"K1 Lp Ls1{' Ls2' if three else ''} {rng.uniform(0.8, 0.99):.3f}")
+        lines.append(".tran 0.02m 0.6m")
+        info["nodes"] = 6 if three else 4
+    else:
+        lines.append(f"Vin 1 0 SIN(0 {rng.uniform(2, 12):.2f} 1k)")
+        lines += [f"Rp 1 2 {r(0.05, 2)}", f"Lp 2 0 core=CX turns={int(rng.integers(50, 400))}", f"Rs 3 4 {r(0.05, 1)}",
+                  f"Ls 3 0 core=CX turns={int(rng.integers(50, 400))}", f"Rload 4 0 {r(100, 5e3)}",
+                  f".model CX core(ms=1.6e6 a=1000 c=0.1 k=2000 area={rng.uniform(0.5, 3):.2f}e-4 len={rng.uniform(0.05, 0.3):.3f})",
+                  f"K1 Lp Ls {rng.uniform(0.8, 0.99):.3f}", ".tran 10u 3m"]
+        info["nodes"] = 4
+    return "\n".join(lines) + "\n", info
 
 
 def rc_ladder(sections: int) -> str:

@@ -25,7 +25,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-AN_OP, AN_TRAN, AN_AC, AN_DC = 0, 1, 2, 3
+AN_OP, AN_TRAN, AN_AC, AN_DC, AN_DC2 = 0, 1, 2, 3, 4
 OUT_WAVE, OUT_STATS, OUT_GRID = 1, 2, 4
 K_R, K_C, K_L, K_V, K_I, K_D, K_Q, K_M, K_K, K_LCORE = range(10)
 ST_OK, ST_OP_FAILED, ST_TRAN_FAILED, ST_DC_FAILED, ST_OVERFLOW = range(5)
@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "tsb_result_counters", "tsb_result_waveform", "tsb_result_wave_all", "tsb_result_stats_all",
     "tsb_result_totals", "tsb_batch_kernel_source", "tsb_batch_kernel_key", "tsb_ctx_launch_count",
     "tsb_lu_order", "tsb_lu_solve_batched", "tsb_lu_solve_batched_dev", "tsb_batch_stamp_dev", "tsb_batch_set_order",
+    "tsb_run_dc2", "tsb_batch_kernel_variant", "tsb_batch_set_param_async", "tsb_ctx_get_stream", "tsb_ctx_wait_event",
 ]
 
 
@@ -77,6 +78,8 @@ def lib():
             "tsb_last_error": (C.c_char_p, [vp]),
             "tsb_ctx_set_stream": (i32, [vp, u64]),
             "tsb_ctx_set_cache_dir": (i32, [vp, C.c_char_p]),
+            "tsb_ctx_get_stream": (i32, [vp, P(u64)]),
+            "tsb_ctx_wait_event": (i32, [vp, u64]),
             "tsb_ctx_measure_fp64_peak": (i32, [vp, P(dbl)]),
             "tsb_ctx_sm_count": (i32, [vp, P(i32)]),
             "tsb_ctx_launch_count": (i64, [vp]),
@@ -101,10 +104,12 @@ def lib():
             "tsb_batch_destroy": (None, [vp]),
             "tsb_batch_set_param": (i32, [vp, i32, i32, P(dbl)]),
             "tsb_batch_set_param_dev": (i32, [vp, i32, i32, u64]),
+            "tsb_batch_set_param_async": (i32, [vp, i32, i32, P(dbl)]),
             "tsb_batch_set_param_uniform": (i32, [vp, i32, i32, dbl]),
             "tsb_run_op": (i32, [vp, P(Opts)]),
             "tsb_run_tran": (i32, [vp, dbl, dbl, dbl, dbl, i32, i32, i64, P(Opts)]),
             "tsb_run_dc": (i32, [vp, i32, dbl, dbl, dbl, i32, P(Opts)]),
+            "tsb_run_dc2": (i32, [vp, i32, dbl, dbl, dbl, i32, dbl, dbl, dbl, i32, P(Opts)]),
             "tsb_batch_sync": (i32, [vp]),
             "tsb_result_dims": (i32, [vp, P(i64), P(i32), P(i64)]),
             "tsb_result_dev_ptrs": (i32, [vp, P(u64), P(u64), P(u64), P(u64), P(u64)]),
@@ -117,6 +122,7 @@ def lib():
             "tsb_result_totals": (i32, [vp, P(i64)]),
             "tsb_batch_kernel_source": (i32, [vp, P(Opts), C.c_char_p, i64, P(i64)]),
             "tsb_batch_kernel_key": (i32, [vp, P(Opts), C.c_char_p, i32]),
+            "tsb_batch_kernel_variant": (i32, [vp, i32, i32, i32]),
             "tsb_batch_stamp_dev": (i32, [vp, i32, dbl, dbl, dbl, u64, u64, P(Opts)]),
             "tsb_batch_set_order": (i32, [vp, P(i64)]),
             "tsb_lu_order": (i32, [i32, P(dbl), P(i32), P(i32)]),
@@ -170,6 +176,24 @@ class Context:
     def set_stream(self, stream: int):
         self._check(lib().tsb_ctx_set_stream(self.h, stream), "set_stream")
 
+    @property
+    def stream(self) -> int:
+        v = C.c_uint64()
+        self._check(lib().tsb_ctx_get_stream(self.h, C.byref(v)), "get_stream")
+        return v.value
+
+    def wait_torch_stream(self):
+        """Orders the context's stream after everything queued so far on torch's current stream (tsb_ctx_wait_event): call
+        it between producing a CUDA tensor with torch and handing its pointer to the library (tspice_b200.h, 'Stream
+        ordering contract').  A no-op when the context already launches on torch's current stream."""
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == self.stream:
+            return
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._check(lib().tsb_ctx_wait_event(self.h, ev.cuda_event), "tsb_ctx_wait_event")
+
     def set_cache_dir(self, d: str):
         self._check(lib().tsb_ctx_set_cache_dir(self.h, d.encode()), "set_cache_dir")
 
@@ -202,7 +226,9 @@ class Context:
         return x, st
 
     def lu_solve_batched_dev(self, n: int, n_inst: int, A_ptr: int, b_ptr: int, x_ptr: int, status_ptr: int, order, strict: bool = False):
-        """Same with device pointers (e.g. torch tensors' data_ptr()); asynchronous on the context's stream."""
+        """Same with device pointers (e.g. torch tensors' data_ptr()); asynchronous on the context's stream, which is first
+        ordered after torch's current stream (the producer of the buffers)."""
+        self.wait_torch_stream()
         pr = np.ascontiguousarray(order[0], dtype=np.int32); pc = np.ascontiguousarray(order[1], dtype=np.int32)
         ip = C.POINTER(C.c_int)
         self._check(lib().tsb_lu_solve_batched_dev(self.h, n, pr.ctypes.data_as(ip), pc.ctypes.data_as(ip), A_ptr, b_ptr, x_ptr,
@@ -351,7 +377,7 @@ class Batch:
         rc = lib().tsb_batch_create(ckt.h, self.n_inst, C.byref(self.h))
         if rc != 0:
             raise TsbError(f"tsb_batch_create failed ({rc})")
-        self._keep = []
+        self._keep = {}           # (dev, param) -> the array / tensor the library still reads from (one reference per slot)
 
     def _err(self) -> str:
         return lib().tsb_last_error(self.ckt.ctx.h if self.ckt.ctx else None).decode()
@@ -371,8 +397,10 @@ class Batch:
     def _dev(self, dev) -> int:
         return self.ckt.dev_index(dev) if isinstance(dev, str) else int(dev)
 
-    def set_param(self, dev, param: int, values):
-        """values: host array [n_inst] (copied H2D), a scalar (uniform), or a CUDA torch tensor (borrowed)."""
+    def set_param(self, dev, param: int, values, zero_copy: bool = False):
+        """values: host array [n_inst] (copied: staged through a library-owned pinned buffer), a scalar (uniform), or a CUDA
+        torch tensor (borrowed; the context's stream is ordered after torch's current stream).  zero_copy=True hands a
+        (pinned) host array to tsb_batch_set_param_async: it must stay unmodified until the next sync()."""
         d = self._dev(dev)
         if np.isscalar(values):
             self._check(lib().tsb_batch_set_param_uniform(self.h, d, param, float(values)), "set_param_uniform")
@@ -380,7 +408,9 @@ class Batch:
         if hasattr(values, "is_cuda") and values.is_cuda:
             import torch
             assert values.dtype == torch.float64 and values.is_contiguous() and values.numel() == self.n_inst
-            self._keep.append(values)
+            self._keep[(d, param)] = values
+            if self.ckt.ctx is not None:
+                self.ckt.ctx.wait_torch_stream()
             self._check(lib().tsb_batch_set_param_dev(self.h, d, param, values.data_ptr()), "set_param_dev")
             return
         if hasattr(values, "numpy"):
@@ -388,10 +418,20 @@ class Batch:
         v = np.ascontiguousarray(values, dtype=np.float64)
         if v.shape != (self.n_inst,):
             raise ValueError("values must have shape [n_inst]")
-        self._keep.append(v)
-        self._check(lib().tsb_batch_set_param(self.h, d, param, v.ctypes.data_as(C.POINTER(C.c_double))), "set_param")
+        if zero_copy:
+            self._keep[(d, param)] = v
+            self._check(lib().tsb_batch_set_param_async(self.h, d, param, v.ctypes.data_as(C.POINTER(C.c_double))), "set_param_async")
+        else:
+            self._keep.pop((d, param), None)
+            self._check(lib().tsb_batch_set_param(self.h, d, param, v.ctypes.data_as(C.POINTER(C.c_double))), "set_param")
 
     # -- kernel introspection -------------------------------------------------------------------
+    def kernel_variant(self, dc_src=-1, dc_src2=-1, grid=False):
+        """Select the specialisation kernel_source / kernel_key describe (introspection-only batches; build step)."""
+        d1 = self._dev(dc_src) if dc_src != -1 else -1
+        d2 = self._dev(dc_src2) if dc_src2 != -1 else -1
+        self._check(lib().tsb_batch_kernel_variant(self.h, d1, d2, int(bool(grid))), "tsb_batch_kernel_variant")
+
     def kernel_source(self, opts: Opts | None = None) -> str:
         need = C.c_int64()
         o = C.byref(opts) if opts is not None else None
@@ -417,6 +457,11 @@ class Batch:
         self._check(lib().tsb_run_dc(self.h, self._dev(src), start, stop, inc, out,
                                      C.byref(opts) if opts is not None else None), "tsb_run_dc")
 
+    def run_dc2(self, src1, start1, stop1, inc1, src2, start2, stop2, inc2, out=OUT_WAVE, opts: Opts | None = None):
+        """Nested sweep (DCSweep.nestedSweep, dc.go:205-270): source 1 is the outer loop."""
+        self._check(lib().tsb_run_dc2(self.h, self._dev(src1), start1, stop1, inc1, self._dev(src2), start2, stop2, inc2, out,
+                                      C.byref(opts) if opts is not None else None), "tsb_run_dc2")
+
     def set_order(self, perm):
         """Processing order (tsb_batch_set_order): slot s works on instance perm[s]; None removes it."""
         if perm is None:
@@ -427,6 +472,8 @@ class Batch:
 
     def stamp_dev(self, mode: int, time: float, dt: float, gmin: float, A_ptr: int, b_ptr: int, opts: Opts | None = None):
         """Operator level: the dense stamped system of every instance into device memory (tsb_batch_stamp_dev)."""
+        if self.ckt.ctx is not None:
+            self.ckt.ctx.wait_torch_stream()
         self._check(lib().tsb_batch_stamp_dev(self.h, mode, time, dt, gmin, A_ptr, b_ptr,
                                               C.byref(opts) if opts is not None else None), "tsb_batch_stamp_dev")
 
@@ -589,9 +636,14 @@ class DCSweep(_BaseAnalysis):
     def Execute(self):
         if self.batch is None:
             raise TsbError("circuit not set")
-        if len(self.sourceNames) != 1:
-            raise TsbError(f"unsupported number of sweep sources: {len(self.sourceNames)}")   # dc.go:86 (nested: not batched yet)
-        self.batch.run_dc(self.sourceNames[0], self.startVals[0], self.stopVals[0], self.increments[0], self.out, self.opts)
+        if len(self.sourceNames) == 1:                                                        # dc.go:76-78 singleSweep
+            self.batch.run_dc(self.sourceNames[0], self.startVals[0], self.stopVals[0], self.increments[0], self.out, self.opts)
+        elif len(self.sourceNames) == 2:                                                      # dc.go:81-83 nestedSweep
+            self._analysis = AN_DC2
+            self.batch.run_dc2(self.sourceNames[0], self.startVals[0], self.stopVals[0], self.increments[0],
+                               self.sourceNames[1], self.startVals[1], self.stopVals[1], self.increments[1], self.out, self.opts)
+        else:
+            raise TsbError(f"unsupported number of sweep sources: {len(self.sourceNames)}")   # dc.go:86
         self.batch.sync()
         return None
 

@@ -240,6 +240,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("static constexpr int N = " + std::to_string(n) + ";");
     e.line("static constexpr int NCOL_MAX = " + std::to_string(ncol_tran) + ";");
     e.line("static constexpr bool HAS_NL = " + std::string(pl.has_nonlinear ? "true" : "false") + ";");
+    e.line("static constexpr int DC_NESTED = " + std::string(cfg.dc_nested ? "1" : "0") + ";   // tsb_dc: rows carry SWEEP1 and SWEEP2 (dc.go:272-288)");
     e.line("double P[" + std::to_string(std::max(1, pl.n_params)) + "];      // parameters");
     e.line("double S[" + std::to_string(std::max(1, pl.n_state)) + "];      // device state carried between solves");
     e.line("double D[" + std::to_string(std::max(1, pl.n_derived)) + "];      // per-instance constants derived from P (1/R, L0, M)");
@@ -351,6 +352,12 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("__device__ __forceinline__ void set_dc(double v) {");
     ++e.ind;
     if (cfg.dc_param >= 0) e.line("P[" + std::to_string(cfg.dc_param) + "] = v;   // VoltageSource.SetValue (vsource.go:241-244)");
+    e.line("(void)v;");
+    --e.ind;
+    e.line("}");
+    e.line("__device__ __forceinline__ void set_dc2(double v) {   // the inner source of a nested sweep (dc.go:236)");
+    ++e.ind;
+    if (cfg.dc_param2 >= 0) e.line("P[" + std::to_string(cfg.dc_param2) + "] = v;");
     e.line("(void)v;");
     --e.ind;
     e.line("}");

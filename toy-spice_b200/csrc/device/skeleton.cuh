@@ -53,6 +53,7 @@ struct TsbArgs {
     long long n_run;           // instances [0, n_run) are processed (n_inst stays the array stride); < n_inst only
                                // while the library times launch-bounds candidates on a sub-batch
     const long long* order;    // optional processing order (tsb_batch_set_order): slot s works on instance order[s]
+    const double* sweep2;      // nested DC sweep (dc.go:205-270): value of the inner source at point k (sweep[] holds the outer one)
 };
 
 // Slot -> instance.  With an order, lanes of a warp can be given instances that behave alike (similar Newton
@@ -638,11 +639,15 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
 // keeps only what has an effect — the side effects of Stamp() on device state; its factor + solve, whose result the
 // first Newton iteration overwrites before anything reads it, are not executed.  `valid`: this lane has an instance
 // (every lane of a warp must call: full-mask votes).
+// Nested sweep (dc.go:205-288, Ckt::DC_NESTED): the host flattens `for val1 { for val2 {...} }` into one list of
+// points (sweep[k], sweep2[k]) — SetValue on the outer source with an unchanged value is idempotent — and a stored row
+// is [SWEEP1, SWEEP2, signals...] (StoreNestedResult).
 template <class Ckt>
 __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long inst, bool valid) {
     constexpr int N = Ckt::N;
+    constexpr int NC = Ckt::NCOL_MAX + Ckt::DC_NESTED;
     Ckt c;
-    TsbSink<Ckt::NCOL_MAX> sink(a, inst);
+    TsbSink<NC> sink(a, inst);
     if (valid) { c.load(a, inst); c.init(); sink.begin(inst); }
     int n_sol = 0, n_pts = 0;
     int status = TSB_ST_OK;
@@ -651,6 +656,7 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     for (int k = 0; k < a.n_sweep && __any_sync(0xffffffffu, live); ++k) {
         if (live) {
             c.set_dc(a.sweep[k]);
+            if (Ckt::DC_NESTED) c.set_dc2(a.sweep2[k]);
             c.eval_sources(0.0, 1.0);
             (void)c.template assemble_solve<TSB_MODE_OP, true, false>(TSB_MODE_OP, 0.0, 0.0, 0.0, 1e-12);
             ++n_pts;
@@ -677,9 +683,10 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
         if (live) {
             if (fail) { status = TSB_ST_DC_FAILED; fail_at = a.sweep[k]; live = false; }
             else {
-                double row[Ckt::NCOL_MAX];
+                double row[NC];
                 row[0] = a.sweep[k];
-                c.signals(row + 1);
+                if (Ckt::DC_NESTED) row[1] = a.sweep2[k];
+                c.signals(row + 1 + Ckt::DC_NESTED);
                 sink.push(row);
             }
         }

@@ -120,7 +120,7 @@ int Plan::num_columns(int an) const {
     if (an == TSB_AN_OP) return n_nodes + n_branches;
     int nr = 0;
     for (const Dev& d : devs) if (d.kind == TSB_R) ++nr;
-    return 1 + n_nodes + n_branches + nr;
+    return (an == TSB_AN_DC2 ? 2 : 1) + n_nodes + n_branches + nr;     // nested sweep: SWEEP1, SWEEP2 (dc.go:272-288)
 }
 
 std::string Plan::column_name(int an, int col) const {
@@ -128,6 +128,10 @@ std::string Plan::column_name(int an, int col) const {
     if (an != TSB_AN_OP) {
         if (k == 0) return an == TSB_AN_TRAN ? "TIME" : "SWEEP1";
         --k;
+        if (an == TSB_AN_DC2) {
+            if (k == 0) return "SWEEP2";
+            --k;
+        }
     }
     if (k < n_nodes) {
         if ((int)node_names.size() > k + 1) return "V(" + node_names[k + 1] + ")";

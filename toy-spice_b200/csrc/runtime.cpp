@@ -59,6 +59,7 @@ struct TsbArgsHost {
     int n_grid;
     long long n_run;
     const long long* order;
+    const double* sweep2;
 };
 
 struct KernelModule {
@@ -83,6 +84,7 @@ struct tsb_ctx {
     std::atomic<int> refs{1};
     bool guard = false;                                // $TSB_GUARD=1: result buffers carry guard bands checked at every sync
     long long choice_epoch = 0;                        // bumped whenever auto_choice changes (invalidates batch memos)
+    std::string tuned_suffix = ".tuned";               // ".<gpu name>-<SMs>sm.tuned": a timed choice holds for one GPU model only
 };
 
 struct tsb_plan {
@@ -101,6 +103,8 @@ struct tsb_batch {
     std::vector<int> var_slot;
     std::vector<double*> slot_ptr;                     // device pointer per slot
     std::vector<char> slot_owned;
+    std::vector<double*> slot_stage;                   // per slot: library-owned pinned staging buffer of tsb_batch_set_param
+    std::vector<cudaEvent_t> slot_staged;              //           and the event that marks its H2D copy as done
     double* d_uniform = nullptr;
     // results of the last run
     int analysis = -1, ncol = 0, out_flags = 0;
@@ -111,6 +115,10 @@ struct tsb_batch {
     unsigned long long* d_totals = nullptr;
     unsigned long long* d_work = nullptr;              // lane-refill work counter
     bool grid_kernel = false;                          // the next module request wants the TSB_OUT_GRID specialisation
+    bool dc_nested = false;                            // ... the nested-sweep specialisation of tsb_dc (rows carry SWEEP1 and SWEEP2)
+    int dc_param2 = -1;                                //     and the inner source's parameter
+    double* d_sweep2 = nullptr;
+    int intro_dc_param = -1;                           // tsb_batch_kernel_variant: what kernel_source / kernel_key describe
     std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
     // memo of the last module request: generating the kernel source to derive its cache key costs ~0.3 ms of host
     // time, which is the length of a short launch (the stamp kernel); identical requests skip it
@@ -242,6 +250,7 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
     cfg.grid = b->grid_kernel;
+    cfg.dc_nested = b->dc_nested; cfg.dc_param2 = b->dc_param2;
     cfg.order = b->d_order != nullptr;
     if (const char* x = getenv("TSB_EXTRA_DEFINES")) {          // development knob for A/B kernel experiments
         std::string item;
@@ -265,6 +274,14 @@ bool read_file(const std::string& path, std::vector<char>& out) {
     if (!f) return false;
     out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
     return !out.empty();
+}
+
+// Small cache files (<autokey>.auto, <autokey>.<gpu>.tuned) are written under a private name and renamed into place like
+// the cubins: ranks of one job share the directory.
+void write_small_file(const std::string& path, const std::string& content) {
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    { std::ofstream f(tmp); f << content; }
+    rename(tmp.c_str(), path.c_str());
 }
 
 // cubin (+ ptxas figures) of one fully specified source: kernel cache first, NVRTC on a miss.
@@ -307,8 +324,8 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     sig.append(b->varying.begin(), b->varying.end());
     const char* xd = getenv("TSB_EXTRA_DEFINES");
     char tail[160];
-    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
-             (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, ctx->choice_epoch, (void*)ctx);
+    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
+             (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, (int)b->dc_nested, b->dc_param2, ctx->choice_epoch, (void*)ctx);
     sig += tail;
     if (xd) sig += xd;
     if (b->memo_module && sig == b->memo_sig) {
@@ -338,7 +355,7 @@ int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** o
         auto ch = ctx->auto_choice.find(autokey);
         int chosen = ch != ctx->auto_choice.end() ? ch->second : 0;
         if (!chosen) {                       // a choice timed by an earlier process on this machine
-            std::ifstream f(ctx->cache_dir + "/" + autokey + ".tuned");
+            std::ifstream f(ctx->cache_dir + "/" + autokey + ctx->tuned_suffix);
             if (f && (f >> chosen) && chosen >= 1 && chosen <= 8) ctx->tuned[autokey] = chosen; else chosen = 0;
         }
         if (!chosen) {
@@ -359,8 +376,7 @@ int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** o
                 if (sp <= TSB_SPILL_OK) { best = mb; break; }
             }
             chosen = best;
-            std::ofstream f(ctx->cache_dir + "/" + autokey + ".auto");
-            f << chosen << "\n";
+            write_small_file(ctx->cache_dir + "/" + autokey + ".auto", std::to_string(chosen) + "\n");
         }
         if (!ctx->auto_choice.count(autokey) || ctx->auto_choice[autokey] != chosen) { ctx->auto_choice[autokey] = chosen; ++ctx->choice_epoch; }
         o.min_blocks = chosen;
@@ -434,9 +450,9 @@ int guard_check(tsb_batch* b) {
 
 void free_results(tsb_batch* b) {
     gfree(b, b->d_wave); gfree(b, b->d_stats); gfree(b, b->d_rows); gfree(b, b->d_status);
-    gfree(b, b->d_counters); gfree(b, b->d_scratch); gfree(b, b->d_sweep); cudaFree(b->d_totals); cudaFree(b->d_work);
+    gfree(b, b->d_counters); gfree(b, b->d_scratch); gfree(b, b->d_sweep); gfree(b, b->d_sweep2); cudaFree(b->d_totals); cudaFree(b->d_work);
     b->d_work = nullptr;
-    b->d_wave = b->d_stats = b->d_scratch = b->d_sweep = nullptr;
+    b->d_wave = b->d_stats = b->d_scratch = b->d_sweep = b->d_sweep2 = nullptr;
     b->d_rows = b->d_counters = nullptr; b->d_status = nullptr; b->d_totals = nullptr;
     b->wave_bytes = b->stats_bytes = 0;
 }
@@ -462,7 +478,11 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     if (!b->d_scratch) CU(ctx, galloc(b, (void**)&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
     if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 5 * sizeof(unsigned long long)));
     if (!b->d_work) CU(ctx, cudaMalloc(&b->d_work, sizeof(unsigned long long)));
-    if (n_sweep > 0) { gfree(b, b->d_sweep); CU(ctx, galloc(b, (void**)&b->d_sweep, (size_t)n_sweep * sizeof(double))); }
+    if (n_sweep > 0) {
+        gfree(b, b->d_sweep); CU(ctx, galloc(b, (void**)&b->d_sweep, (size_t)n_sweep * sizeof(double)));
+        gfree(b, b->d_sweep2);
+        if (analysis == TSB_AN_DC2) CU(ctx, galloc(b, (void**)&b->d_sweep2, (size_t)n_sweep * sizeof(double)));
+    }
     b->analysis = analysis; b->ncol = ncol; b->out_flags = out_flags; b->cap_rows = cap_rows;
     return TSB_OK;
 }
@@ -470,7 +490,8 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
 int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args, bool persistent = false, int min_blocks = 0) {
     tsb_ctx* ctx = b->ctx;
     int block = o.block_size > 0 ? o.block_size : 128;
-    size_t smem = (args.out_flags & (TSB_OUT_STATS | TSB_OUT_GRID)) ? (size_t)4 * b->plan->p.num_columns(TSB_AN_TRAN) * block * sizeof(double) : 0;
+    const int ncol_smem = b->plan->p.num_columns(b->analysis == TSB_AN_DC2 ? TSB_AN_DC2 : TSB_AN_TRAN);
+    size_t smem = (args.out_flags & (TSB_OUT_STATS | TSB_OUT_GRID)) ? (size_t)4 * ncol_smem * block * sizeof(double) : 0;
     if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = (args.n_run + block - 1) / block;
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
@@ -575,8 +596,7 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
     ctx->auto_choice[autokey] = best;
     ++ctx->choice_epoch;
     ctx->tuned[autokey] = best;
-    std::ofstream f(ctx->cache_dir + "/" + autokey + ".tuned");
-    f << best << "\n";
+    write_small_file(ctx->cache_dir + "/" + autokey + ctx->tuned_suffix, std::to_string(best) + "\n");
     return TSB_OK;
 }
 
@@ -615,6 +635,14 @@ int tsb_ctx_create(int device_ordinal, tsb_ctx** out) {
     ctx->stream = ctx->own_stream;
     const char* env = getenv("TSB_KCACHE");
     ctx->cache_dir = env && *env ? env : lib_dir() + "/_kcache";
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) {
+            std::string nm;
+            for (const char* c = prop.name; *c; ++c) nm += (isalnum((unsigned char)*c) ? *c : '_');
+            ctx->tuned_suffix = "." + nm + "-" + std::to_string(ctx->sms) + "sm.tuned";
+        } else cudaGetLastError();
+    }
     const char* g = getenv("TSB_GUARD");
     ctx->guard = g && *g && *g != '0';
     *out = ctx.release();
@@ -637,6 +665,19 @@ const char* tsb_last_error(tsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_glo
 int tsb_ctx_set_stream(tsb_ctx* ctx, uint64_t stream) {
     if (!ctx) return TSB_E_INVALID;
     ctx->stream = stream ? (cudaStream_t)(uintptr_t)stream : ctx->own_stream;
+    return TSB_OK;
+}
+int tsb_ctx_get_stream(tsb_ctx* ctx, uint64_t* stream) {
+    if (!ctx || !stream) return TSB_E_INVALID;
+    *stream = (uint64_t)(uintptr_t)ctx->stream;
+    return TSB_OK;
+}
+// Orders everything launched on the context's stream from now on after `event` (a cudaEvent_t recorded by the caller on
+// the stream that produced borrowed device buffers: tsb_batch_set_param_dev, tsb_batch_stamp_dev, tsb_lu_solve_batched_dev).
+int tsb_ctx_wait_event(tsb_ctx* ctx, uint64_t event) {
+    if (!ctx || !event) return TSB_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)(uintptr_t)event, 0));
     return TSB_OK;
 }
 int tsb_ctx_set_cache_dir(tsb_ctx* ctx, const char* dir) {
@@ -799,7 +840,10 @@ void tsb_batch_destroy(tsb_batch* b) {
     if (!b) return;
     if (b->ctx) {
         cudaSetDevice(b->ctx->device);
-        for (size_t s = 0; s < b->slot_ptr.size(); ++s) if (b->slot_owned[s]) cudaFree(b->slot_ptr[s]);
+        for (size_t s = 0; s < b->slot_ptr.size(); ++s) {
+            if (b->slot_owned[s]) cudaFree(b->slot_ptr[s]);
+            if (b->slot_stage[s]) { cudaEventSynchronize(b->slot_staged[s]); cudaFreeHost(b->slot_stage[s]); cudaEventDestroy(b->slot_staged[s]); }
+        }
         cudaFree(b->d_uniform);
         cudaFree(b->d_order);
         free_results(b);
@@ -825,9 +869,15 @@ static int claim_slot(tsb_batch* b, int flat) {
     b->var_slot[flat] = (int)b->slot_ptr.size();
     b->slot_ptr.push_back(nullptr);
     b->slot_owned.push_back(0);
+    b->slot_stage.push_back(nullptr);
+    b->slot_staged.push_back(nullptr);
     return b->var_slot[flat];
 }
-int tsb_batch_set_param(tsb_batch* b, int dev, int param, const double* values) {
+// Host values -> the parameter's device array.  `staged`: the values are first copied into a library-owned pinned
+// buffer, so the caller's buffer is free again when the call returns whatever memory it is (with pinned caller memory
+// cudaMemcpyAsync is a true DMA that reads the buffer later).  !staged (tsb_batch_set_param_async): zero-copy, the
+// caller keeps the buffer valid and unmodified until the next tsb_batch_sync / result read.
+static int set_param_host(tsb_batch* b, int dev, int param, const double* values, bool staged) {
     int flat = 0, rc = param_index(b, dev, param, &flat);
     if (rc != TSB_OK) return rc;
     if (!values) return TSB_E_INVALID;
@@ -835,14 +885,27 @@ int tsb_batch_set_param(tsb_batch* b, int dev, int param, const double* values) 
     if (!b->ctx) return TSB_OK;      // host-only plan: only the "varies per instance" fact is recorded
     tsb_ctx* ctx = b->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)b->n_inst * sizeof(double);
     if (!b->slot_owned[slot]) {
         double* p = nullptr;
-        CU(ctx, cudaMalloc(&p, (size_t)b->n_inst * sizeof(double)));
+        CU(ctx, cudaMalloc(&p, bytes));
         b->slot_ptr[slot] = p; b->slot_owned[slot] = 1;
     }
-    CU(ctx, cudaMemcpyAsync(b->slot_ptr[slot], values, (size_t)b->n_inst * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const double* src = values;
+    if (staged) {
+        if (!b->slot_stage[slot]) {
+            CU(ctx, cudaMallocHost((void**)&b->slot_stage[slot], bytes));
+            CU(ctx, cudaEventCreateWithFlags(&b->slot_staged[slot], cudaEventDisableTiming));
+        } else CU(ctx, cudaEventSynchronize(b->slot_staged[slot]));      // the previous copy out of this staging buffer
+        memcpy(b->slot_stage[slot], values, bytes);
+        src = b->slot_stage[slot];
+    }
+    CU(ctx, cudaMemcpyAsync(b->slot_ptr[slot], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (staged) CU(ctx, cudaEventRecord(b->slot_staged[slot], ctx->stream));
     return TSB_OK;
 }
+int tsb_batch_set_param(tsb_batch* b, int dev, int param, const double* values) { return set_param_host(b, dev, param, values, true); }
+int tsb_batch_set_param_async(tsb_batch* b, int dev, int param, const double* values) { return set_param_host(b, dev, param, values, false); }
 int tsb_batch_set_param_dev(tsb_batch* b, int dev, int param, uint64_t dev_ptr) {
     int flat = 0, rc = param_index(b, dev, param, &flat);
     if (rc != TSB_OK) return rc;
@@ -914,8 +977,10 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     a.grid_dt = grid_dt; a.n_grid = (int)n_grid;
     const bool persistent = b->plan->p.has_nonlinear && o.lane_refill != 0;
     const char* tune_env = getenv("TSB_AUTOTUNE");
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
     if (o.min_blocks <= 0 && !autokey.empty() && b->n_inst >= TSB_TUNE_MIN_INSTANCES && !ctx->tuned.count(autokey) &&
-        !(tune_env && *tune_env == '0')) {
+        !(tune_env && *tune_env == '0') && cap == cudaStreamCaptureStatusNone) {
         rc = autotune_min_blocks(b, o, autokey, m->min_blocks, a, persistent);
         if (rc == TSB_OK) rc = get_module(b, o, -1, &m);
         if (rc != TSB_OK) { b->grid_kernel = false; return rc; }
@@ -924,32 +989,64 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     return launch(b, o, m->optran, a, persistent, m->min_blocks);
 }
 
-int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts) {
+// DC sweep, one source (dc.go:88-140) or two nested sources (dc.go:205-270; src2_dev >= 0: the outer loop runs over
+// source 1, the inner over source 2).  The sweep axes are the same for every instance, so the host flattens them into
+// one list of points and the device loop stays warp-uniform.
+static int run_dc_impl(tsb_batch* b, int src_dev, double start, double stop, double inc, int src2_dev, double start2, double stop2,
+                       double inc2, int out_flags, const tsb_opts* opts) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
     const Plan& p = b->plan->p;
-    if (src_dev < 0 || src_dev >= (int)p.devs.size() || p.devs[src_dev].kind != TSB_V)
-        return fail(ctx, TSB_E_INVALID, "source not found");                       // dc.go:47-68
-    if (!(inc > 0)) return fail(ctx, TSB_E_INVALID, "sweep increment must be positive");
+    const bool nested = src2_dev != -1;
+    auto is_vsrc = [&](int d) { return d >= 0 && d < (int)p.devs.size() && p.devs[d].kind == TSB_V; };
+    if (!is_vsrc(src_dev) || (nested && !is_vsrc(src2_dev)))
+        return fail(ctx, TSB_E_INVALID, nested ? "source not found" : "source not found");       // dc.go:47-68, :226-228
+    if (!(inc > 0) || (nested && !(inc2 > 0))) return fail(ctx, TSB_E_INVALID, "sweep increment must be positive");
     if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID applies to transient analysis only");
     if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
-    std::vector<double> sweep;
-    for (double v = start; v <= stop; v += inc) { sweep.push_back(v); if (sweep.size() > (1u << 24)) break; }   // dc.go:36-42
+    std::vector<double> s1, s2;
+    for (double v = start; v <= stop; v += inc) { s1.push_back(v); if (s1.size() > (1u << 24)) break; }   // dc.go:36-42
+    if (nested) for (double v = start2; v <= stop2; v += inc2) { s2.push_back(v); if (s2.size() > (1u << 24)) break; }
+    std::vector<double> sweep, sweep2;
+    if (!nested) sweep = s1;
+    else {
+        if ((double)s1.size() * (double)s2.size() > (double)(1u << 24)) return fail(ctx, TSB_E_INVALID, "nested sweep: more than 2^24 points");
+        for (double v1 : s1) for (double v2 : s2) { sweep.push_back(v1); sweep2.push_back(v2); }
+    }
     tsb_opts o = resolve(opts, b->plan->p);
     CU(ctx, cudaSetDevice(ctx->device));
-    const Dev& sd = p.devs[src_dev];
-    int st = sd.src_type();
-    int dc_param = (st == TSB_SRC_DC || st == TSB_SRC_SIN) ? sd.p_off : -1;   // SetValue only reaches dcValue
-    if (dc_param >= 0 && b->varying[dc_param]) return fail(ctx, TSB_E_INVALID, "the swept source value is set per instance");
+    auto dc_param_of = [&](int d) {
+        const Dev& sd = p.devs[d];
+        const int st = sd.src_type();
+        return (st == TSB_SRC_DC || st == TSB_SRC_SIN) ? sd.p_off : -1;          // SetValue only reaches dcValue
+    };
+    const int dc_param = dc_param_of(src_dev), dc_param2 = nested ? dc_param_of(src2_dev) : -1;
+    if ((dc_param >= 0 && b->varying[dc_param]) || (dc_param2 >= 0 && b->varying[dc_param2]))
+        return fail(ctx, TSB_E_INVALID, "the swept source value is set per instance");
+    const int an = nested ? (int)TSB_AN_DC2 : (int)TSB_AN_DC;
     KernelModule* m = nullptr;
-    if ((rc = get_module(b, o, dc_param, &m)) != TSB_OK) return rc;
-    if ((rc = alloc_results(b, TSB_AN_DC, out_flags, (out_flags & TSB_OUT_WAVE) ? (int64_t)sweep.size() : 0, (int)sweep.size())) != TSB_OK) return rc;
+    b->dc_nested = nested; b->dc_param2 = dc_param2;
+    rc = get_module(b, o, dc_param, &m);
+    b->dc_nested = false; b->dc_param2 = -1;
+    if (rc != TSB_OK) return rc;
+    if ((rc = alloc_results(b, an, out_flags, (out_flags & TSB_OUT_WAVE) ? (int64_t)sweep.size() : 0, (int)sweep.size())) != TSB_OK) return rc;
     TsbArgsHost a;
     if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
-    if (!sweep.empty()) CU(ctx, cudaMemcpyAsync(b->d_sweep, sweep.data(), sweep.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (!sweep.empty()) {
+        CU(ctx, cudaMemcpyAsync(b->d_sweep, sweep.data(), sweep.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (nested) CU(ctx, cudaMemcpyAsync(b->d_sweep2, sweep2.data(), sweep2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));     // `sweep` is a stack vector
-    a.analysis = TSB_AN_DC; a.sweep = b->d_sweep; a.n_sweep = (int)sweep.size();
+    a.analysis = TSB_AN_DC; a.sweep = b->d_sweep; a.sweep2 = b->d_sweep2; a.n_sweep = (int)sweep.size();
     return launch(b, o, m->dc, a);
+}
+int tsb_run_dc(tsb_batch* b, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts) {
+    return run_dc_impl(b, src_dev, start, stop, inc, -1, 0, 0, 0, out_flags, opts);
+}
+int tsb_run_dc2(tsb_batch* b, int src1_dev, double start1, double stop1, double inc1, int src2_dev, double start2, double stop2,
+                double inc2, int out_flags, const tsb_opts* opts) {
+    if (src2_dev < 0) return fail(b ? b->ctx : nullptr, TSB_E_INVALID, "source not found");
+    return run_dc_impl(b, src1_dev, start1, stop1, inc1, src2_dev, start2, stop2, inc2, out_flags, opts);
 }
 
 // Operator level: the device-stamp kernel on its own.  Writes, for every instance, the dense MNA system the reference
@@ -1163,10 +1260,28 @@ int tsb_lu_solve_batched(tsb_ctx* ctx, int n, const int* pivot_row, const int* p
 }
 
 // ---- introspection -------------------------------------------------------------------------------
+// Selects which specialisation tsb_batch_kernel_source / _key describe (the build step pre-compiles them): the DC-sweep
+// kernels are specialised for the swept source(s), the TSB_OUT_GRID kernels carry the resampling code.
+int tsb_batch_kernel_variant(tsb_batch* b, int dc_src_dev, int dc_src2_dev, int grid) {
+    if (!b) return TSB_E_INVALID;
+    const Plan& p = b->plan->p;
+    auto param_of = [&](int d, int* out) {
+        if (d < 0) { *out = -1; return true; }
+        if (d >= (int)p.devs.size() || p.devs[d].kind != TSB_V) return false;
+        const int st = p.devs[d].src_type();
+        *out = (st == TSB_SRC_DC || st == TSB_SRC_SIN) ? p.devs[d].p_off : -1;
+        return true;
+    };
+    int p1 = -1, p2 = -1;
+    if (!param_of(dc_src_dev, &p1) || !param_of(dc_src2_dev, &p2)) return fail(b->ctx, TSB_E_INVALID, "source not found");
+    b->intro_dc_param = p1; b->dc_param2 = p2; b->dc_nested = dc_src2_dev >= 0; b->grid_kernel = grid != 0;
+    b->memo_module = nullptr;
+    return TSB_OK;
+}
 int tsb_batch_kernel_source(tsb_batch* b, const tsb_opts* opts, char* buf, int64_t cap, int64_t* needed) {
     if (!b) return TSB_E_INVALID;
     tsb_opts o = resolve(opts, b->plan->p);
-    std::string src = generate_source(b->plan->p, make_config(b, o, -1));
+    std::string src = generate_source(b->plan->p, make_config(b, o, b->intro_dc_param));
     if (needed) *needed = (int64_t)src.size() + 1;
     if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", src.c_str()); }
     return TSB_OK;
@@ -1174,7 +1289,7 @@ int tsb_batch_kernel_source(tsb_batch* b, const tsb_opts* opts, char* buf, int64
 int tsb_batch_kernel_key(tsb_batch* b, const tsb_opts* opts, char* buf, int cap) {
     if (!b || !buf || cap < 33) return TSB_E_INVALID;
     tsb_opts o = resolve(opts, b->plan->p);
-    std::string src = generate_source(b->plan->p, make_config(b, o, -1));
+    std::string src = generate_source(b->plan->p, make_config(b, o, b->intro_dc_param));
     snprintf(buf, cap, "%s", source_key(src, compile_options_string(o)).c_str());
     return TSB_OK;
 }

@@ -107,6 +107,8 @@ struct CodegenConfig {
     int n_var = 0;
     int block_size = 128;
     int dc_param = -1;              // flat parameter index overwritten by the DC sweep value
+    int dc_param2 = -1;             // nested sweep (dc.go:205-270): parameter of the inner source; dc_nested marks the kernel
+    bool dc_nested = false;
     bool fast_div = false;          // TSB_FAST_DIV build (non-strict): see device/models.cuh
     int min_blocks = 1;             // __launch_bounds__ second argument of the transient kernel
     bool skip_linear = true;        // compile the redundant second linear solve away
