@@ -113,6 +113,13 @@ typedef struct tsb_opts {
                            whose lanes finish together).  Results are bit-identical either way. */
     double grid_dt;     /* TSB_OUT_GRID: spacing of the output grid; 0 (default) = the analysis' tStep after
                            NewTransient's clamping (tran.go:31-33), i.e. >= 300 points */
+    int share_time_grid; /* transient analysis of circuits without nonlinear devices: instances that have taken the same
+                           accept / reject decisions are at the same (time, dt), and what depends on those two only (the
+                           clamped step, 1/dt, the source values when no source parameter varies per instance, the key of
+                           StoreTimeResult's de-duplication) is the same for all of them.  1: a pilot launch (one instance,
+                           beside the main launch) publishes these per attempt, every other instance looks them up and
+                           verifies (time, dt) bit for bit, computing them itself on a miss — results are bit-identical
+                           with and without; 0: off; -1 (default): on for batches of >= 2^18 instances */
 } tsb_opts;
 
 /* Output selection for tsb_run_tran / tsb_run_dc. */

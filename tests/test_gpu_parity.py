@@ -113,6 +113,51 @@ def test_skipping_the_redundant_linear_solve_changes_no_bit(ctx, name):
     assert np.all(counters[0][6] < counters[1][6])
 
 
+@pytest.mark.parametrize("name,n", [("rlc", 2048), ("rc", 4096), ("transformer1", 1024), ("ipulse", 512), ("rr", 256)])
+def test_shared_time_grid_changes_no_bit(ctx, name, n):
+    """tsb_opts.share_time_grid: a pilot launch publishes, per attempt, what depends on (time, dt) only; the other
+    instances look it up, verify (time, dt) bit for bit and compute it themselves on a miss.  With a batch this small
+    the pilot races the readers, so hits and misses interleave: statistics, row counts and every counter must be
+    identical to the run without the table, bit for bit — in the fast AND the strict build."""
+    text = T.BUNDLED[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    for strict in (0, 1):
+        res = []
+        for share in (0, 1, 1):
+            ckt, b, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS, opts=T.default_opts(share_time_grid=share, strict_fp=strict))
+            res.append((b.stats_all(), b.counters(), b.rows(), b.status()))
+        for r in res[1:]:
+            for x, y in zip(res[0], r):
+                assert np.array_equal(x, y, equal_nan=True), (name, strict)
+    # waveforms too (every stored row of 64 instances)
+    ov = PU.draws(name, T.Circuit.from_netlist(text), 64)
+    waves = []
+    for share in (0, 1):
+        ckt, b, _ = PU.run_gpu(ctx, text, 64, ov, cap_rows=24000, opts=T.default_opts(share_time_grid=share))
+        waves.append(b.wave_all())
+    assert np.array_equal(waves[0], waves[1], equal_nan=True)
+
+
+def test_shared_time_grid_with_instances_that_leave_the_grid(ctx):
+    """Instances whose accept / reject decisions differ from the pilot's — here the source amplitude is swept over eight
+    decades, so the truncation error rejects steps in some instances and never in others (20 795 vs ~200 accepted
+    steps) — stop matching the table and compute everything themselves; nothing may change.  (With a per-instance
+    source parameter the table never supplies source values, only the step, 1/dt and the store key.)"""
+    text = T.BUNDLED["rlc"]
+    n = 1024
+    ov = PU.draws("rlc", T.Circuit.from_netlist(text), n)
+    ov[("Vin", 1)] = np.tile(np.array([5.0, 1e-3, 1e-5, 1e-7]), n // 4)
+    res = []
+    for share in (0, 1):
+        ckt, b, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS, opts=T.default_opts(share_time_grid=share))
+        res.append((b.stats_all(), b.counters(), b.rows()))
+    for x, y in zip(*res):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert len(np.unique(res[0][1][0])) >= 3          # the instances really took different numbers of steps
+    _, ores = PU.run_oracle(text, 8, {k: v[:8] for k, v in ov.items()}, want_wave=False)
+    assert np.array_equal(res[1][1][:4, :8].T, ores["counters"][:, :4])
+
+
 def test_nvrtc_runtime_specialisation(ctx, built):
     """An unseen netlist (not in the pre-built kernel cache) is specialised at run time with NVRTC."""
     text = ("ladder\nV1 1 0 SIN(0 1 2k)\nR1 1 2 10\nC1 2 0 100n\nR2 2 3 22\nC2 3 0 47n\nR3 3 4 33\nC3 4 0 10n\n"

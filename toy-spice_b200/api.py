@@ -53,7 +53,8 @@ class TsbError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("abstol", C.c_double), ("reltol", C.c_double), ("gmin", C.c_double),
-                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int), ("lane_refill", C.c_int), ("grid_dt", C.c_double)]
+                ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int), ("lane_refill", C.c_int), ("grid_dt", C.c_double),
+                ("share_time_grid", C.c_int)]
 
 
 def lib_path() -> str:

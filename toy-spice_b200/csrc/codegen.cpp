@@ -232,6 +232,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("#define TSB_LANE_REFILL " + std::to_string(cfg.lane_refill && pl.has_nonlinear ? 1 : 0));
     e.line("#define TSB_GRID " + std::to_string(cfg.grid ? 1 : 0));
     e.line("#define TSB_ORDER " + std::to_string(cfg.order ? 1 : 0));
+    e.line("#define TSB_TGRID " + std::to_string(cfg.tgrid && !pl.has_nonlinear && cfg.skip_linear ? 1 : 0));
     if (!cfg.extra_defines.empty()) e.os << cfg.extra_defines << "\n";     // development knob ($TSB_EXTRA_DEFINES)
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
@@ -240,6 +241,16 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("static constexpr int N = " + std::to_string(n) + ";");
     e.line("static constexpr int NCOL_MAX = " + std::to_string(ncol_tran) + ";");
     e.line("static constexpr bool HAS_NL = " + std::string(pl.has_nonlinear ? "true" : "false") + ";");
+    {
+        // SRC_UNIFORM: no parameter of any source varies per instance, so the source values at a given time are the same
+        // in every instance (what the shared time grid may hand from the pilot to the others)
+        bool uniform = true;
+        for (const Dev& d : pl.devs)
+            if (d.src_slot >= 0 && d.src_type() != TSB_SRC_PWL)
+                for (size_t j = 0; j < d.p.size(); ++j) if (cfg.varying[d.p_off + (int)j]) uniform = false;
+        e.line("static constexpr int NSRC = " + std::to_string(std::max(1, pl.n_src)) + ";");
+        e.line("static constexpr bool SRC_UNIFORM = " + std::string(uniform ? "true" : "false") + ";");
+    }
     e.line("static constexpr int DC_NESTED = " + std::string(cfg.dc_nested ? "1" : "0") + ";   // tsb_dc: rows carry SWEEP1 and SWEEP2 (dc.go:272-288)");
     e.line("double P[" + std::to_string(std::max(1, pl.n_params)) + "];      // parameters");
     e.line("double S[" + std::to_string(std::max(1, pl.n_state)) + "];      // device state carried between solves");

@@ -54,6 +54,12 @@ struct TsbArgs {
                                // while the library times launch-bounds candidates on a sub-batch
     const long long* order;    // optional processing order (tsb_batch_set_order): slot s works on instance order[s]
     const double* sweep2;      // nested DC sweep (dc.go:205-270): value of the inner source at point k (sweep[] holds the outer one)
+    // Shared time grid (TSB_TGRID kernels, see tsb_tran_linear): attempt k of the PILOT instance as
+    // [time, dt | next_time, dt after the tstop clamp | 1/dt, result-store key | source values...]
+    double* tgrid;                       // [tgrid_cap][TsbTgLayout::ND] doubles, or NULL (feature off for this launch)
+    unsigned long long* tgrid_pub;       // number of entries published so far (release / acquire)
+    int tgrid_cap;
+    int tgrid_role;                      // 0: reader, 1: the pilot launch (one instance, publishes)
 };
 
 // Slot -> instance.  With an order, lanes of a warp can be given instances that behave alike (similar Newton
@@ -225,16 +231,44 @@ struct TsbSink {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Shared time grid.  In a sweep over R / L / C ... values the SOURCES are the same in every instance, and as long as
+// two instances have taken the same accept / reject decisions so far they are at the same (time, dt): everything that
+// depends on those two numbers only — the clamped step, 1/dt, every source value (a 45-instruction math.Sin), the
+// formatted-time key of StoreTimeResult — is the same in both, bit for bit.  One extra launch of the SAME kernel, the
+// pilot (one instance, one warp, an SM to itself, so it advances ~2-3x faster per step than a warp that shares its
+// scheduler with five others), publishes these values per attempt; every other thread looks attempt k up, checks that
+// the entry's (time, dt) are its own bit for bit, and on a hit skips the computation.  A miss — entry not published
+// yet, or this instance took another decision somewhere (its LTE differs) — runs the very instructions the pilot ran,
+// so results do not depend on hits and misses (test_shared_time_grid_changes_no_bit).  Decisions (LTE, step growth,
+// solve failures) always stay per instance.  Entries are immutable once published: the pilot stores the entry, then
+// the count with release semantics; readers load the count with acquire semantics and entries below it through L2.
+#ifndef TSB_TGRID
+#define TSB_TGRID 0
+#endif
+#define TSB_TG_HDR 6
+template <int NSRC> struct TsbTgLayout { static constexpr int ND = ((TSB_TG_HDR + NSRC + 1) / 2) * 2; };
+__device__ __forceinline__ unsigned long long tsb_ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tsb_st_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // An accepted transient step (tran.go:137-151): LoadState, Update, advance time, StoreTimeResult with its
 // formatted-time de-duplication (anlysis.go:61-85; `last_key` < 0 = nothing stored yet), step growth.
-template <class Ckt, class Sink>
+// HAVE_KEY: the caller already holds key(next_time) (tsb_tran_linear computes or looks it up with the step's other
+// time-only quantities); otherwise it is computed here.
+template <bool HAVE_KEY = false, class Ckt, class Sink>
 __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& sink, double& time, double& dt,
-                                                double next_time, double lte, TsbTimeKeyer& keyer, double& last_key) {
+                                                double next_time, double lte, TsbTimeKeyer& keyer, double& last_key, double key_in = 0.0) {
     c.load_state(dt);
     c.update_state();
     time = next_time;
     if (time >= a.tstart) {
-        double key = keyer.key(time);             // equal times give equal keys, so one comparison covers both tests
+        double key = HAVE_KEY ? key_in : keyer.key(time);             // equal times give equal keys, so one comparison covers both tests
         if (key != last_key) {
             double row[Ckt::NCOL_MAX];
             row[0] = time;
@@ -262,12 +296,8 @@ __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& 
 //   * the step body kept free of branches up to the accept (TSB_X_NB): reciprocal of dt, source evaluation,
 //     factorisation and substitution form one basic block, so the independent chains (math.Sin polynomial, 1/dt,
 //     pivot reciprocals) overlap instead of queueing behind each other's latency.
-#ifndef TSB_X_PRELTE
-#define TSB_X_PRELTE 1
-#endif
-#ifndef TSB_X_NB
-#define TSB_X_NB 1
-#endif
+//   * everything that depends on (time, dt) only is computed at the top of the attempt — or looked up in the shared
+//     time grid (above), when the batch has one.
 template <class Ckt, class Sink>
 __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& sink, long long& n_acc_out, long long& n_rej_out,
                                                 long long& n_sol_tran_out, long long& n_exec_out, int& status, double& fail_at) {
@@ -275,40 +305,76 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     double last_key = -1.0;
     TsbTimeKeyer keyer; keyer.reset();
     int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves
+    constexpr int ND = TsbTgLayout<Ckt::NSRC>::ND;
+    const bool tg_pub = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 1;
+    bool tg_use = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0;
+    int tg_k = 0, tg_limit = 0, tg_strays = 0;
     while (time < a.tstop) {
-        double next_time = time + dt;
-        if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
-        __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
-        const double rdt = TSB_X_NB ? tsb_rcp_dt(dt) : 1.0 / dt;
-        const double lte = c.lte(dt, rdt);
-        if (TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
-        bool solved;
-        if (TSB_X_NB) {
-            const bool in_range = c.eval_sources_nb(time);
-            solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
-            if (!in_range) {                      // a math.Sin argument beyond 2^29: redo with the general routine
-                c.eval_sources(time, 1.0);
-                solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+        double next_time = 0.0, rdt = 0.0, key = 0.0;
+        bool hit = false;
+        if (TSB_TGRID && tg_use) {
+            if (tg_k >= tg_limit) {                       // caught up with what this thread knows to be published: look again
+                const unsigned long long pub = tsb_ld_acquire(a.tgrid_pub);
+                tg_limit = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
+                if (tg_k >= a.tgrid_cap) tg_use = false;
             }
-        } else {
-            c.eval_sources(time, 1.0);
-            solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+            if (tg_k < tg_limit) {
+                const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)tg_k * ND);
+                const double2 e0 = __ldcg(e), e1 = __ldcg(e + 1), e2 = __ldcg(e + 2);
+                hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(time)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt))) == 0;
+                if (hit) {
+                    next_time = e1.x; dt = e1.y; rdt = e2.x; key = e2.y;
+                    if (Ckt::SRC_UNIFORM) {
+#pragma unroll
+                        for (int j = 0; j < Ckt::NSRC; j += 2) {
+                            const double2 sv = __ldcg(e + 3 + j / 2);
+                            c.SV[j] = sv.x;
+                            if (j + 1 < Ckt::NSRC) c.SV[j + 1] = sv.y;
+                        }
+                    }
+                    tg_strays = 0;
+                } else if (++tg_strays > 64) tg_use = false;     // this instance has left the pilot's grid for good
+            }
         }
+        if (!hit) {
+            const double t_tag = time, dt_tag = dt;
+            next_time = time + dt;
+            if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+            rdt = tsb_rcp_dt(dt);                          // the one division by the time step of this attempt
+            key = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
+            // sources are evaluated at the START of the step; branch-free sine core, general routine only for
+            // an argument beyond its range
+            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
+            if (tg_pub && tg_k < a.tgrid_cap) {
+                double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)tg_k * ND);
+                __stcg(e, make_double2(t_tag, dt_tag));
+                __stcg(e + 1, make_double2(next_time, dt));
+                __stcg(e + 2, make_double2(rdt, key));
+#pragma unroll
+                for (int j = 0; j < Ckt::NSRC; j += 2) __stcg(e + 3 + j / 2, make_double2(c.SV[j], j + 1 < Ckt::NSRC ? c.SV[j + 1] : 0.0));
+                tsb_st_release(a.tgrid_pub, (unsigned long long)tg_k + 1);
+            }
+        } else if (!Ckt::SRC_UNIFORM) {                    // a source parameter varies per instance: the values are this instance's own
+            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
+        }
+        ++tg_k;
+        __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
+        const double lte = c.lte(dt, rdt);
+        if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
+        const bool solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
         if (!solved) {
             ++n_bad;
             if (dt > a.minstep) { dt /= 2; ++n_rej; continue; }
             status = TSB_ST_TRAN_FAILED; fail_at = time;
             break;
         }
-        if (!TSB_X_PRELTE && lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
-        tsb_accept_step(a, c, sink, time, dt, next_time, lte, keyer, last_key);
+        tsb_accept_step<true>(a, c, sink, time, dt, next_time, lte, keyer, last_key, key);
         ++n_acc;
     }
     n_acc_out += n_acc; n_rej_out += n_rej;
     const int failed = status == TSB_ST_TRAN_FAILED ? 1 : 0;
-    // rejected attempts whose solve WAS executed: those rejected for a failing solve (n_bad - failed), or all of
-    // them when the truncation-error test runs after the solve
-    n_exec_out += n_acc + (TSB_X_PRELTE ? n_bad - failed : n_rej) + failed;
+    // rejected attempts whose solve WAS executed: those rejected for a failing solve (n_bad - failed)
+    n_exec_out += n_acc + (n_bad - failed) + failed;
     n_sol_tran_out += 2LL * (n_acc + n_rej) - n_bad + 2 * failed;      // the reference stops at a failing solve, else runs two
 }
 

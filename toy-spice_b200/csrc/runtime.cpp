@@ -60,6 +60,10 @@ struct TsbArgsHost {
     long long n_run;
     const long long* order;
     const double* sweep2;
+    double* tgrid;
+    unsigned long long* tgrid_pub;
+    int tgrid_cap;
+    int tgrid_role;
 };
 
 struct KernelModule {
@@ -72,6 +76,8 @@ struct tsb_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t pilot_stream = nullptr;               // shared time grid: the pilot launch runs beside the main one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     std::string cache_dir;
     std::map<std::string, KernelModule> modules;      // key -> loaded module
@@ -119,6 +125,10 @@ struct tsb_batch {
     int dc_param2 = -1;                                //     and the inner source's parameter
     double* d_sweep2 = nullptr;
     int intro_dc_param = -1;                           // tsb_batch_kernel_variant: what kernel_source / kernel_key describe
+    double* d_tgrid = nullptr;                         // shared time grid of the last transient run (skeleton.cuh)
+    unsigned long long* d_tgrid_pub = nullptr;
+    int tgrid_cap = 0, tgrid_nd = 0;
+    int tgrid_used = 0;                                // the last transient run had a pilot
     std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
     // memo of the last module request: generating the kernel source to derive its cache key costs ~0.3 ms of host
     // time, which is the length of a short launch (the stamp kernel); identical requests skip it
@@ -249,6 +259,7 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.min_blocks = o.min_blocks;            // 0 = "auto" placeholder (never compiled as such)
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
+    cfg.tgrid = o.share_time_grid != 0;
     cfg.grid = b->grid_kernel;
     cfg.dc_nested = b->dc_nested; cfg.dc_param2 = b->dc_param2;
     cfg.order = b->d_order != nullptr;
@@ -324,7 +335,7 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     sig.append(b->varying.begin(), b->varying.end());
     const char* xd = getenv("TSB_EXTRA_DEFINES");
     char tail[160];
-    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
+    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.share_time_grid != 0, o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
              (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, (int)b->dc_nested, b->dc_param2, ctx->choice_epoch, (void*)ctx);
     sig += tail;
     if (xd) sig += xd;
@@ -600,6 +611,48 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
     return TSB_OK;
 }
 
+// Shared time grid (device/skeleton.cuh): the pilot — one more launch of the transient kernel, ONE instance (slot 0),
+// no result output, on a stream of its own so that it runs beside the main launch, with enough dynamic shared memory
+// that no other block shares its SM — publishes what depends on (time, dt) only for every attempt of its run.  Worth it
+// only when the main launch lasts many times longer than the pilot (one instance alone is latency-bound: ~10-20 ms
+// for the 2.4e4 attempts of an inductor deck), hence the instance threshold of the automatic mode.
+const int64_t TSB_TGRID_MIN_INSTANCES = 1 << 18;
+const int TSB_TGRID_CAP = 1 << 16;
+
+int launch_pilot(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& a) {
+    tsb_ctx* ctx = b->ctx;
+    const int nsrc = b->plan->p.n_src > 1 ? b->plan->p.n_src : 1;
+    const int nd = ((6 + nsrc + 1) / 2) * 2;
+    if (!b->d_tgrid || b->tgrid_nd != nd) {
+        cudaFree(b->d_tgrid); b->d_tgrid = nullptr;
+        CU(ctx, cudaMalloc(&b->d_tgrid, (size_t)TSB_TGRID_CAP * nd * sizeof(double)));
+        b->tgrid_nd = nd; b->tgrid_cap = TSB_TGRID_CAP;
+    }
+    if (!b->d_tgrid_pub) CU(ctx, cudaMalloc(&b->d_tgrid_pub, sizeof(unsigned long long)));
+    if (!ctx->pilot_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CU(ctx, cudaStreamCreateWithPriority(&ctx->pilot_stream, cudaStreamNonBlocking, hi));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    // only the published count is reset: readers never look at entries at or above it
+    CU(ctx, cudaMemsetAsync(b->d_tgrid_pub, 0, sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // parameters, uniform table and the reset are in place
+    CU(ctx, cudaStreamWaitEvent(ctx->pilot_stream, ctx->ev_fork, 0));
+    a.tgrid = b->d_tgrid; a.tgrid_pub = b->d_tgrid_pub; a.tgrid_cap = b->tgrid_cap; a.tgrid_role = 0;
+    TsbArgsHost ap = a;
+    ap.tgrid_role = 1; ap.n_run = 1; ap.out_flags = 0; ap.work_counter = b->d_work; ap.first_free = 1;
+    const int block = o.block_size > 0 ? o.block_size : 128;
+    const size_t smem = 208 * 1024;                                // > 227 KB - one main-launch block: the SM is the pilot's alone
+    CU(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* kargs[] = {&ap};
+    CU(ctx, cudaLaunchKernel((const void*)kernel, dim3(1), dim3((unsigned)block), kargs, smem, ctx->pilot_stream));
+    ++ctx->launches;
+    b->tgrid_used = 1;
+    return TSB_OK;
+}
+
 int check_batch(tsb_batch* b) {
     if (!b || !b->plan) return TSB_E_INVALID;
     if (!b->ctx) return fail(nullptr, TSB_E_CUDA, "batch has no GPU context (host-only plan): analyses run on the GPU only");
@@ -615,6 +668,7 @@ void tsb_default_opts(tsb_opts* o) {
     if (!o) return;
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
     o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0; o->grid_dt = 0.0;
+    o->share_time_grid = -1;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -653,6 +707,9 @@ static void ctx_release(tsb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& kv : ctx->modules) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->pilot_stream) cudaStreamDestroy(ctx->pilot_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 static void plan_release(tsb_plan* plan) {
@@ -846,6 +903,7 @@ void tsb_batch_destroy(tsb_batch* b) {
         }
         cudaFree(b->d_uniform);
         cudaFree(b->d_order);
+        cudaFree(b->d_tgrid); cudaFree(b->d_tgrid_pub);
         free_results(b);
     }
     plan_release(b->plan);
@@ -986,7 +1044,19 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         if (rc != TSB_OK) { b->grid_kernel = false; return rc; }
     }
     b->grid_kernel = false;
-    return launch(b, o, m->optran, a, persistent, m->min_blocks);
+    b->tgrid_used = 0;
+    const Plan& pl = b->plan->p;
+    const bool tg_possible = !pl.has_nonlinear && o.skip_linear_resolve != 0 && o.share_time_grid != 0 && !persistent;
+    if (tg_possible && (o.share_time_grid > 0 || b->n_inst >= TSB_TGRID_MIN_INSTANCES)) {
+        if ((rc = launch_pilot(b, o, m->optran, a)) != TSB_OK) return rc;
+    }
+    rc = launch(b, o, m->optran, a, persistent, m->min_blocks);
+    if (rc == TSB_OK && b->tgrid_used) {
+        // join: whatever follows on the context's stream (result reads, the next run) also follows the pilot
+        CU(ctx, cudaEventRecord(ctx->ev_join, ctx->pilot_stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    return rc;
 }
 
 // DC sweep, one source (dc.go:88-140) or two nested sources (dc.go:205-270; src2_dev >= 0: the outer loop runs over

@@ -116,6 +116,7 @@ struct CodegenConfig {
     bool grid = false;              // kernels that carry the TSB_OUT_GRID resampling code
     bool order = false;             // kernels that map launch slots to instances through a processing order
     bool lane_refill = false;       // nonlinear circuits: resident grid, finished lanes fetch the next instance
+    bool tgrid = false;             // linear circuits: kernels that can read / publish the shared time grid (skeleton.cuh)
 };
 std::string generate_source(const Plan& plan, const CodegenConfig& cfg);
 
