@@ -40,6 +40,7 @@ extern "C" {
 typedef struct tsb_ctx tsb_ctx;
 typedef struct tsb_plan tsb_plan;
 typedef struct tsb_batch tsb_batch;
+typedef struct tsb_job tsb_job;
 
 enum {
     TSB_OK = 0,
@@ -252,6 +253,42 @@ int tsb_result_stats_all(tsb_batch* batch, double* out /*[4][n_columns][n_inst]*
 /* Batch totals computed on the GPU: sum over instances of accepted steps, rejected steps, transient solves,
  * OP solves (reference-equivalent counts) and executed factor+solve passes. */
 int tsb_result_totals(tsb_batch* batch, int64_t totals[5]);
+
+/* Asynchronous read-back of the last run's per-instance results into caller-owned PINNED host buffers (NULL = not
+ * wanted): stats [4][n_columns][n_inst], rows [n_inst], status [n_inst], counters [8][n_inst].  The copies run on a copy
+ * stream of the context behind the run and overlap whatever is launched next (another batch's run); the buffers are
+ * complete after tsb_batch_sync(batch).  A later run on the SAME batch waits for them before overwriting the results. */
+int tsb_result_fetch_async(tsb_batch* batch, double* stats, int64_t* rows, int32_t* status, int64_t* counters);
+/* Batch summary reduced ON THE DEVICE: out[3][n_columns] = per column the minimum, maximum and sum over all instances and
+ * stored rows (NaN samples ignored); *rows_total = stored rows of the whole batch (mean = sum / rows_total).  A few KB
+ * cross the bus instead of 32 * n_columns bytes per instance.  Needs TSB_OUT_STATS in the last run. */
+int tsb_result_summary(tsb_batch* batch, double* out, int64_t* rows_total);
+
+/* ---- job: one sweep over several GPUs of one box, from ONE host process ------------------------------------------------
+ * (`tsb_ctx_create(const int* gpu_ids, int n, ...)`; §8(e).)  A job owns a context + plan + batch per GPU
+ * and splits the instance range contiguously: shard g = instances [g*N/G, (g+1)*N/G).  No exchange between GPUs during a
+ * run; every call fans out to the shards from one host thread per GPU.  Parameter arrays and per-instance results are in
+ * JOB order (length n_inst); summaries are reduced on each device first.  gpu_ids may repeat a device (several contexts
+ * on one GPU).  Replaces, for the sweep, what a Go host would do with one analysis.Analysis per goroutine. */
+int tsb_job_create(const int* gpu_ids, int n_gpus, const char* netlist_text, int64_t n_inst, tsb_job** out);
+void tsb_job_destroy(tsb_job* job);
+const char* tsb_job_error(tsb_job* job);
+int tsb_job_num_shards(const tsb_job* job);
+int tsb_job_shard(const tsb_job* job, int g, tsb_batch** batch, int64_t* lo, int64_t* hi);   /* borrowed handle of shard g */
+tsb_plan* tsb_job_plan(const tsb_job* job);                                                  /* structure / column queries */
+int tsb_job_set_param(tsb_job* job, int dev, int param, const double* values /*[n_inst], host*/);
+int tsb_job_set_param_uniform(tsb_job* job, int dev, int param, double value);
+int tsb_job_run_op(tsb_job* job, const tsb_opts* opts);
+int tsb_job_run_tran(tsb_job* job, double tstart, double tstop, double tstep, double tmax, int uic, int out_flags,
+                     int64_t wave_cap_rows, const tsb_opts* opts);
+int tsb_job_run_dc(tsb_job* job, int src_dev, double start, double stop, double inc, int out_flags, const tsb_opts* opts);
+int tsb_job_sync(tsb_job* job);
+int tsb_job_result_status(tsb_job* job, int32_t* status /*[n_inst]*/);
+int tsb_job_result_rows(tsb_job* job, int64_t* rows /*[n_inst]*/);
+int tsb_job_result_stats(tsb_job* job, double* stats /*[4][n_columns][n_inst]*/);
+int tsb_job_result_waveform(tsb_job* job, int64_t inst, double* out, int64_t cap_rows, int64_t* n_rows);
+/* out[3][n_columns] (min, max, sum), stored rows and the five totals of tsb_result_totals, merged over the GPUs. */
+int tsb_job_result_summary(tsb_job* job, double* out, int64_t* rows_total, int64_t totals[5]);
 
 /* ---- operator level: batched factor + solve -------------------------------------------------------
  * Drop-in for the reference's matrix OPERATOR (pkg/matrix/circuit.go:126-150 Solve() = sparse Factor + Solve, fed by

@@ -113,11 +113,15 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
         nan_g, nan_o = np.isnan(wg), np.isnan(wo)
         if not np.array_equal(nan_g, nan_o):
             rep["nan_mismatch"] += 1
+            r, c = np.argwhere(nan_g != nan_o)[0]
+            rep.setdefault("first_class_mismatch", ("nan", i, int(r), int(c), float(wg[r, c]), float(wo[r, c])))
             continue
         # infinities are results too (BJT overflow lanes): same places, same signs
         inf_g, inf_o = np.isinf(wg), np.isinf(wo)
         if not np.array_equal(inf_g, inf_o) or not np.array_equal(np.sign(wg[inf_g]), np.sign(wo[inf_o])):
             rep["inf_mismatch"] += 1
+            r, c = np.argwhere((inf_g != inf_o) | (inf_g & inf_o & (np.sign(wg) != np.sign(wo))))[0]
+            rep.setdefault("first_class_mismatch", ("inf", i, int(r), int(c), float(wg[r, c]), float(wo[r, c])))
             continue
         ok = ~nan_o & np.isfinite(wo) & np.isfinite(wg)
         err = np.abs(wg[ok] - wo[ok])
@@ -131,6 +135,11 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
                 rep["max_abs"] = float(err[j])
                 rep["worst"] = (i, float(wg[ok][j]), float(wo[ok][j]))
     return rep
+
+
+def report_str(rep) -> str:
+    """The whole report on one line (pytest abbreviates dict reprs in assertion messages)."""
+    return "; ".join(f"{k}={v}" for k, v in rep.items() if k != "counter_flips" or v)
 
 
 def report_ok(rep) -> bool:

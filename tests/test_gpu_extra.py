@@ -51,9 +51,9 @@ def _run_both(ctx, name, kind, mode, n=N):
 def test_extra_deck_matches_oracle(ctx, name, kind, mode):
     batch, ores, ana = _run_both(ctx, name, kind, mode)
     rep = PU.compare_waves(batch, ores, N)
-    assert PU.report_ok(rep), rep
+    assert PU.report_ok(rep), PU.report_str(rep)
     # discrete decisions (Newton stop iteration): identical up to the documented near-threshold flips
-    assert rep["counter_mismatch"] <= 2, rep
+    assert rep["counter_mismatch"] <= 2, PU.report_str(rep)
     # failing lanes fail at the same time / sweep value (tran.go:119, dc.go:128)
     st = batch.status()
     cnt = batch.counters()
@@ -79,8 +79,8 @@ def test_nested_sweep_columns_and_layout(ctx):
     assert np.array_equal(r["SWEEP1"], np.repeat(np.arange(n1) * c1 + a1, n2))
     assert np.array_equal(r["SWEEP2"], np.tile(np.arange(n2) * c2 + a2, n1))
     assert np.array_equal(r["V(2)"], r["SWEEP1"]) and np.array_equal(r["V(1)"], r["SWEEP2"])
-    # output characteristics: the drain current grows with VGS at fixed VDS (I(VDS) = -x[branch] = -Id)
-    idrain = -r["I(VDS)"].reshape(n1, n2)
+    # output characteristics: the drain current grows with VGS at fixed VDS (GetSolution's I(VDS) = -x[branch] = +Id)
+    idrain = r["I(VDS)"].reshape(n1, n2)
     assert np.all(np.diff(idrain[:, -1]) >= 0) and idrain[-1, -1] > 1e-4
     # three sources: the reference's error (dc.go:86)
     dc3 = T.NewDCSweep(["VDS", "VGS", "VDS"], [0, 0, 0], [1, 1, 1], [1, 1, 1])

@@ -44,6 +44,10 @@ ABI_SYMBOLS = [
     "tsb_result_totals", "tsb_batch_kernel_source", "tsb_batch_kernel_key", "tsb_ctx_launch_count",
     "tsb_lu_order", "tsb_lu_solve_batched", "tsb_lu_solve_batched_dev", "tsb_batch_stamp_dev", "tsb_batch_set_order",
     "tsb_run_dc2", "tsb_batch_kernel_variant", "tsb_batch_set_param_async", "tsb_ctx_get_stream", "tsb_ctx_wait_event",
+    "tsb_result_fetch_async", "tsb_result_summary", "tsb_job_create", "tsb_job_destroy", "tsb_job_error", "tsb_job_num_shards",
+    "tsb_job_shard", "tsb_job_plan", "tsb_job_set_param", "tsb_job_set_param_uniform", "tsb_job_run_op", "tsb_job_run_tran",
+    "tsb_job_run_dc", "tsb_job_sync", "tsb_job_result_status", "tsb_job_result_rows", "tsb_job_result_stats",
+    "tsb_job_result_waveform", "tsb_job_result_summary",
 ]
 
 
@@ -126,6 +130,25 @@ def lib():
             "tsb_batch_kernel_variant": (i32, [vp, i32, i32, i32]),
             "tsb_batch_stamp_dev": (i32, [vp, i32, dbl, dbl, dbl, u64, u64, P(Opts)]),
             "tsb_batch_set_order": (i32, [vp, P(i64)]),
+            "tsb_result_fetch_async": (i32, [vp, vp, vp, vp, vp]),
+            "tsb_result_summary": (i32, [vp, P(dbl), P(i64)]),
+            "tsb_job_create": (i32, [P(i32), i32, C.c_char_p, i64, P(vp)]),
+            "tsb_job_destroy": (None, [vp]),
+            "tsb_job_error": (C.c_char_p, [vp]),
+            "tsb_job_num_shards": (i32, [vp]),
+            "tsb_job_shard": (i32, [vp, i32, P(vp), P(i64), P(i64)]),
+            "tsb_job_plan": (vp, [vp]),
+            "tsb_job_set_param": (i32, [vp, i32, i32, P(dbl)]),
+            "tsb_job_set_param_uniform": (i32, [vp, i32, i32, dbl]),
+            "tsb_job_run_op": (i32, [vp, P(Opts)]),
+            "tsb_job_run_tran": (i32, [vp, dbl, dbl, dbl, dbl, i32, i32, i64, P(Opts)]),
+            "tsb_job_run_dc": (i32, [vp, i32, dbl, dbl, dbl, i32, P(Opts)]),
+            "tsb_job_sync": (i32, [vp]),
+            "tsb_job_result_status": (i32, [vp, P(C.c_int32)]),
+            "tsb_job_result_rows": (i32, [vp, P(i64)]),
+            "tsb_job_result_stats": (i32, [vp, P(dbl)]),
+            "tsb_job_result_waveform": (i32, [vp, i64, P(dbl), i64, P(i64)]),
+            "tsb_job_result_summary": (i32, [vp, P(dbl), P(i64), P(i64)]),
             "tsb_lu_order": (i32, [i32, P(dbl), P(i32), P(i32)]),
             "tsb_lu_solve_batched": (i32, [vp, i32, P(i32), P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int32), i64, i32]),
             "tsb_lu_solve_batched_dev": (i32, [vp, i32, P(i32), P(i32), u64, u64, u64, u64, i64, i32]),
@@ -251,9 +274,10 @@ class Circuit:
     """The numbered netlist (reference: *circuit.Circuit after SetupDevices).  ctx may be None for
     host-only use (structure queries, kernel source generation)."""
 
-    def __init__(self, ctx: Context | None, handle):
+    def __init__(self, ctx: Context | None, handle, owned: bool = True):
         self.ctx = ctx
         self.h = handle
+        self._owned = owned          # False: a handle borrowed from a Job (the job destroys it)
 
     # -- construction ------------------------------------------------------------------------
     @classmethod
@@ -286,9 +310,9 @@ class Circuit:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self._owned:
                 lib().tsb_plan_destroy(self.h)
-                self.h = None
+            self.h = None
         except Exception:
             pass
 
@@ -528,10 +552,117 @@ class Batch:
         self._check(lib().tsb_result_stats_all(self.h, out.ctypes.data_as(C.POINTER(C.c_double))), "result_stats_all")
         return out
 
+    def fetch_async(self, stats=None, rows=None, status=None, counters=None):
+        """tsb_result_fetch_async: queue device -> host copies of the last run's results into (pinned) numpy arrays; they
+        overlap later launches on the context and are complete after sync()."""
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        self._check(lib().tsb_result_fetch_async(self.h, ptr(stats), ptr(rows), ptr(status), ptr(counters)), "result_fetch_async")
+
+    def summary(self) -> dict:
+        """tsb_result_summary: per-column min / max / sum over all instances, reduced on the device."""
+        _, ncol, _ = self.dims()
+        out = np.zeros((3, ncol))
+        n = C.c_int64()
+        self._check(lib().tsb_result_summary(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)), "result_summary")
+        return dict(min=out[0], max=out[1], sum=out[2], rows=n.value, mean=out[2] / max(1, n.value))
+
     def dev_ptrs(self) -> dict:
         v = [C.c_uint64() for _ in range(5)]
         lib().tsb_result_dev_ptrs(self.h, *[C.byref(x) for x in v])
         return dict(zip(("wave", "stats", "rows", "status", "counters"), [x.value for x in v]))
+
+
+class Job:
+    """One sweep over several GPUs from one process (tsb_job_*): contiguous instance shards, one host thread per GPU,
+    summaries reduced on each device.  gpu_ids may repeat a device ordinal."""
+
+    def __init__(self, gpu_ids, netlist_text: str, n_inst: int):
+        ids = (C.c_int * len(gpu_ids))(*gpu_ids)
+        self.h = C.c_void_p()
+        rc = lib().tsb_job_create(ids, len(gpu_ids), netlist_text.encode(), int(n_inst), C.byref(self.h))
+        if rc != 0:
+            raise TsbError(f"tsb_job_create failed ({rc}): {lib().tsb_last_error(None).decode()}")
+        self.n_inst, self.n_gpus = int(n_inst), len(gpu_ids)
+        self.ckt = Circuit(None, lib().tsb_job_plan(self.h), owned=False)      # borrowed: the job owns it
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise TsbError(f"{what} failed ({rc}): {lib().tsb_job_error(self.h).decode()}")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ckt.h = None
+                lib().tsb_job_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def shards(self):
+        out = []
+        for g in range(lib().tsb_job_num_shards(self.h)):
+            lo, hi = C.c_int64(), C.c_int64()
+            lib().tsb_job_shard(self.h, g, None, C.byref(lo), C.byref(hi))
+            out.append((lo.value, hi.value))
+        return out
+
+    def columns(self, analysis: int):
+        return self.ckt.columns(analysis)
+
+    def set_param(self, dev, param: int, values):
+        d = self.ckt.dev_index(dev) if isinstance(dev, str) else int(dev)
+        if np.isscalar(values):
+            self._check(lib().tsb_job_set_param_uniform(self.h, d, param, float(values)), "job_set_param_uniform")
+            return
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.shape != (self.n_inst,):
+            raise ValueError("values must have shape [n_inst]")
+        self._check(lib().tsb_job_set_param(self.h, d, param, v.ctypes.data_as(C.POINTER(C.c_double))), "job_set_param")
+
+    def run_op(self, opts: Opts | None = None):
+        self._check(lib().tsb_job_run_op(self.h, C.byref(opts) if opts is not None else None), "job_run_op")
+
+    def run_tran(self, tstart, tstop, tstep, tmax=0.0, uic=False, out=OUT_STATS, cap_rows=0, opts: Opts | None = None):
+        self._check(lib().tsb_job_run_tran(self.h, tstart, tstop, tstep, tmax, int(uic), out, cap_rows,
+                                           C.byref(opts) if opts is not None else None), "job_run_tran")
+
+    def run_dc(self, src, start, stop, inc, out=OUT_WAVE, opts: Opts | None = None):
+        d = self.ckt.dev_index(src) if isinstance(src, str) else int(src)
+        self._check(lib().tsb_job_run_dc(self.h, d, start, stop, inc, out, C.byref(opts) if opts is not None else None), "job_run_dc")
+
+    def sync(self):
+        self._check(lib().tsb_job_sync(self.h), "job_sync")
+
+    def status(self) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int32)
+        self._check(lib().tsb_job_result_status(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))), "job_result_status")
+        return out
+
+    def rows(self) -> np.ndarray:
+        out = np.zeros(self.n_inst, dtype=np.int64)
+        self._check(lib().tsb_job_result_rows(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))), "job_result_rows")
+        return out
+
+    def stats(self, analysis: int = AN_TRAN) -> np.ndarray:
+        out = np.zeros((4, len(self.columns(analysis)), self.n_inst))
+        self._check(lib().tsb_job_result_stats(self.h, out.ctypes.data_as(C.POINTER(C.c_double))), "job_result_stats")
+        return out
+
+    def waveform(self, inst: int, cap_rows: int, analysis: int = AN_TRAN) -> np.ndarray:
+        ncol = len(self.columns(analysis))
+        out = np.zeros((max(1, cap_rows), ncol))
+        nr = C.c_int64()
+        self._check(lib().tsb_job_result_waveform(self.h, inst, out.ctypes.data_as(C.POINTER(C.c_double)), cap_rows, C.byref(nr)), "job_result_waveform")
+        return out[: nr.value]
+
+    def summary(self, analysis: int = AN_TRAN) -> dict:
+        ncol = len(self.columns(analysis))
+        out = np.zeros((3, ncol))
+        n = C.c_int64()
+        tot = np.zeros(5, dtype=np.int64)
+        self._check(lib().tsb_job_result_summary(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n),
+                                                 tot.ctypes.data_as(C.POINTER(C.c_int64))), "job_result_summary")
+        return dict(min=out[0], max=out[1], sum=out[2], rows=n.value, mean=out[2] / max(1, n.value), totals=tot)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -255,6 +255,32 @@ __device__ __forceinline__ unsigned long long tsb_ld_acquire(const unsigned long
 __device__ __forceinline__ void tsb_st_release(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// A look at the published count is a relaxed load (no L1 invalidation — ld.acquire costs a CCTL.IVALL, which also evicts
+// the block's spilled registers); only a look that FINDS new entries is followed by the acquire fence.
+__device__ __forceinline__ unsigned long long tsb_ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tsb_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void tsb_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef TSB_TG_PUBLISH_EVERY
+#define TSB_TG_PUBLISH_EVERY 8      // the pilot releases the count every 8 entries (a release is a MEMBAR: ~1 us)
+#endif
+#ifndef TSB_TG_BACKOFF0
+#define TSB_TG_BACKOFF0 4
+#endif
+#ifndef TSB_TG_CACHED
+#define TSB_TG_CACHED 1             // entries are read through L1 (published entries are immutable and a reader only ever
+#endif                              // requests sectors of published entries), optionally prefetched one attempt ahead
+#ifndef TSB_TG_PREFETCH
+#define TSB_TG_PREFETCH 1
+#endif
+#if TSB_TG_CACHED
+#define TSB_TG_LD(p) __ldca(p)
+#else
+#define TSB_TG_LD(p) __ldcg(p)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // An accepted transient step (tran.go:137-151): LoadState, Update, advance time, StoreTimeResult with its
@@ -306,61 +332,68 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     TsbTimeKeyer keyer; keyer.reset();
     int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves
     constexpr int ND = TsbTgLayout<Ckt::NSRC>::ND;
+    constexpr double NO_KEY = -3.0;         // entry of an attempt the pilot rejected before it needed sources and key
     const bool tg_pub = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 1;
     bool tg_use = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0;
-    int tg_k = 0, tg_limit = 0, tg_strays = 0;
+    int tg_k = 0, tg_limit = 0, tg_poll_at = 0, tg_backoff = TSB_TG_BACKOFF0, tg_strays = 0;
     while (time < a.tstop) {
-        double next_time = 0.0, rdt = 0.0, key = 0.0;
+        double next_time = 0.0, rdt = 0.0, key = NO_KEY;
+        const double t_tag = time, dt_tag = dt;
         bool hit = false;
         if (TSB_TGRID && tg_use) {
-            if (tg_k >= tg_limit) {                       // caught up with what this thread knows to be published: look again
-                const unsigned long long pub = tsb_ld_acquire(a.tgrid_pub);
-                tg_limit = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
+            if (tg_k >= tg_limit && tg_k >= tg_poll_at) {
+                // caught up with what this thread knows to be published: look again — seldom (a reader that runs ahead
+                // of the pilot will not find anything for a while: the distance between looks doubles up to 1024 attempts)
+                const unsigned long long pub = tsb_ld_relaxed(a.tgrid_pub);
+                const int lim = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
+                if (lim > tg_k) { tsb_fence_acquire(); tg_limit = lim; tg_backoff = TSB_TG_BACKOFF0; }
+                else { tg_poll_at = tg_k + tg_backoff; tg_backoff = tg_backoff < 1024 ? tg_backoff * 2 : 1024; }
                 if (tg_k >= a.tgrid_cap) tg_use = false;
             }
             if (tg_k < tg_limit) {
                 const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)tg_k * ND);
-                const double2 e0 = __ldcg(e), e1 = __ldcg(e + 1), e2 = __ldcg(e + 2);
+                const double2 e0 = TSB_TG_LD(e), e1 = TSB_TG_LD(e + 1), e2 = TSB_TG_LD(e + 2);
                 hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(time)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt))) == 0;
                 if (hit) {
                     next_time = e1.x; dt = e1.y; rdt = e2.x; key = e2.y;
-                    if (Ckt::SRC_UNIFORM) {
+                    if (Ckt::SRC_UNIFORM && key != NO_KEY) {
 #pragma unroll
                         for (int j = 0; j < Ckt::NSRC; j += 2) {
-                            const double2 sv = __ldcg(e + 3 + j / 2);
+                            const double2 sv = TSB_TG_LD(e + 3 + j / 2);
                             c.SV[j] = sv.x;
                             if (j + 1 < Ckt::NSRC) c.SV[j + 1] = sv.y;
                         }
                     }
                     tg_strays = 0;
+                    if (TSB_TG_PREFETCH && tg_k + 1 < tg_limit) tsb_prefetch_l1(a.tgrid + (long long)(tg_k + 1) * ND);
                 } else if (++tg_strays > 64) tg_use = false;     // this instance has left the pilot's grid for good
             }
         }
         if (!hit) {
-            const double t_tag = time, dt_tag = dt;
             next_time = time + dt;
             if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
             rdt = tsb_rcp_dt(dt);                          // the one division by the time step of this attempt
-            key = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
-            // sources are evaluated at the START of the step (SURVEY Q2); branch-free sine core, general routine only for
-            // an argument beyond its range
-            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
-            if (tg_pub && tg_k < a.tgrid_cap) {
-                double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)tg_k * ND);
-                __stcg(e, make_double2(t_tag, dt_tag));
-                __stcg(e + 1, make_double2(next_time, dt));
-                __stcg(e + 2, make_double2(rdt, key));
-#pragma unroll
-                for (int j = 0; j < Ckt::NSRC; j += 2) __stcg(e + 3 + j / 2, make_double2(c.SV[j], j + 1 < Ckt::NSRC ? c.SV[j + 1] : 0.0));
-                tsb_st_release(a.tgrid_pub, (unsigned long long)tg_k + 1);
-            }
-        } else if (!Ckt::SRC_UNIFORM) {                    // a source parameter varies per instance: the values are this instance's own
-            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
         }
-        ++tg_k;
         __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
         const double lte = c.lte(dt, rdt);
-        if (lte > a.trtol && dt > a.minstep) { dt /= 2; ++n_rej; continue; }
+        const bool reject = lte > a.trtol && dt > a.minstep;
+        if (!reject && (key == NO_KEY || !Ckt::SRC_UNIFORM)) {
+            // sources are evaluated at the START of the step (SURVEY Q2); branch-free sine core, general routine only for
+            // an argument beyond its range.  This is the one place they are computed: the pilot's values come from here.
+            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
+            if (key == NO_KEY) key = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
+        }
+        if (tg_pub && tg_k < a.tgrid_cap) {
+            double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)tg_k * ND);
+            __stcg(e, make_double2(t_tag, dt_tag));
+            __stcg(e + 1, make_double2(next_time, dt));
+            __stcg(e + 2, make_double2(rdt, key));
+#pragma unroll
+            for (int j = 0; j < Ckt::NSRC; j += 2) __stcg(e + 3 + j / 2, make_double2(c.SV[j], j + 1 < Ckt::NSRC ? c.SV[j + 1] : 0.0));
+            if ((tg_k & (TSB_TG_PUBLISH_EVERY - 1)) == TSB_TG_PUBLISH_EVERY - 1) tsb_st_release(a.tgrid_pub, (unsigned long long)tg_k + 1);
+        }
+        ++tg_k;
+        if (reject) { dt /= 2; ++n_rej; continue; }
         const bool solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
         if (!solved) {
             ++n_bad;
@@ -371,6 +404,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
         tsb_accept_step<true>(a, c, sink, time, dt, next_time, lte, keyer, last_key, key);
         ++n_acc;
     }
+    if (tg_pub) tsb_st_release(a.tgrid_pub, (unsigned long long)(tg_k < a.tgrid_cap ? tg_k : a.tgrid_cap));
     n_acc_out += n_acc; n_rej_out += n_rej;
     const int failed = status == TSB_ST_TRAN_FAILED ? 1 : 0;
     // rejected attempts whose solve WAS executed: those rejected for a failing solve (n_bad - failed)

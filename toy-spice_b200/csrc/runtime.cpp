@@ -25,6 +25,7 @@ namespace tsb {
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t launch_totals(const long long* counters, long long n_inst, unsigned long long* totals, int sms, cudaStream_t s);
 cudaError_t launch_fill_i64(long long* p, long long n, long long v, int sms, cudaStream_t s);
+cudaError_t launch_summary(const double* stats, long long n_inst, int ncol, double* partial, int blocks_x, cudaStream_t s);
 cudaError_t launch_lu_warp(const double* A, const double* b, double* x, int* status, long long n_inst, int n, const int* prow,
                            const int* pcol, int strict, int sms, cudaStream_t s);
 }
@@ -76,6 +77,7 @@ struct tsb_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                // tsb_result_fetch_async: device -> host copies beside the next launches
     cudaStream_t pilot_stream = nullptr;               // shared time grid: the pilot launch runs beside the main one
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
@@ -129,6 +131,9 @@ struct tsb_batch {
     unsigned long long* d_tgrid_pub = nullptr;
     int tgrid_cap = 0, tgrid_nd = 0;
     int tgrid_used = 0;                                // the last transient run had a pilot
+    cudaEvent_t ev_run = nullptr, ev_fetch = nullptr;  // tsb_result_fetch_async: run finished / copies finished
+    bool fetch_pending = false;
+    double* d_partial = nullptr;                       // tsb_result_summary: per-block partial results
     std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
     // memo of the last module request: generating the kernel source to derive its cache key costs ~0.3 ms of host
     // time, which is the length of a short launch (the stamp kernel); identical requests skip it
@@ -487,7 +492,7 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     if (!b->d_status) CU(ctx, galloc(b, (void**)&b->d_status, N * sizeof(int)));
     if (!b->d_counters) CU(ctx, galloc(b, (void**)&b->d_counters, 8 * N * sizeof(long long)));
     if (!b->d_scratch) CU(ctx, galloc(b, (void**)&b->d_scratch, (size_t)(p.n() + 1) * N * sizeof(double)));
-    if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 5 * sizeof(unsigned long long)));
+    if (!b->d_totals) CU(ctx, cudaMalloc(&b->d_totals, 6 * sizeof(unsigned long long)));
     if (!b->d_work) CU(ctx, cudaMalloc(&b->d_work, sizeof(unsigned long long)));
     if (n_sweep > 0) {
         gfree(b, b->d_sweep); CU(ctx, galloc(b, (void**)&b->d_sweep, (size_t)n_sweep * sizeof(double)));
@@ -532,6 +537,10 @@ int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& ar
 
 int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     tsb_ctx* ctx = b->ctx;
+    if (b->fetch_pending) {            // results of the previous run are still being copied out: the next run overwrites them
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_fetch, 0));
+        b->fetch_pending = false;
+    }
     memset(&a, 0, sizeof a);
     a.n_inst = b->n_inst;
     a.n_run = b->n_inst;
@@ -708,6 +717,7 @@ static void ctx_release(tsb_ctx* ctx) {
     for (auto& kv : ctx->modules) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->pilot_stream) cudaStreamDestroy(ctx->pilot_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -903,7 +913,9 @@ void tsb_batch_destroy(tsb_batch* b) {
         }
         cudaFree(b->d_uniform);
         cudaFree(b->d_order);
-        cudaFree(b->d_tgrid); cudaFree(b->d_tgrid_pub);
+        cudaFree(b->d_tgrid); cudaFree(b->d_tgrid_pub); cudaFree(b->d_partial);
+        if (b->ev_fetch) { cudaEventSynchronize(b->ev_fetch); cudaEventDestroy(b->ev_fetch); }
+        if (b->ev_run) cudaEventDestroy(b->ev_run);
         free_results(b);
     }
     plan_release(b->plan);
@@ -1187,8 +1199,68 @@ int tsb_batch_set_order(tsb_batch* b, const int64_t* perm) {
 
 int tsb_batch_sync(tsb_batch* b) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    CU(b->ctx, cudaSetDevice(b->ctx->device));
     CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    if (b->ev_fetch) CU(b->ctx, cudaEventSynchronize(b->ev_fetch));
     return guard_check(b);
+}
+
+static int result_totals6(tsb_batch* b, int64_t totals[6]);
+
+// Asynchronous read-back of the last run's per-instance results into (pinned) host buffers; NULL = not wanted.  The
+// copies are queued on a copy stream of the context behind the run, so they overlap whatever is launched next on the
+// context's stream (another batch's run); the buffers are complete after tsb_batch_sync(batch).  A later run on the SAME
+// batch waits for them on the device before it overwrites the results.
+int tsb_result_fetch_async(tsb_batch* b, double* stats, int64_t* rows, int32_t* status, int64_t* counters) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (stats && !b->d_stats) return fail(ctx, TSB_E_INVALID, "the last run did not keep statistics");
+    if (!b->d_rows) return fail(ctx, TSB_E_INVALID, "no run yet");
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!b->ev_run) {
+        CU(ctx, cudaEventCreateWithFlags(&b->ev_run, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&b->ev_fetch, cudaEventDisableTiming));
+    }
+    CU(ctx, cudaEventRecord(b->ev_run, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, b->ev_run, 0));
+    if (stats) CU(ctx, cudaMemcpyAsync(stats, b->d_stats, b->stats_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (rows) CU(ctx, cudaMemcpyAsync(rows, b->d_rows, b->n_inst * sizeof(long long), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (status) CU(ctx, cudaMemcpyAsync(status, b->d_status, b->n_inst * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (counters) CU(ctx, cudaMemcpyAsync(counters, b->d_counters, 8 * b->n_inst * sizeof(long long), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(b->ev_fetch, ctx->copy_stream));
+    b->fetch_pending = true;
+    return TSB_OK;
+}
+
+// Batch-level summary computed on the device: out[3][n_columns] = per column the minimum, the maximum and the sum over
+// ALL instances and stored rows; *rows_total = number of stored rows of the batch (mean = sum / rows_total).  A few KB
+// cross the bus instead of 32 * n_columns bytes per instance.
+int tsb_result_summary(tsb_batch* b, double* out, int64_t* rows_total) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    if (!out) return TSB_E_INVALID;
+    if (!b->d_stats) return fail(ctx, TSB_E_INVALID, "the last run did not keep statistics (TSB_OUT_STATS)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int bx = 64, ncol = b->ncol;
+    if (!b->d_partial) CU(ctx, cudaMalloc(&b->d_partial, (size_t)64 * 64 * 3 * sizeof(double) + 64));
+    if (ncol > 64) return fail(ctx, TSB_E_UNSUPPORTED, "tsb_result_summary: more than 64 result columns");
+    CU(ctx, launch_summary(b->d_stats, b->n_inst, ncol, b->d_partial, bx, ctx->stream));
+    ++ctx->launches;
+    std::vector<double> h((size_t)ncol * bx * 3);
+    CU(ctx, cudaMemcpyAsync(h.data(), b->d_partial, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t totals[6];
+    if ((rc = result_totals6(b, totals)) != TSB_OK) return rc;             // synchronises the stream
+    for (int c = 0; c < ncol; ++c) {
+        double mn = HUGE_VAL, mx = -HUGE_VAL, sm = 0.0;
+        for (int k = 0; k < bx; ++k) {
+            const double* p = &h[((size_t)c * bx + k) * 3];
+            mn = fmin(mn, p[0]); mx = fmax(mx, p[1]); sm += p[2];
+        }
+        out[0 * ncol + c] = mn; out[1 * ncol + c] = mx; out[2 * ncol + c] = sm;
+    }
+    if (rows_total) *rows_total = totals[5];          // counters[7]: rows of the result series the statistics run over
+    return TSB_OK;
 }
 
 // ---- results -----------------------------------------------------------------------------------
@@ -1244,18 +1316,25 @@ int tsb_result_waveform(tsb_batch* b, int64_t inst, double* out, int64_t cap_row
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return TSB_OK;
 }
-int tsb_result_totals(tsb_batch* b, int64_t totals[5]) {
+static int result_totals6(tsb_batch* b, int64_t totals[6]) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
     if (!totals || !b->d_counters) return TSB_E_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMemsetAsync(b->d_totals, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    CU(ctx, cudaMemsetAsync(b->d_totals, 0, 6 * sizeof(unsigned long long), ctx->stream));
     CU(ctx, launch_totals(b->d_counters, b->n_inst, b->d_totals, ctx->sms, ctx->stream));
     ++ctx->launches;
-    unsigned long long h[5];
+    unsigned long long h[6];
     CU(ctx, cudaMemcpyAsync(h, b->d_totals, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < 5; ++k) totals[k] = (int64_t)h[k];
+    for (int k = 0; k < 6; ++k) totals[k] = (int64_t)h[k];
+    return TSB_OK;
+}
+int tsb_result_totals(tsb_batch* b, int64_t totals[5]) {
+    int64_t t[6];
+    int rc = result_totals6(b, t);
+    if (rc != TSB_OK) return rc;
+    for (int k = 0; k < 5; ++k) totals[k] = t[k];
     return TSB_OK;
 }
 
