@@ -1,27 +1,34 @@
 #!/usr/bin/env python
 """bench.py — circuit-timesteps/sec of the batched FP64 transient hot path (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): rc.cir + rlc.cir linear transient, 2^20-instance R/L/C parameter
-sweep per GPU (nominal * LogUniform[0.5, 2], PCG64 seed 1234), summary-statistics
-output (min / max / sum / last per signal + row counts; full rlc waveforms for 2^20 instances would be
-~640 GB).  One "step" = one pass of the hot path over that batch: one transient launch per deck.
+Headline workload (BASELINE.json configs[1]): rc.cir + rlc.cir linear transient, 2^20-instance R/L/C parameter
+sweep per GPU (nominal * LogUniform[0.5, 2], PCG64 seed 1234), summary-statistics output
+(min / max / sum / last per signal + row counts; full rlc waveforms for 2^20 instances would be ~640 GB).
+One "step" = one pass of the hot path over that batch: one transient launch per deck.
 
   value     whole-job accepted transient steps / s with parameters already resident in HBM
-  e2e       the same through the public API with HOST buffers: per step the parameter arrays are
-            copied H2D from pinned memory and the statistics / row counts / status are read back
-  roofline  the dominant launch (rlc transient): algorithmic FP64 flops / CUDA-event time vs the
-            DFMA-chain peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+  e2e       the same through the public API with HOST buffers: every step the parameter arrays are copied H2D from
+            pinned memory and every instance's statistics / row count / status are read back into pinned memory
+            (tsb_result_fetch_async: the read-back of one launch overlaps the next launch)
+  roofline  the dominant launch (rlc transient): algorithmic FP64 flops / CUDA-event time vs the DFMA-chain peak
+            measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+  configs   one entry per BASELINE.json config (rr plumbing; rc + rlc; diode1-5; bjt1-3 + mosfet1; transformer1-3
+            with 2^24 instances split over the N GPUs): ms per launch, circuit-timesteps/s, executed solves, FP64
+            roofline fraction of an executed-flop model, lane utilisation
+  strong    transformer1.cir, 2^24 instances IN TOTAL over the N GPUs (strong scaling)
   cpu_baseline / --impl reference
-            the CPU restatement of the reference solver (oracle/, `kind: port` — the Go reference
-            cannot be built here), one task per instance on all host threads, bounded sample.
+            the CPU restatement of the reference solver (oracle/, `kind: port` — the Go reference cannot be built
+            here), one task per instance on all host threads, bounded sample.  The reference arm imports nothing of
+            the product (front-end: oracle/netlist.py; draws: the workload module loaded by file path).
 
-Launch: `python bench.py --gpus N --steps K --warmup W`; for N > 1 under torchrun (one rank per GPU,
-instances sharded by rank, no collective on the data path; totals all-reduced at the end).
+Launch: `python bench.py --gpus N --steps K --warmup W`; for N > 1 under torchrun (one rank per GPU, instances
+sharded by rank, no collective on the data path; totals all-reduced at the end).
 """
 from __future__ import annotations
 
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -37,38 +44,47 @@ sys.path.insert(0, ROOT)
 DECKS = ("rc", "rlc")
 
 
+def load_workloads():
+    """toy-spice_b200/workloads.py (decks = input data, sweep definitions) loaded BY FILE PATH: no import of the
+    product package, no CUDA library in the process — what the reference arm needs."""
+    spec = importlib.util.spec_from_file_location("tsb_workloads", os.path.join(ROOT, "toy-spice_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 # --------------------------------------------------------------------------------------------
-# Algorithmic FP64 work per Newton solve, stated in DESIGN.md §Roofline.
+# Algorithmic FP64 work per Newton solve (SURVEY.md §8(d) / a11), stated in DESIGN.md §6.1.
 def f_lu_dense(n: int) -> int:
     """Dense LU + triangular solves as the reference performs them (structure is dense n x n,
     SURVEY Q16): sum_k [1 + (n-k) + 2(n-k)^2] + n + 2n(n-1)."""
     return sum(1 + (n - k) + 2 * (n - k) ** 2 for k in range(1, n + 1)) + n + 2 * n * (n - 1)
 
 
-STAMP_FLOPS = {0: 5, 1: 8, 2: 9, 3: 5, 4: 2, 5: 30, 6: 90, 7: 80, 8: 12, 9: 9}   # per device kind (adds into A/b + model arithmetic)
+# per device kind: stamp arithmetic incl. the transcendental functions at ~40 flop per exp / log / pow and ~20 per
+# sqrt (SURVEY §8(d): "nonlinear add ~40-60 flops per exp/pow"): R 5, C 8, L 9, V 5 (+ sin), I 2, D 15 + 1 exp,
+# Q 60 + 2 exp + 1 pow, M 60 + 2 sqrt (Level 1), K 12 per pair, core L 9
+STAMP_FLOPS = {0: 5, 1: 8, 2: 9, 3: 5, 4: 2, 5: 55, 6: 180, 7: 100, 8: 12, 9: 9}
 
 
-def ncu_traffic(deck: str, n: int, mode: str):
-    """DRAM bytes per launch of this kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{deck}:{n}:{mode}")
-    except Exception:
-        return None
-
-
-def ncu_counters(deck: str, n: int, mode: str):
-    """FP64-pipe / issue utilisation of this kernel from the committed ncu capture, or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"ncu:{deck}:{n}:{mode}")
-    except Exception:
-        return None
-
-
-def flops_per_solve(ckt) -> dict:
-    n = ckt.n
-    stamp = sum(STAMP_FLOPS[d["kind"]] for d in ckt.devices())
+def flops_per_solve(devs, n) -> dict:
+    stamp = sum(STAMP_FLOPS[d["kind"]] for d in devs)
     conv = 5 * n
     return dict(n=n, lu=f_lu_dense(n), stamp=stamp, conv=conv, total=f_lu_dense(n) + stamp + conv)
+
+
+def ncu_json(key: str):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
 # --------------------------------------------------------------------------------------------
@@ -123,21 +139,22 @@ def host_threads() -> int:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_sample(T, O, W, target_seconds: float, threads: int):
-    """Time the CPU oracle on a bounded sample of the SAME workload (same decks, same draws)."""
+def cpu_sample(O, W, target_seconds: float, threads: int):
+    """Time the CPU oracle on a bounded sample of the SAME workload (same decks, same draws).  Device table from the
+    oracle's own front-end (oracle/netlist.py): nothing of the product is imported here."""
     per_deck = {}
     total_steps, total_time = 0, 0.0
     desc = []
     for name in DECKS:
-        oc = O.OracleCircuit(T.BUNDLED[name])
-        ckt = T.Circuit.from_netlist(T.BUNDLED[name])
+        oc = O.OracleCircuit(W.BUNDLED[name])
+        devs = [dict(kind=r.kind, name=r.name, p=list(r.p)) for r in oc.plan.devices]
         probe_n = max(threads, 8)
-        ov = W.sweep_draws(ckt.devices(), probe_n, W.sweep_seed(name))
+        ov = W.sweep_draws(devs, probe_n, W.sweep_seed(name))
         t0 = time.time()
         oc.run(probe_n, overrides=ov, threads=threads, want_wave=False, want_stats=True)
         rate = probe_n / max(time.time() - t0, 1e-6)
         n = int(min(1 << 16, max(probe_n, rate * target_seconds / len(DECKS))))
-        ov = W.sweep_draws(ckt.devices(), n, W.sweep_seed(name))
+        ov = W.sweep_draws(devs, n, W.sweep_seed(name))
         t0 = time.time()
         res = oc.run(n, overrides=ov, threads=threads, want_wave=False, want_stats=True)
         dt = time.time() - t0
@@ -150,6 +167,16 @@ def cpu_sample(T, O, W, target_seconds: float, threads: int):
     return total_steps / total_time, "; ".join(desc), per_deck
 
 
+def headline_config(n, world, strict_fp):
+    return {"workload": f"rc.cir + rlc.cir transient, {n}-instance R/L/C sweep per GPU (LogUniform[0.5,2], PCG64 seed 1234), "
+                        "summary-statistics output", "instances_per_deck_per_gpu": n,
+            "parallelism": f"instances sharded over {world} GPU(s), no collective", "l2": "flushed between timed iterations (256 MB write)",
+            "strict_fp": strict_fp,
+            "excluded": "one-time set-up outside the timed region: plan + batch creation (netlist front-end, symbolic pass), loading the "
+                        "pre-built cubins (NVRTC on a cache miss), the launch-bounds timing pass of a batch's first run, the shared-time-grid "
+                        "pilot of a batch's first run (later runs with unchanged analysis arguments reuse its table), pinned-buffer allocation"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Go solver cannot be
     built in this image (no Go toolchain, un-vendored sparse module), so this is the C++ restatement
@@ -157,26 +184,26 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    T = importlib.import_module("toy-spice_b200")
-    W = importlib.import_module("toy-spice_b200.workloads")
+    W = load_workloads()
     from oracle import oracle as O
     threads = host_threads()
     for _ in range(args.warmup):
-        cpu_sample(T, O, W, 1.0, threads)
+        cpu_sample(O, W, 1.0, threads)
     vals, t_all, sample = [], 0.0, ""
     for _ in range(args.steps):
         t0 = time.time()
-        v, sample, _ = cpu_sample(T, O, W, max(2.0, 20.0 / max(1, args.steps)), threads)
+        v, sample, _ = cpu_sample(O, W, max(2.0, 20.0 / max(1, args.steps)), threads)
         t_all += time.time() - t0
         vals.append(v)
     value = float(np.mean(vals))
+    cfg = headline_config(args.instances, args.gpus, args.strict_fp)
+    cfg["l2"] = "n/a (CPU)"
+    cfg["reference_arm"] = "bounded CPU sample of the same decks and draws, per-instance rate"
     line = {
         "metric": "circuit-timesteps/sec (batched FP64 transient)", "value": value, "unit": "circuit-timesteps/s",
         "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "rc.cir + rlc.cir transient, R/L/C sweep (LogUniform[0.5,2], PCG64 seed 1234), bounded CPU sample",
-                   "l2": "n/a (CPU)"},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "circuit-timesteps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,6 +221,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=1 << 20, help="instances per deck per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config entries and the strong-scaling entry")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="scale the instance counts of the `configs` / `strong` entries")
     ap.add_argument("--strict-fp", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -212,11 +241,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     T = importlib.import_module("toy-spice_b200")
     W = importlib.import_module("toy-spice_b200.workloads")
+    S = importlib.import_module("toy-spice_b200.sharding")
     ctx = T.Context(local)
     stream = torch.cuda.Stream(device=local)
     ctx.set_stream(stream.cuda_stream)
     opts = T.default_opts(strict_fp=args.strict_fp)
     n = args.instances
+    dev_name = f"cuda:{local}"
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
 
     # ---- workload: decks, per-rank parameter draws (rank r owns its own instance range) ---------
     decks = []
@@ -226,44 +260,50 @@ def main():
         card = ckt.analysis_card()
         ov = W.sweep_draws(ckt.devices(), n, W.sweep_seed(name) + 7919 * rank)
         host = {k: torch.from_numpy(v).pin_memory() for k, v in ov.items()}
-        dev = {k: v.to(f"cuda:{local}", non_blocking=True) for k, v in host.items()}
+        dev = {k: v.to(dev_name, non_blocking=True) for k, v in host.items()}
         b_res = ckt.batch(n)       # parameters resident in HBM (borrowed torch tensors)
         for (d, p), v in dev.items():
             b_res.set_param(d, p, v)
-        b_e2e = ckt.batch(n)       # parameters copied from pinned host memory every step
-        for (d, p), v in host.items():
-            b_e2e.set_param(d, p, v.numpy())
+        ncol = len(ckt.columns(T.AN_TRAN))
+        # end-to-end: two batches per deck, used alternately, so that the read-back of step i overlaps step i + 1
+        e2e = []
+        for _ in range(2):
+            b = ckt.batch(n)
+            for (d, p), v in host.items():
+                b.set_param(d, p, v.numpy(), zero_copy=True)
+            e2e.append(dict(batch=b, stats=pinned((4, ncol, n), torch.float64), rows=pinned((n,), torch.int64), status=pinned((n,), torch.int32)))
         h2d_bytes += sum(v.numel() * 8 for v in host.values())
-        decks.append(dict(name=name, ckt=ckt, card=card, host=host, dev=dev, b_res=b_res, b_e2e=b_e2e,
-                          flops=flops_per_solve(ckt), ncol=len(ckt.columns(T.AN_TRAN))))
+        decks.append(dict(name=name, ckt=ckt, card=card, host=host, dev=dev, b_res=b_res, e2e=e2e,
+                          flops=flops_per_solve(ckt.devices(), ckt.n), ncol=ncol))
     torch.cuda.synchronize()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=f"cuda:{local}")   # 256 MB > 126 MB L2
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev_name)   # 256 MB > 126 MB L2
 
-    def launch_deck(d, batch):
+    def launch_deck(d, batch, out=None):
         c = d["card"]
-        batch.run_tran(c["tstart"], c["tstop"], c["tstep"], c["tmax"], c["uic"], out=T.OUT_STATS, opts=opts)
+        batch.run_tran(c["tstart"], c["tstop"], c["tstep"], c["tmax"], c["uic"], out=T.OUT_STATS if out is None else out, opts=opts)
 
     def step_resident():
         for d in decks:
             launch_deck(d, d["b_res"])
 
     d2h_bytes = sum(n * (4 * d["ncol"] * 8 + 8 + 4) for d in decks)
-    host_out = {d["name"]: dict(stats=torch.empty((4, d["ncol"], n), dtype=torch.float64).pin_memory().numpy(),
-                                rows=torch.empty(n, dtype=torch.int64).pin_memory().numpy(),
-                                status=torch.empty(n, dtype=torch.int32).pin_memory().numpy()) for d in decks}
 
-    def step_e2e():
+    def step_e2e(i):
+        """Host buffers in, host buffers out: parameters H2D from pinned memory (DMA on the launch stream), launch, and
+        the read-back of every instance's statistics / rows / status queued behind the launch on the copy stream."""
         for d in decks:
-            b = d["b_e2e"]
+            e = d["e2e"][i & 1]
+            b = e["batch"]
+            b.sync()                                   # the buffers of step i - 2 are complete (results consumed by the host here)
             for (dv, p), v in d["host"].items():
-                b.set_param(dv, p, v.numpy())          # cudaMemcpyAsync H2D from pinned memory
+                b.set_param(dv, p, v.numpy(), zero_copy=True)
             launch_deck(d, b)
+            b.fetch_async(e["stats"], e["rows"], e["status"])
+
+    def e2e_drain():
         for d in decks:
-            b = d["b_e2e"]
-            o = host_out[d["name"]]
-            b.stats_all(o["stats"])
-            b.rows(o["rows"])
-            b.status(o["status"])
+            for e in d["e2e"]:
+                e["batch"].sync()
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,7 +315,7 @@ def main():
     fp64_peak = ctx.measure_fp64_peak()
 
     # ---- warm-up (also loads / compiles the specialised kernels) --------------------------------
-    step_resident()             # priming pass (not one of the W warm-up steps): loads the kernels, runs the launch-bounds autotuner
+    step_resident()             # priming pass (not one of the W warm-up steps): loads the kernels, runs the launch-bounds autotuner, the pilot
     for _ in range(max(args.warmup, 3 if args.warmup > 0 else 0)):
         step_resident()
     torch.cuda.synchronize()
@@ -310,23 +350,26 @@ def main():
     solves_local = int(sum(t[2] + t[3] for t in totals.values()))     # as the reference counts them
     exec_local = int(sum(t[4] for t in totals.values()))              # factor+solve passes actually executed
     t_local = sum(ms_steps) * 1e-3
-    S = importlib.import_module("toy-spice_b200.sharding")
-    t_job, (acc_job, solves_job, exec_job) = S.reduce_job(t_local, [acc_local, solves_local, exec_local], device=f"cuda:{local}")
+    t_job, (acc_job, solves_job, exec_job) = S.reduce_job(t_local, [acc_local, solves_local, exec_local], device=dev_name)
     value = acc_job * args.steps / t_job if t_job > 0 else 0.0
 
     # ---- timed: end to end through the public API with host buffers -----------------------------
-    step_e2e()
+    step_e2e(0); step_e2e(1)
+    e2e_drain()
     barrier()
     t0 = time.time()
-    for _ in range(args.steps):
-        step_e2e()
+    for i in range(args.steps):
+        step_e2e(i)
+    e2e_drain()
     torch.cuda.synchronize()
     t_e2e_local = time.time() - t0
-    te = torch.tensor([t_e2e_local], dtype=torch.float64, device=f"cuda:{local}")
+    te = torch.tensor([t_e2e_local], dtype=torch.float64, device=dev_name)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = acc_job * args.steps / float(te[0])
-    bad_status = int(sum((host_out[d["name"]]["status"] != 0).sum() for d in decks))
+    bad_status = int(sum((e["status"] != 0).sum() for d in decks for e in d["e2e"][:1]))
+    # the read-back really is this step's result: the e2e statistics equal the resident run's (same draws)
+    e2e_ok = all(np.array_equal(d["e2e"][0]["rows"], d["b_res"].rows()) for d in decks)
 
     # ---- roofline of the dominant launch (rlc transient) -----------------------------------------
     dom = decks[-1]
@@ -337,20 +380,32 @@ def main():
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": "tsb_optran (rlc.cir)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_traffic(dom["name"], n, "stats"),
+        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_json(f"{dom['name']}:{n}:stats"),
         "peak_source": "DFMA-chain microbenchmark measured in this run (tsb_ctx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_solve": dom["flops"], "executed_solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
-        # `achieved` / `frac` count only the factor+solve passes this kernel EXECUTES (the conservative reading).
-        # SURVEY §8(d)'s per-unit figure is iters*(F_LU + F_stamp + F_conv) per circuit-timestep with iters = 2 for a
-        # linear circuit, i.e. the work of the reference algorithm, whose second solve and LTE-rejected solves this
-        # kernel proves redundant and does not run: reported beside it, not instead of it.
+        # `achieved` / `frac` count only the factor+solve passes this kernel EXECUTES (the conservative reading), at
+        # SURVEY §8(d)'s per-solve figure F_LU(n, dense as the reference factors it) + F_stamp + F_conv.  The work of the
+        # reference algorithm (two solves per step and the LTE-rejected solves, which this kernel proves redundant and
+        # does not run) is reported beside it, not instead of it.
         "reference_algorithm": {
             "flops_per_launch": int(dom_tot[2]) * dom["flops"]["total"], "solves_per_launch": int(dom_tot[2]),
             "achieved": int(dom_tot[2]) * dom["flops"]["total"] / (dom_ms * 1e-3) / 1e12,
             "frac": (int(dom_tot[2]) * dom["flops"]["total"] / (dom_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None},
-        "ncu": ncu_counters(dom["name"], n, "stats"),
+        "ncu": ncu_json(f"ncu:{dom['name']}:{n}:stats"),
         "algorithmic_hbm_bytes_per_launch": n * (8 * 3 + 4 * dom["ncol"] * 8 + 8 + 4 + 6 * 8),
     }
+
+    def timed_launches(fn, reps=3, warm=1):
+        ms = []
+        for i in range(warm + reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            stream.synchronize()
+            if i >= warm:
+                ms.append(e0.elapsed_time(e1))
+        return ms
 
     # ---- the HBM-bound regime of the same kernel: rc.cir with every stored row materialised --------------
     # (8*O bytes per stored row; not part of `value`, reported beside the FP64 roofline)
@@ -358,30 +413,16 @@ def main():
     try:
         rc = decks[0]
         c = rc["card"]
-        cap = 320
         bw = rc["ckt"].batch(n)
         for (d, p), v in rc["dev"].items():
             bw.set_param(d, p, v)
-        ms_w = []
-        for i in range(4):
-            flush.zero_()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            bw.run_tran(c["tstart"], c["tstop"], c["tstep"], c["tmax"], c["uic"], out=T.OUT_WAVE, cap_rows=cap, opts=opts)
-            e1.record(stream)
-            stream.synchronize()
-            if i > 0:
-                ms_w.append(e0.elapsed_time(e1))
+        ms_w = timed_launches(lambda: bw.run_tran(c["tstart"], c["tstop"], c["tstep"], c["tmax"], c["uic"], out=T.OUT_WAVE, cap_rows=320, opts=opts))
         rows_total = int(bw.totals()[0])                    # rc stores every accepted step (305 rows per instance)
         alg_bytes = rows_total * rc["ncol"] * 8 + n * (2 * 8 + 8 + 4 + 8 * 8)
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        if os.path.exists(peaks_path):
-            hbm_peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        hp, src = hbm_peak()
         ach = alg_bytes / (min(ms_w) * 1e-3) / 1e9
-        roofline_hbm = {"bound": "hbm", "kernel": "tsb_optran (rc.cir, TSB_OUT_WAVE)", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("rc", n, "wave"), "peak_source": src,
+        roofline_hbm = {"bound": "hbm", "kernel": "tsb_optran (rc.cir, TSB_OUT_WAVE)", "achieved": ach, "peak": hp,
+                        "unit": "GB/s", "frac": ach / hp, "traffic": ncu_json(f"rc:{n}:wave"), "peak_source": src,
                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": min(ms_w),
                         "circuit_timesteps_per_sec": rows_total / (min(ms_w) * 1e-3)}
         del bw
@@ -389,8 +430,6 @@ def main():
         roofline_hbm = {"error": str(ex)[:200]}
 
     # ---- the operator-level device-stamp kernel (HBM-write-bound: (n^2 + n) * 8 bytes per instance) -----------------
-    # rlc.cir transient companion stamps of 2^22 instances, coalesced through shared memory (tsb_stamp_staged); not part
-    # of `value` (the analysis kernels never materialise the matrix), reported as the stamp stage's own roofline
     roofline_stamp = None
     try:
         ns = 1 << 22
@@ -400,26 +439,13 @@ def main():
         bs = rl["ckt"].batch(ns)
         keep = []
         for (d, p), v in ovs.items():
-            t = torch.from_numpy(v).to(f"cuda:{local}"); keep.append(t)
+            t = torch.from_numpy(v).to(dev_name); keep.append(t)
             bs.set_param(d, p, t)
-        dA = torch.empty((ns, nn, nn), dtype=torch.float64, device=f"cuda:{local}")
-        dB = torch.empty((ns, nn), dtype=torch.float64, device=f"cuda:{local}")
-        ms_s = []
-        for i in range(5):
-            flush.zero_()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            bs.stamp_dev(T.AN_TRAN, 1e-4, 1e-6, 0.0, dA.data_ptr(), dB.data_ptr(), opts=opts)
-            e1.record(stream)
-            stream.synchronize()
-            if i > 0:
-                ms_s.append(e0.elapsed_time(e1))
+        dA = torch.empty((ns, nn, nn), dtype=torch.float64, device=dev_name)
+        dB = torch.empty((ns, nn), dtype=torch.float64, device=dev_name)
+        ms_s = timed_launches(lambda: bs.stamp_dev(T.AN_TRAN, 1e-4, 1e-6, 0.0, dA.data_ptr(), dB.data_ptr(), opts=opts), reps=4)
         sbytes = ns * ((nn * nn + nn) * 8 + len(ovs) * 8)
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hp, hsrc = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        if os.path.exists(peaks_path):
-            hp, hsrc = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        hp, hsrc = hbm_peak()
         ach_s = sbytes / (min(ms_s) * 1e-3) / 1e9
         roofline_stamp = {"bound": "hbm", "kernel": "tsb_stamp_staged (rlc.cir transient stamps, operator level)", "achieved": ach_s, "peak": hp,
                           "unit": "GB/s", "frac": ach_s / hp, "traffic": None, "peak_source": hsrc, "algorithmic_bytes_per_launch": sbytes,
@@ -428,12 +454,117 @@ def main():
     except Exception as ex:
         roofline_stamp = {"error": str(ex)[:200]}
 
+    # ---- one entry per BASELINE.json config ------------------------------------------------------------------------
+    def lane_util(cnt_exec):
+        """Share of the lane-iterations of a warp-synchronous run that do work: sum of the executed solves over 32 x the
+        slowest lane of every warp (from per-instance totals: an upper bound, waits inside a step are not visible)."""
+        m = len(cnt_exec) // 32 * 32
+        if m == 0:
+            return None
+        w = cnt_exec[:m].reshape(-1, 32)
+        den = float(32 * w.max(axis=1).sum())
+        return float(w.sum()) / den if den > 0 else None
+
+    def measure_deck(name, n_inst, text=None, analysis=None, tran=None, seed=None, reps=2, strict=None):
+        text = T.BUNDLED[name] if text is None else text
+        ckt = T.Circuit.from_netlist(text, ctx)
+        card = ckt.analysis_card()
+        if tran:
+            card = dict(card, **tran, analysis=T.AN_TRAN)
+        an = card["analysis"] if analysis is None else analysis
+        lo, hi = S.shard_range(n_inst, rank, world) if seed == "global" else (0, n_inst)
+        ov = W.sweep_draws(ckt.devices(), n_inst, W.sweep_seed(name) + (0 if seed == "global" else 7919 * rank))
+        b = ckt.batch(hi - lo)
+        keep = []
+        for (d, p), v in ov.items():
+            t = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).to(dev_name); keep.append(t)
+            b.set_param(d, p, t)
+        del ov
+        o = T.default_opts(strict_fp=args.strict_fp if strict is None else strict)
+        if an == T.AN_TRAN:
+            run = lambda: b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=o)
+        elif an == T.AN_OP:
+            run = lambda: b.run_op(o)
+        else:
+            run = lambda: b.run_dc(card["dc_src_dev"], card["dc_start"], card["dc_stop"], card["dc_inc"], out=T.OUT_STATS, opts=o)
+        ms = min(timed_launches(run, reps=reps))
+        tot = b.totals()
+        nl = ckt_has_nonlinear(ckt)
+        cnt = b.counters() if (nl or an != T.AN_TRAN) else None               # per-instance counters only where they are looked at
+        st = b.status()
+        fl = flops_per_solve(ckt.devices(), ckt.n)
+        steps = int(tot[0]) if an == T.AN_TRAN else int(cnt[7].sum())        # accepted steps / stored sweep points / 1 per OP
+        tf = int(tot[4]) * fl["total"] / (ms * 1e-3) / 1e12
+        ent = {"deck": name, "analysis": {T.AN_OP: "op", T.AN_TRAN: "tran", T.AN_DC: "dc"}[an], "instances": hi - lo, "n": ckt.n,
+               "ms_per_launch": ms, "steps": steps, "circuit_timesteps_per_sec": steps / (ms * 1e-3), "executed_solves": int(tot[4]),
+               "flops_per_solve": fl["total"], "tflops": tf, "frac": tf / fp64_peak if fp64_peak else None,
+               "lane_util": lane_util(cnt[6]) if nl else 1.0,
+               "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+               "nan_instances": int(np.isnan(b.stats_all()[3]).any(axis=0).sum()) if hi - lo <= (1 << 22) else None}
+        del b, keep
+        return ent
+
+    def ckt_has_nonlinear(ckt):
+        return any(d["kind"] in (T.api.K_D, T.api.K_Q, T.api.K_M) for d in ckt.devices())
+
+    configs, strong = None, None
+    if not args.no_configs:
+        sc = args.config_scale
+        n20, n22, n24 = max(1024, int((1 << 20) * sc)), max(1024, int((1 << 22) * sc)), max(1024 * world, int((1 << 24) * sc))
+        tran150 = dict(tstart=0.0, tstop=150e-6, tstep=1e-6, tmax=0.0, uic=False)
+        configs = []
+        try:
+            # [0] rr.cir operating point, batch = 1: plumbing (exact known answer)
+            ckt = T.Circuit.from_netlist(T.BUNDLED["rr"], ctx)
+            op = T.NewOP(); op.Setup(ckt); op.Execute(); r = op.GetResults()
+            configs.append({"config": "configs[0] rr.cir DC operating point, batch=1", "V(2)": float(r["V(2)"][0]), "I(Vin)": float(r["I(Vin)"][0]),
+                            "exact": bool(r["V(1)"][0] == 5.0 and r["V(2)"][0] == 2.5)})
+            # [1] the headline decks
+            configs.append({"config": "configs[1] rc.cir + rlc.cir linear transient, R/L/C sweep",
+                            "decks": [{"deck": d["name"], "analysis": "tran", "instances": n, "n": d["ckt"].n,
+                                       "ms_per_launch": float(np.mean([ms_steps[i] - ms_dom[i] for i in range(len(ms_dom))])) if d is decks[0] else dom_ms,
+                                       "steps": int(totals[d["name"]][0]), "executed_solves": int(totals[d["name"]][4]),
+                                       "flops_per_solve": d["flops"]["total"], "lane_util": 1.0} for d in decks]})
+            for e in configs[-1]["decks"]:
+                e["circuit_timesteps_per_sec"] = e["steps"] / (e["ms_per_launch"] * 1e-3)
+                e["tflops"] = e["executed_solves"] * e["flops_per_solve"] / (e["ms_per_launch"] * 1e-3) / 1e12
+                e["frac"] = e["tflops"] / fp64_peak if fp64_peak else None
+            # [2] diode1-5: Monte Carlo over Is / n
+            configs.append({"config": "configs[2] diode1-5.cir, Monte Carlo over Is / n (Newton with per-instance convergence masks)",
+                            "decks": [measure_deck(nm, n20) for nm in ("diode2", "diode4", "diode1", "diode5", "diode3")]})
+            # [3] bjt1-3 + mosfet1: device-parameter sweep (bjt1 / bjt3 with the supplied .tran 1u 150u, SURVEY §8(d)(4))
+            configs.append({"config": "configs[3] bjt1-3.cir + mosfet1.cir nonlinear transient, device-parameter sweep",
+                            "decks": [measure_deck("mosfet1", n22), measure_deck("bjt2", n22), measure_deck("bjt1", n22, tran=tran150),
+                                      measure_deck("bjt3", n22, tran=tran150)]})
+            # [4] transformer1-3: coupled inductors, 2^24 instances over the N GPUs (each rank its contiguous shard of ONE global draw)
+            configs.append({"config": f"configs[4] transformer1-3.cir coupled-inductor transient, {n24} instances over {world} GPU(s)",
+                            "decks": [measure_deck(nm, n24, seed="global", reps=1) for nm in ("transformer3", "transformer1", "transformer2")]})
+        except Exception as ex:
+            configs.append({"error": repr(ex)[:300]})
+        # multi-GPU: per-deck time = max over ranks, work = sum over ranks
+        if world > 1:
+            for cfg in configs:
+                for e in cfg.get("decks", []):
+                    t = torch.tensor([e["ms_per_launch"]], dtype=torch.float64, device=dev_name)
+                    w = torch.tensor([float(e["steps"]), float(e["executed_solves"]), float(e["instances"])], dtype=torch.float64, device=dev_name)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(w, op=dist.ReduceOp.SUM)
+                    e["ms_per_launch"], e["steps"], e["executed_solves"], e["instances"] = float(t[0]), int(w[0]), int(w[1]), int(w[2])
+                    e["circuit_timesteps_per_sec"] = e["steps"] / (e["ms_per_launch"] * 1e-3)
+                    e["tflops"] = e["executed_solves"] * e["flops_per_solve"] / (e["ms_per_launch"] * 1e-3) / 1e12
+                    e["frac"] = e["tflops"] / (fp64_peak * world) if fp64_peak else None
+        t1 = [e for cfg in configs for e in cfg.get("decks", []) if e.get("deck") == "transformer1"]
+        if t1:
+            e = t1[0]
+            strong = {"workload": f"transformer1.cir transient, {e['instances']} instances in total over {world} GPU(s) (strong scaling: "
+                                  "contiguous shards of one global draw, seed 4567)", "n_gpus": world, "ms": e["ms_per_launch"],
+                      "circuit_timesteps_per_sec": e["circuit_timesteps_per_sec"], "scaling": "strong"}
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         threads = host_threads()
-        v, sample, _ = cpu_sample(T, O, W, 16.0, threads)
+        v, sample, _ = cpu_sample(O, W, 16.0, threads)
         cpu = {"value": v, "unit": "circuit-timesteps/s", "cores": threads, "kind": "port", "sample": sample}
 
     if rank == 0:
@@ -441,15 +572,15 @@ def main():
             "metric": "circuit-timesteps/sec (batched FP64 transient)", "value": value, "unit": "circuit-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_job / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"rc.cir + rlc.cir transient, {n}-instance R/L/C sweep per GPU (LogUniform[0.5,2], PCG64 seed 1234), "
-                                   "summary-statistics output", "instances_per_deck_per_gpu": n, "parallelism": f"instances sharded over {world} GPU(s), no collective",
-                       "l2": "flushed between timed iterations (256 MB write)", "strict_fp": args.strict_fp},
+            "config": headline_config(n, world, args.strict_fp),
             "accepted_steps_per_step": acc_job, "newton_solves_per_step": solves_job,
             "newton_solves_per_sec": solves_job * args.steps / t_job if t_job > 0 else 0.0,
             "executed_solves_per_step": exec_job,
-            "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world},
+            "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
+                    "pipelined": "read-back of step i overlaps step i+1 (two batches per deck, tsb_result_fetch_async)", "results_check": bool(e2e_ok)},
             "gpu_launches": int(launches), "failed_instances": bad_status,
-            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp,
+            "configs": configs, "strong": strong, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,6 +1,6 @@
 """Development driver (not a pytest file): A/B timing of one deck's transient launch under option sets and
 code-shape switches.  Usage:
-    python tests/gpu_ab.py <deck> <instances> "<opts>|<defines>" ...
+    python tests/gpu_ab.py <deck> <instances> "<opts>|<defines>|<env>" ...
 e.g. python tests/gpu_ab.py rlc 1048576 "share_time_grid=0" "share_time_grid=1" "share_time_grid=1|TSB_X_FOO=1;TSB_X_BAR=0"
 <opts>: comma-separated tsb_opts fields; <defines>: $TSB_EXTRA_DEFINES for that variant.  Prints ms per launch (best of 3
 after a priming run), steps/s, and the largest deviation of the statistics from the first variant's (0 = bit-identical)."""
@@ -28,7 +28,11 @@ def main():
     card = ckt.analysis_card()
     ref = None
     for spec in variants:
-        o, _, defs = spec.partition("|")
+        o, _, rest = spec.partition("|")
+        defs, _, envs = rest.partition("|")
+        for item in filter(None, envs.split(";")):          # third field: environment variables for this variant
+            k, v = item.split("=")
+            os.environ[k] = v
         kw = {}
         for item in filter(None, o.split(",")):
             k, v = item.split("=")

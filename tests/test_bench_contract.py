@@ -50,9 +50,21 @@ def test_recorded_reference_arm_line():
 
 @pytest.mark.gpu
 def test_live_bench_line(built):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--instances", "65536", "--no-cpu-baseline"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--instances", "65536", "--no-cpu-baseline",
+                        "--config-scale", "0.004"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     d["cpu_baseline"] = d["cpu_baseline"] or {"value": 1.0, "unit": "", "cores": 1, "kind": "port", "sample": "skipped"}
     check_line(d)
+    # one entry per BASELINE.json config, every deck with a time, a throughput and a roofline fraction
+    cfgs = d["configs"]
+    assert len(cfgs) == 5 and not any("error" in c for c in cfgs), cfgs
+    assert cfgs[0]["exact"] is True
+    names = [[e["deck"] for e in c["decks"]] for c in cfgs[1:]]
+    assert names == [["rc", "rlc"], ["diode2", "diode4", "diode1", "diode5", "diode3"], ["mosfet1", "bjt2", "bjt1", "bjt3"],
+                     ["transformer3", "transformer1", "transformer2"]]
+    for c in cfgs[1:]:
+        for e in c["decks"]:
+            assert e["ms_per_launch"] > 0 and e["circuit_timesteps_per_sec"] > 0 and 0 < e["frac"] < 1.2 and 0 < e["lane_util"] <= 1.0, e
+    assert d["strong"]["scaling"] == "strong" and d["e2e"]["results_check"] is True and "excluded" in d["config"]

@@ -118,8 +118,22 @@ void emit_clear(Emitter& e, const LuProgram& lu, int n, const std::set<std::stri
 }
 
 // Emits the stamps of the listed devices into A[] (indexed through `lu.index`) and b[].
-void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only, bool first_assign = false) {
+// `deferred`: source-valued right-hand-side entries (b[row] = +-SV[slot]) that are the ONLY stamp into their row are not
+// emitted here but collected (as ready-made statements) for the caller to place after the factorisation — nothing before
+// the substitution reads them, so where they are assigned changes no value; a row that several stamps accumulate into
+// keeps its position (the order of additions is part of the rounding).
+void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_only, bool op_only, bool first_assign = false,
+                 std::vector<std::string>* deferred = nullptr) {
     std::set<std::string> touched;
+    std::map<std::string, int> writers;
+    if (deferred)
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (linear_only && d.nonlinear()) continue;
+            if (op_only && d.kind == TSB_K) continue;
+            for (const StampEntry& s : pl.stamps[di])
+                if (!(op_only && s.tran_only) && s.col == 0) ++writers["b[" + std::to_string(s.row) + "]"];
+        }
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
         if (linear_only && d.nonlinear()) continue;
@@ -141,8 +155,10 @@ void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_on
                 if (it == lu.index.end()) continue;     // cannot happen: pattern built from these entries
                 tgt = "A[" + std::to_string(it->second) + "]";
             }
-            if (first_assign && touched.insert(tgt).second) e.line(tgt + (s.sign < 0 ? " = -" : " = ") + val + ";");
-            else e.line(tgt + (s.sign < 0 ? " -= " : " += ") + val + ";");
+            const bool fresh = touched.insert(tgt).second;
+            std::string stmt = (first_assign && fresh) ? tgt + (s.sign < 0 ? " = -" : " = ") + val + ";" : tgt + (s.sign < 0 ? " -= " : " += ") + val + ";";
+            if (deferred && s.out == -2 && s.col == 0 && writers[tgt] == 1) deferred->push_back(stmt);
+            else e.line(stmt);
         }
         --e.ind;
         e.line("}");
@@ -155,7 +171,7 @@ void emit_stamps(Emitter& e, const Plan& pl, const LuProgram& lu, bool linear_on
 // `b_zero` (fast sparse builds): rows of b no stamp writes — forward / back substitution skips the operations whose
 // operand is such a structural zero.  `early_cond`: condition under which a zero pivot returns before the solve.
 void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string& xout, const std::set<int>* b_zero = nullptr,
-             const std::string& early_cond = "!lu_ok") {
+             const std::string& early_cond = "!lu_ok", const std::vector<std::string>* mid = nullptr) {
     const int n = lu.n;
     if (!lu.dense) e.line("bool lu_ok = true;");
     if (load_gmin) {
@@ -183,6 +199,7 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
         }
     }
     if (!lu.dense) e.line("if (" + early_cond + ") return false;");
+    if (mid) for (const std::string& st : *mid) e.line(st);
     e.line("double c[" + std::to_string(n + 1) + "];");
     std::vector<char> cz(n + 1, 0);          // c[k] is a structural zero so far
     for (int k = 1; k <= n; ++k) {
@@ -271,7 +288,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
             if (cfg.varying[k])
                 e.line("P[" + std::to_string(k) + "] = __ldcs(a.pv[" + std::to_string(cfg.var_slot[k]) + "] + inst);   // " + d.name + " p" + std::to_string(j));
             else
-                e.line("P[" + std::to_string(k) + "] = a.U[" + std::to_string(k) + "];");
+                e.line("P[" + std::to_string(k) + "] = a." + (k < 32 ? "Uc[" : "U[") + std::to_string(k) + "];");
         }
     }
     for (int i = 0; i < std::max(1, pl.n_state); ++i) e.line("S[" + std::to_string(i) + "] = 0.0;");
@@ -422,8 +439,12 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("// EARLY = false (the dedicated linear transient loop): a zero pivot does not return before the solve — the body");
     e.line("// stays one basic block; the caller discards x when the result is false.");
     e.line("// SOLVE = false: stamps only, for their side effects on device state (the DC sweep's discarded pass, dc.go:119-125).");
-    e.line("template <int MODE, bool EARLY = true, bool SOLVE = true>");
-    e.line("__device__ __forceinline__ bool assemble_solve(int mode_rt, double time, double dt, double rdt, double gmin) {");
+    e.line("// `mid` runs between the factorisation and the substitution: the source values SV[] that feed only the right-hand");
+    e.line("// side are read after it, so a caller may produce them there (tsb_tran_linear: looked up in the shared time grid");
+    e.line("// or computed) — off the critical path of the factorisation.");
+    e.line("struct TsbNoMid { __device__ __forceinline__ void operator()() const {} };");
+    e.line("template <int MODE, bool EARLY = true, bool SOLVE = true, class Mid = TsbNoMid>");
+    e.line("__device__ __forceinline__ bool assemble_solve(int mode_rt, double time, double dt, double rdt, double gmin, Mid mid = Mid()) {");
     ++e.ind;
     e.line("const int mode = MODE >= 0 ? MODE : mode_rt;");
     e.line("TsbEnv e; e.mode = mode; e.time = time; e.dt = dt; e.gmin = gmin; e.rdt = rdt;");
@@ -435,10 +456,12 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         std::set<int> bz;
         for (int i = 1; i <= n; ++i) if (!tg.count("b[" + std::to_string(i) + "]")) bz.insert(i);
         emit_clear(e, pl.lu_main, n, fa ? &tg : nullptr);
-        emit_stamps(e, pl, pl.lu_main, false, false, fa);
+        std::vector<std::string> late;
+        emit_stamps(e, pl, pl.lu_main, false, false, fa, &late);
+        late.insert(late.begin(), "mid();");
         e.line("if (!SOLVE) return true;");
         e.line("double xt[" + std::to_string(n + 1) + "];");
-        emit_lu(e, pl.lu_main, true, "xt", fa ? &bz : nullptr, "EARLY && !lu_ok");
+        emit_lu(e, pl.lu_main, true, "xt", fa ? &bz : nullptr, "EARLY && !lu_ok", &late);
     }
     for (int i = 1; i <= n; ++i) e.line("x[" + std::to_string(i) + "] = xt[" + std::to_string(i) + "];");
     e.line(pl.lu_main.dense ? "return true;" : "return lu_ok;");

@@ -25,6 +25,7 @@
 #define TSB_SKELETON_CUH
 
 #define TSB_MAX_VARYING 64
+#define TSB_UC_MAX 32
 
 struct TsbArgs {
     long long n_inst;
@@ -55,11 +56,15 @@ struct TsbArgs {
     const long long* order;    // optional processing order (tsb_batch_set_order): slot s works on instance order[s]
     const double* sweep2;      // nested DC sweep (dc.go:205-270): value of the inner source at point k (sweep[] holds the outer one)
     // Shared time grid (TSB_TGRID kernels, see tsb_tran_linear): attempt k of the PILOT instance as
-    // [time, dt | next_time, dt after the tstop clamp | 1/dt, result-store key | source values...]
+    // [time, dt | result-store key, source value 0 | further source values...]
     double* tgrid;                       // [tgrid_cap][TsbTgLayout::ND] doubles, or NULL (feature off for this launch)
     unsigned long long* tgrid_pub;       // number of entries published so far (release / acquire)
     int tgrid_cap;
     int tgrid_role;                      // 0: reader, 1: the pilot launch (one instance, publishes)
+    // The first TSB_UC_MAX uniform parameter values BY VALUE: kernel parameters live in the constant bank, so a value
+    // that is the same for every instance can be an instruction operand (or be re-read) instead of occupying a register
+    // pair of every thread for the whole run.  U (global memory) keeps the full table (PWL points, parameters beyond).
+    double Uc[TSB_UC_MAX];
 };
 
 // Slot -> instance.  With an order, lanes of a warp can be given instances that behave alike (similar Newton
@@ -245,7 +250,9 @@ struct TsbSink {
 #ifndef TSB_TGRID
 #define TSB_TGRID 0
 #endif
-#define TSB_TG_HDR 6
+// entry = [time, dt | key, SV[0] | SV[1], SV[2] | ...]: 32 bytes for a circuit with one source
+#define TSB_TG_HDR 3
+#define TSB_TG_NO_KEY (-3.0)       // key slot of an attempt the pilot rejected before it needed sources and key
 template <int NSRC> struct TsbTgLayout { static constexpr int ND = ((TSB_TG_HDR + NSRC + 1) / 2) * 2; };
 __device__ __forceinline__ unsigned long long tsb_ld_acquire(const unsigned long long* p) {
     unsigned long long v;
@@ -267,8 +274,8 @@ __device__ __forceinline__ void tsb_prefetch_l1(const void* p) { asm volatile("p
 #ifndef TSB_TG_PUBLISH_EVERY
 #define TSB_TG_PUBLISH_EVERY 8      // the pilot releases the count every 8 entries (a release is a MEMBAR: ~1 us)
 #endif
-#ifndef TSB_TG_BACKOFF0
-#define TSB_TG_BACKOFF0 4
+#ifndef TSB_TG_LOOK_EVERY
+#define TSB_TG_LOOK_EVERY 16        // a reader that has caught up with the published count looks again every 16 attempts
 #endif
 #ifndef TSB_TG_CACHED
 #define TSB_TG_CACHED 1             // entries are read through L1 (published entries are immutable and a reader only ever
@@ -330,71 +337,79 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     double time = 0.0, dt = a.minstep;
     double last_key = -1.0;
     TsbTimeKeyer keyer; keyer.reset();
-    int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves
+    int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves; attempt number = n_acc + n_rej
     constexpr int ND = TsbTgLayout<Ckt::NSRC>::ND;
-    constexpr double NO_KEY = -3.0;         // entry of an attempt the pilot rejected before it needed sources and key
     const bool tg_pub = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 1;
-    bool tg_use = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0;
-    int tg_k = 0, tg_limit = 0, tg_poll_at = 0, tg_backoff = TSB_TG_BACKOFF0, tg_strays = 0;
+    // entries [0, tg_limit) are known to be published; -1: this thread does not (or no longer) read the table
+    int tg_limit = (TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0) ? 0 : -1;
     while (time < a.tstop) {
-        double next_time = 0.0, rdt = 0.0, key = NO_KEY;
+        const int k = n_acc + n_rej;                       // attempt number: the table index
         const double t_tag = time, dt_tag = dt;
-        bool hit = false;
-        if (TSB_TGRID && tg_use) {
-            if (tg_k >= tg_limit && tg_k >= tg_poll_at) {
-                // caught up with what this thread knows to be published: look again — seldom (a reader that runs ahead
-                // of the pilot will not find anything for a while: the distance between looks doubles up to 1024 attempts)
+        bool look = false;
+        if (TSB_TGRID && tg_limit >= 0) {
+            if (k >= tg_limit && (k & (TSB_TG_LOOK_EVERY - 1)) == 0) {
+                // caught up with what this thread knows to be published: look again every few attempts (a reader that
+                // runs ahead of the pilot will not find anything new for a while)
                 const unsigned long long pub = tsb_ld_relaxed(a.tgrid_pub);
                 const int lim = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
-                if (lim > tg_k) { tsb_fence_acquire(); tg_limit = lim; tg_backoff = TSB_TG_BACKOFF0; }
-                else { tg_poll_at = tg_k + tg_backoff; tg_backoff = tg_backoff < 1024 ? tg_backoff * 2 : 1024; }
-                if (tg_k >= a.tgrid_cap) tg_use = false;
+                if (lim > k) { tsb_fence_acquire(); tg_limit = lim; }
+                if (k >= a.tgrid_cap) tg_limit = -1;
             }
-            if (tg_k < tg_limit) {
-                const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)tg_k * ND);
-                const double2 e0 = TSB_TG_LD(e), e1 = TSB_TG_LD(e + 1), e2 = TSB_TG_LD(e + 2);
-                hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(time)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt))) == 0;
+            look = k < tg_limit;
+            if (TSB_TG_PREFETCH && look) tsb_prefetch_l1(a.tgrid + (long long)k * ND);      // consumed after the factorisation
+        }
+        double next_time = time + dt;
+        if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+        __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
+        const double rdt = tsb_rcp_dt(dt);        // the one division by the time step of this attempt
+        const double lte = c.lte(dt, rdt);
+        if (lte > a.trtol && dt > a.minstep) {
+            if (tg_pub && k < a.tgrid_cap) {      // the pilot rejected this attempt before it needed sources or key
+                double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)k * ND);
+                __stcg(e, make_double2(t_tag, dt_tag));
+                __stcg(e + 1, make_double2(TSB_TG_NO_KEY, 0.0));
+                if ((k & (TSB_TG_PUBLISH_EVERY - 1)) == TSB_TG_PUBLISH_EVERY - 1) tsb_st_release(a.tgrid_pub, (unsigned long long)k + 1);
+            }
+            dt /= 2; ++n_rej; continue;
+        }
+        double key = 0.0;
+        // Between the factorisation and the substitution (assemble_solve's `mid` hook): the source values at the START
+        // of the step and the result-store key of its end — taken from the table when the entry's (time, dt)
+        // are this thread's own, else computed here, the one place they are computed (the pilot's values come from
+        // here too).  Branch-free sine core, general routine only for an argument beyond its range.
+        auto mid = [&]() {
+            bool hit = false;
+            if (TSB_TGRID && look) {
+                const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)k * ND);
+                const double2 e0 = TSB_TG_LD(e), e1 = TSB_TG_LD(e + 1);
+                hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(t_tag)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt_tag))) == 0;
+                if (!hit) tg_limit = -1;                    // this instance has left the pilot's grid: stop looking
+                hit = hit && e1.x != TSB_TG_NO_KEY;
                 if (hit) {
-                    next_time = e1.x; dt = e1.y; rdt = e2.x; key = e2.y;
-                    if (Ckt::SRC_UNIFORM && key != NO_KEY) {
+                    key = e1.x;
+                    if (Ckt::SRC_UNIFORM) {
+                        c.SV[0] = e1.y;
 #pragma unroll
-                        for (int j = 0; j < Ckt::NSRC; j += 2) {
-                            const double2 sv = TSB_TG_LD(e + 3 + j / 2);
+                        for (int j = 1; j < Ckt::NSRC; j += 2) {
+                            const double2 sv = TSB_TG_LD(e + 2 + j / 2);
                             c.SV[j] = sv.x;
                             if (j + 1 < Ckt::NSRC) c.SV[j + 1] = sv.y;
                         }
                     }
-                    tg_strays = 0;
-                    if (TSB_TG_PREFETCH && tg_k + 1 < tg_limit) tsb_prefetch_l1(a.tgrid + (long long)(tg_k + 1) * ND);
-                } else if (++tg_strays > 64) tg_use = false;     // this instance has left the pilot's grid for good
+                }
             }
-        }
-        if (!hit) {
-            next_time = time + dt;
-            if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
-            rdt = tsb_rcp_dt(dt);                          // the one division by the time step of this attempt
-        }
-        __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
-        const double lte = c.lte(dt, rdt);
-        const bool reject = lte > a.trtol && dt > a.minstep;
-        if (!reject && (key == NO_KEY || !Ckt::SRC_UNIFORM)) {
-            // sources are evaluated at the START of the step; branch-free sine core, general routine only for
-            // an argument beyond its range.  This is the one place they are computed: the pilot's values come from here.
-            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
-            if (key == NO_KEY) key = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
-        }
-        if (tg_pub && tg_k < a.tgrid_cap) {
-            double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)tg_k * ND);
-            __stcg(e, make_double2(t_tag, dt_tag));
-            __stcg(e + 1, make_double2(next_time, dt));
-            __stcg(e + 2, make_double2(rdt, key));
+            if (!hit || !Ckt::SRC_UNIFORM) { if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0); }
+            if (!hit) key = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
+            if (tg_pub && k < a.tgrid_cap) {
+                double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)k * ND);
+                __stcg(e, make_double2(t_tag, dt_tag));
+                __stcg(e + 1, make_double2(key, c.SV[0]));
 #pragma unroll
-            for (int j = 0; j < Ckt::NSRC; j += 2) __stcg(e + 3 + j / 2, make_double2(c.SV[j], j + 1 < Ckt::NSRC ? c.SV[j + 1] : 0.0));
-            if ((tg_k & (TSB_TG_PUBLISH_EVERY - 1)) == TSB_TG_PUBLISH_EVERY - 1) tsb_st_release(a.tgrid_pub, (unsigned long long)tg_k + 1);
-        }
-        ++tg_k;
-        if (reject) { dt /= 2; ++n_rej; continue; }
-        const bool solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+                for (int j = 1; j < Ckt::NSRC; j += 2) __stcg(e + 2 + j / 2, make_double2(c.SV[j], j + 1 < Ckt::NSRC ? c.SV[j + 1] : 0.0));
+                if ((k & (TSB_TG_PUBLISH_EVERY - 1)) == TSB_TG_PUBLISH_EVERY - 1) tsb_st_release(a.tgrid_pub, (unsigned long long)k + 1);
+            }
+        };
+        const bool solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0, mid);
         if (!solved) {
             ++n_bad;
             if (dt > a.minstep) { dt /= 2; ++n_rej; continue; }
@@ -404,7 +419,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
         tsb_accept_step<true>(a, c, sink, time, dt, next_time, lte, keyer, last_key, key);
         ++n_acc;
     }
-    if (tg_pub) tsb_st_release(a.tgrid_pub, (unsigned long long)(tg_k < a.tgrid_cap ? tg_k : a.tgrid_cap));
+    if (tg_pub) { const int k = n_acc + n_rej; tsb_st_release(a.tgrid_pub, (unsigned long long)(k < a.tgrid_cap ? k : a.tgrid_cap)); }
     n_acc_out += n_acc; n_rej_out += n_rej;
     const int failed = status == TSB_ST_TRAN_FAILED ? 1 : 0;
     // rejected attempts whose solve WAS executed: those rejected for a failing solve (n_bad - failed)

@@ -65,6 +65,7 @@ struct TsbArgsHost {
     unsigned long long* tgrid_pub;
     int tgrid_cap;
     int tgrid_role;
+    double Uc[32];
 };
 
 struct KernelModule {
@@ -131,6 +132,7 @@ struct tsb_batch {
     unsigned long long* d_tgrid_pub = nullptr;
     int tgrid_cap = 0, tgrid_nd = 0;
     int tgrid_used = 0;                                // the last transient run had a pilot
+    std::string tgrid_sig;                             // what the table on the device was built for (analysis + uniform values)
     cudaEvent_t ev_run = nullptr, ev_fetch = nullptr;  // tsb_result_fetch_async: run finished / copies finished
     bool fetch_pending = false;
     double* d_partial = nullptr;                       // tsb_result_summary: per-block partial results
@@ -551,6 +553,7 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     if (!b->d_uniform) CU(ctx, cudaMalloc(&b->d_uniform, ub ? ub : 8));
     if (ub) CU(ctx, cudaMemcpyAsync(b->d_uniform, b->uniform.data(), ub, cudaMemcpyHostToDevice, ctx->stream));
     a.U = b->d_uniform;
+    for (size_t k = 0; k < b->uniform.size() && k < 32; ++k) a.Uc[k] = b->uniform[k];
     a.max_iter = o.max_iter; a.abstol = o.abstol; a.reltol = o.reltol; a.trtol = o.trtol;
     a.wave = b->d_wave; a.stats = b->d_stats; a.rows = b->d_rows; a.status = b->d_status;
     a.counters = b->d_counters; a.scratch = b->d_scratch;
@@ -628,10 +631,25 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
 const int64_t TSB_TGRID_MIN_INSTANCES = 1 << 18;
 const int TSB_TGRID_CAP = 1 << 16;
 
+// The table is a pure function of the analysis arguments, the tolerances that steer the step control, the uniform
+// parameter values (sources included) and the pilot's decisions; readers verify every entry against their own (time, dt).
+// So a table built by an earlier run of this batch with the same arguments is still right — and complete, because runs
+// are ordered on the context's stream — and the pilot need not run again (a different pilot instance could at worst
+// lower the hit rate, never change a result).
+std::string tgrid_signature(const tsb_batch* b, const tsb_opts& o, const TsbArgsHost& a, const void* kernel) {
+    std::string s;
+    auto add = [&](const void* p, size_t n) { s.append((const char*)p, n); };
+    add(&a.tstart, sizeof(double) * 5); add(&a.uic, sizeof a.uic); add(&a.trtol, sizeof a.trtol); add(&a.max_iter, sizeof a.max_iter);
+    add(&o.strict_fp, sizeof o.strict_fp); add(&kernel, sizeof kernel); add(&b->d_order, sizeof b->d_order);
+    add(b->uniform.data(), b->uniform.size() * sizeof(double));
+    add(b->varying.data(), b->varying.size());
+    return s;
+}
+
 int launch_pilot(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& a) {
     tsb_ctx* ctx = b->ctx;
     const int nsrc = b->plan->p.n_src > 1 ? b->plan->p.n_src : 1;
-    const int nd = ((6 + nsrc + 1) / 2) * 2;
+    const int nd = ((3 + nsrc + 1) / 2) * 2;      // TsbTgLayout (device/skeleton.cuh)
     if (!b->d_tgrid || b->tgrid_nd != nd) {
         cudaFree(b->d_tgrid); b->d_tgrid = nullptr;
         CU(ctx, cudaMalloc(&b->d_tgrid, (size_t)TSB_TGRID_CAP * nd * sizeof(double)));
@@ -645,11 +663,15 @@ int launch_pilot(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHo
         CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     }
+    a.tgrid = b->d_tgrid; a.tgrid_pub = b->d_tgrid_pub; a.tgrid_cap = b->tgrid_cap; a.tgrid_role = 0;
+    const std::string sig = tgrid_signature(b, o, a, (const void*)kernel);
+    const char* reuse_env = getenv("TSB_TGRID_REUSE");
+    if (sig == b->tgrid_sig && !(reuse_env && *reuse_env == '0')) return TSB_OK;      // the table of the previous run stands
+    b->tgrid_sig = sig;
     // only the published count is reset: readers never look at entries at or above it
     CU(ctx, cudaMemsetAsync(b->d_tgrid_pub, 0, sizeof(unsigned long long), ctx->stream));
     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // parameters, uniform table and the reset are in place
     CU(ctx, cudaStreamWaitEvent(ctx->pilot_stream, ctx->ev_fork, 0));
-    a.tgrid = b->d_tgrid; a.tgrid_pub = b->d_tgrid_pub; a.tgrid_cap = b->tgrid_cap; a.tgrid_role = 0;
     TsbArgsHost ap = a;
     ap.tgrid_role = 1; ap.n_run = 1; ap.out_flags = 0; ap.work_counter = b->d_work; ap.first_free = 1;
     const int block = o.block_size > 0 ? o.block_size : 128;
