@@ -81,7 +81,7 @@ def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, a
     return oc, res
 
 
-def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
+def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL, nonfinite_any=False):
     """Instance-by-instance comparison at identical stored rows.  Returns a report dict
     (max_rel = worst |gpu - ref| / (reltol*|ref| + abstol); <= 1 means inside the tolerance)."""
     rows_g = batch.rows()
@@ -111,6 +111,18 @@ def compare_waves(batch, ores, n, label="", reltol=RELTOL, abstol=ABSTOL):
         wg = wall[:nr_o, :, i] if wall is not None else batch.waveform(i)
         wo = ores["wave"][i, :nr_o, :ncol]
         nan_g, nan_o = np.isnan(wg), np.isnan(wo)
+        if nonfinite_any:
+            # a deck that overflows on purpose: whether an overflowed lane reads Inf or NaN (Inf - Inf, 0 * Inf) depends on the
+            # last bit of exp() and on the elimination order; only finite / non-finite is compared
+            if not np.array_equal(np.isfinite(wg), np.isfinite(wo)):
+                rep["nan_mismatch"] += 1
+                continue
+            ok = np.isfinite(wo)
+            err = np.abs(wg[ok] - wo[ok]); tol = reltol * np.abs(wo[ok]) + abstol
+            rep["compared_points"] += int(ok.sum())
+            if err.size and float((err / tol).max()) > rep["max_rel"]:
+                rep["max_rel"] = float((err / tol).max()); rep["max_abs"] = float(err.max())
+            continue
         if not np.array_equal(nan_g, nan_o):
             rep["nan_mismatch"] += 1
             r, c = np.argwhere(nan_g != nan_o)[0]

@@ -50,7 +50,9 @@ def _run_both(ctx, name, kind, mode, n=N):
 @pytest.mark.parametrize("name,kind", CASES, ids=[f"{n}-{k}" for n, k in CASES])
 def test_extra_deck_matches_oracle(ctx, name, kind, mode):
     batch, ores, ana = _run_both(ctx, name, kind, mode)
-    rep = PU.compare_waves(batch, ores, N)
+    # pnp_op's DC sweep overflows on purpose (no junction limiting): Inf-vs-NaN of an overflowed lane hangs on the
+    # last bit of exp(); there only finite / non-finite classes are compared (bjt1 / bjt2 / pnp_tran keep the exact classes)
+    rep = PU.compare_waves(batch, ores, N, nonfinite_any=(name, kind) == ("pnp_op", "dc"))
     assert PU.report_ok(rep), PU.report_str(rep)
     # discrete decisions (Newton stop iteration): identical up to the documented near-threshold flips
     assert rep["counter_mismatch"] <= 2, PU.report_str(rep)

@@ -233,6 +233,242 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
     for (int k = 1; k <= n; ++k) e.line(xout + "[" + std::to_string(lu.pcol[k]) + "] = c[" + std::to_string(k) + "];");
 }
 
+
+// ---- transient solves of the fast build: static condensation (plan.cpp: build_tranfast) ---------------------------------
+// The elimination program of pl.lu_tf is split in two by what each operation depends on:
+//   prefactor()            every operation whose operands are invariant over the run (resistor conductances, +-1 incidence
+//                          entries and whatever the elimination makes of them) — executed once per instance; the values
+//                          later operations need are kept in AI[];
+//   assemble_solve_tf()    the operations with at least one operand that changes from solve to solve (companion
+//                          conductances C/dt, L/dt, M/dt, nonlinear stamps, the right-hand side), reading invariant operands
+//                          from AI[].  An entry that collects invariant and variant contributions starts each solve from its
+//                          invariant part (AI[]) — a re-association the fast build is allowed.
+// Entry names: "T[k]" inside prefactor, "AI[q]" / "A[k]" inside the solve.
+struct TfSplit {
+    const Plan& pl;
+    const LuProgram& lu;
+    Emitter pre, step;
+    std::vector<char> inv;            // entry k is (still) invariant
+    std::vector<char> has_base;       // entry k has an invariant part computed in prefactor (T[k] is meaningful)
+    std::vector<char> step_init;      // A[k] has been assigned in the per-solve code
+    std::map<int, int> ai_slot;       // entry k -> AI index (value copied out of T[k] at the end of prefactor)
+    int n_ai = 0;
+    std::vector<char> base_final;     // (second pass) entry k ends up with an invariant part: decides how a solve initialises A[k]
+    std::map<int, double> lit;        // T[k] currently holds this literal (+-1 incidence entries): rcp and products fold
+    TfSplit(const Plan& p) : pl(p), lu(p.lu_tf), inv(p.lu_tf.pos.size(), 1), has_base(p.lu_tf.pos.size(), 0), step_init(p.lu_tf.pos.size(), 0) {
+        for (size_t k = 0; k < lu.pos.size(); ++k) if (k < pl.tf_variant.size() && pl.tf_variant[k]) inv[k] = 0;
+    }
+    std::string T(int k) const { return "T[" + std::to_string(k) + "]"; }
+    std::string A(int k) const { return "A[" + std::to_string(k) + "]"; }
+    std::string AI(int k) {          // invariant operand of a per-solve operation
+        auto it = ai_slot.find(k);
+        if (it == ai_slot.end()) it = ai_slot.emplace(k, n_ai++).first;
+        return "AI[" + std::to_string(it->second) + "]";
+    }
+    std::string opnd(int k) { return inv[k] ? AI(k) : A(k); }
+    // first per-solve touch of a variant entry: start from its invariant part if it has one
+    void ensure_init(int k) {
+        if (step_init[k]) return;
+        step_init[k] = 1;
+        step.line(A(k) + " = " + (based(k) ? AI(k) : std::string("0.0")) + ";");
+    }
+    bool based(int k) const { return base_final.empty() ? has_base[k] != 0 : base_final[k] != 0; }
+    // variant update A[k] -= expr (or first assignment)
+    void sub_variant(int k, const std::string& expr) {
+        if (!step_init[k] && !based(k)) { step_init[k] = 1; step.line(A(k) + " = -(" + expr + ");"); return; }
+        ensure_init(k);
+        step.line(A(k) + " -= " + expr + ";");
+    }
+};
+
+void tranfast_walk(TfSplit& sp, const Plan& pl, std::vector<std::string>& late, std::set<std::string>& b_touched);
+
+void emit_tranfast(Emitter& e, const Plan& pl, const CodegenConfig& cfg) {
+    const LuProgram& lu = pl.lu_tf;
+    const int n = lu.n;
+    std::vector<char> base_final;
+    {   // first pass: which entries end up with an invariant part
+        TfSplit dry(pl);
+        std::vector<std::string> l0; std::set<std::string> b0;
+        tranfast_walk(dry, pl, l0, b0);
+        base_final = dry.has_base;
+    }
+    TfSplit sp(pl);
+    sp.base_final = base_final;
+    sp.pre.ind = 2; sp.step.ind = 2;
+    std::vector<std::string> late;
+    std::set<std::string> b_touched;
+    tranfast_walk(sp, pl, late, b_touched);
+    // ---- substitution (always per solve: the right-hand side changes) ---------------------------------------------------
+    Emitter& se = sp.step;
+    se.line("if (EARLY && !lu_ok) return false;");
+    se.line("mid();");
+    for (const std::string& stt : late) se.line(stt);
+    std::set<int> bz;
+    for (int i = 1; i <= n; ++i) if (!b_touched.count("b[" + std::to_string(i) + "]")) bz.insert(i);
+    se.line("double c[" + std::to_string(n + 1) + "];");
+    std::vector<char> cz(n + 1, 0);
+    for (int k = 1; k <= n; ++k) {
+        cz[k] = bz.count(lu.prow[k]) ? 1 : 0;
+        se.line("c[" + std::to_string(k) + "] = " + (cz[k] ? std::string("0.0") : "b[" + std::to_string(lu.prow[k]) + "]") + ";");
+    }
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        std::string ck = "c[" + std::to_string(k) + "]";
+        if (cz[k]) continue;
+        se.line(ck + " *= " + sp.opnd(st.piv) + ";");
+        for (size_t li = 0; li < st.lcol.size(); ++li) {
+            int j = st.lrow_step[li];
+            std::string prod = ck + " * " + sp.opnd(st.lcol[li]);
+            if (cz[j]) { se.line("c[" + std::to_string(j) + "] = -(" + prod + ");"); cz[j] = 0; }
+            else se.line("c[" + std::to_string(j) + "] -= " + prod + ";");
+        }
+    }
+    for (int k = n; k >= 1; --k) {
+        const LuProgram::Step& st = lu.steps[k];
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            int j = st.ucol_step[ui];
+            if (cz[j]) continue;
+            std::string prod = sp.opnd(st.urow[ui]) + " * c[" + std::to_string(j) + "]";
+            if (cz[k]) { se.line("c[" + std::to_string(k) + "] = -(" + prod + ");"); cz[k] = 0; }
+            else se.line("c[" + std::to_string(k) + "] -= " + prod + ";");
+        }
+    }
+    for (int k = 1; k <= n; ++k) se.line("x[" + std::to_string(lu.pcol[k]) + "] = c[" + std::to_string(k) + "];");
+    se.line("return lu_ok;");
+
+    // ---- assemble the two member functions --------------------------------------------------------------------------------
+    e.line("double AI[" + std::to_string(std::max(1, sp.n_ai)) + "];   // invariant factors / invariant parts of the condensed transient elimination");
+    e.line("bool pf_ok;");
+    e.line("// once per instance, after load(): everything of the transient elimination that does not change during the run");
+    e.line("__device__ __forceinline__ void prefactor() {");
+    ++e.ind;
+    e.line("double T[" + std::to_string(lu.pos.size()) + "];");
+    e.line("pf_ok = true;");
+    e.os << sp.pre.os.str();
+    for (auto& kv : sp.ai_slot) e.line("AI[" + std::to_string(kv.second) + "] = T[" + std::to_string(kv.first) + "];");
+    --e.ind;
+    e.line("}");
+    e.line("// one transient solve: stamps and elimination of what changes, substitution.  `mid` as in assemble_solve.");
+    e.line("template <bool EARLY, class Mid>");
+    e.line("__device__ __forceinline__ bool assemble_solve_tf(double time, double dt, double rdt, Mid mid) {");
+    ++e.ind;
+    e.line("TsbEnv e; e.mode = TSB_MODE_TRAN; e.time = time; e.dt = dt; e.gmin = 0.0; e.rdt = rdt;");
+    e.line("double A[" + std::to_string(lu.pos.size()) + "];");
+    e.line("double b[" + std::to_string(n + 1) + "];");
+    e.os << sp.step.os.str();
+    --e.ind;
+    e.line("}");
+    (void)cfg;
+}
+
+void tranfast_walk(TfSplit& sp, const Plan& pl, std::vector<std::string>& late, std::set<std::string>& b_touched) {
+    const LuProgram& lu = pl.lu_tf;
+    const int n = lu.n;
+    // ---- stamps: invariant ones into T[] (prefactor), variant ones into A[] (solve) --------------------------------------
+    // (`late`: source-valued right-hand sides, placed after the factorisation)
+    std::map<std::string, int> rhs_writers;
+    for (int di : pl.stamp_order)
+        for (const StampEntry& s : pl.stamps[di]) if (s.col == 0) ++rhs_writers["b[" + std::to_string(s.row) + "]"];
+    std::set<int> pre_touched;
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        bool any_var = false, any_inv = false;
+        for (const StampEntry& s : pl.stamps[di]) {
+            const bool v = s.col == 0 || !(d.kind == TSB_R || d.kind == TSB_V || d.kind == TSB_I || ((d.kind == TSB_L || d.kind == TSB_LCORE) && s.out == -1));
+            (v ? any_var : any_inv) = true;
+        }
+        if (any_inv) {
+            sp.pre.line("{   // " + std::string(kind_name(d.kind)) + " " + d.name);
+            ++sp.pre.ind;
+            if (d.kind == TSB_R) sp.pre.line("const double o0 = D[" + std::to_string(d.d_off) + "];");
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (s.col == 0) continue;
+                const bool v = !(d.kind == TSB_R || d.kind == TSB_V || d.kind == TSB_I || ((d.kind == TSB_L || d.kind == TSB_LCORE) && s.out == -1));
+                if (v) continue;
+                const int k = lu.index.at({s.row, s.col});
+                std::string val = s.out == -1 ? dlit(s.cval) : std::string("o0");
+                if (pre_touched.insert(k).second) {
+                    sp.pre.line(sp.T(k) + (s.sign < 0 ? " = -" : " = ") + val + ";");
+                    if (s.out == -1) sp.lit[k] = s.sign * s.cval;
+                } else { sp.pre.line(sp.T(k) + (s.sign < 0 ? " -= " : " += ") + val + ";"); sp.lit.erase(k); }
+                sp.has_base[k] = 1;
+            }
+            --sp.pre.ind;
+            sp.pre.line("}");
+        }
+        if (any_var) {
+            sp.step.line("{   // " + std::string(kind_name(d.kind)) + " " + d.name);
+            ++sp.step.ind;
+            if (d.kind != TSB_R) emit_eval(sp.step, pl, di, "o");
+            for (const StampEntry& s : pl.stamps[di]) {
+                const bool v = s.col == 0 || !(d.kind == TSB_R || d.kind == TSB_V || d.kind == TSB_I || ((d.kind == TSB_L || d.kind == TSB_LCORE) && s.out == -1));
+                if (!v) continue;
+                std::string val = s.out == -1 ? dlit(s.cval) : (s.out == -2 ? "SV[" + std::to_string(d.src_slot) + "]" : "o[" + std::to_string(s.out) + "]");
+                if (s.col == 0) {
+                    std::string tgt = "b[" + std::to_string(s.row) + "]";
+                    const bool fresh = b_touched.insert(tgt).second;
+                    std::string stmt = fresh ? tgt + (s.sign < 0 ? " = -" : " = ") + val + ";" : tgt + (s.sign < 0 ? " -= " : " += ") + val + ";";
+                    if (s.out == -2 && rhs_writers[tgt] == 1) late.push_back(stmt); else sp.step.line(stmt);
+                } else {
+                    const int k = lu.index.at({s.row, s.col});
+                    if (!sp.step_init[k] && !sp.based(k)) { sp.step_init[k] = 1; sp.step.line(sp.A(k) + (s.sign < 0 ? " = -" : " = ") + val + ";"); }
+                    else { sp.ensure_init(k); sp.step.line(sp.A(k) + (s.sign < 0 ? " -= " : " += ") + val + ";"); }
+                }
+            }
+            --sp.step.ind;
+            sp.step.line("}");
+        }
+    }
+    // entries nothing stamps and nothing invariant has touched yet start at zero in prefactor (fill-in)
+    // ---- elimination ---------------------------------------------------------------------------------------------------
+    sp.step.line("bool lu_ok = pf_ok;");
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        const int p = st.piv;
+        if (sp.inv[p]) {
+            if (!sp.has_base[p]) { sp.pre.line(sp.T(p) + " = 0.0;"); sp.has_base[p] = 1; }
+            if (sp.lit.count(p) && (sp.lit[p] == 1.0 || sp.lit[p] == -1.0)) {
+                // a +-1 incidence pivot: its reciprocal is itself (kept a literal so that the products below fold away)
+            } else {
+                sp.pre.line("pf_ok = pf_ok & (" + sp.T(p) + " != 0.0);");
+                sp.pre.line(sp.T(p) + " = tsb_rcp(" + sp.T(p) + ");");
+                sp.lit.erase(p);
+            }
+        } else {
+            sp.ensure_init(p);
+            sp.step.line("lu_ok = lu_ok & (" + sp.A(p) + " != 0.0);");
+            sp.step.line(sp.A(p) + " = tsb_rcp(" + sp.A(p) + ");");
+        }
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            const int u = st.urow[ui];
+            if (sp.inv[u] && !sp.has_base[u]) { sp.pre.line(sp.T(u) + " = 0.0;"); sp.has_base[u] = 1; }
+            if (sp.inv[u] && sp.inv[p]) {
+                if (sp.lit.count(p) && sp.lit[p] == 1.0) { /* u * 1 */ }
+                else if (sp.lit.count(p) && sp.lit[p] == -1.0) { sp.pre.line(sp.T(u) + " = -" + sp.T(u) + ";"); if (sp.lit.count(u)) sp.lit[u] = -sp.lit[u]; }
+                else { sp.pre.line(sp.T(u) + " *= " + sp.T(p) + ";"); sp.lit.erase(u); }
+            }
+            else {
+                if (sp.inv[u]) { sp.inv[u] = 0; sp.step_init[u] = 1; sp.step.line(sp.A(u) + " = " + sp.AI(u) + " * " + sp.opnd(p) + ";"); }
+                else { sp.ensure_init(u); sp.step.line(sp.A(u) + " *= " + sp.opnd(p) + ";"); }
+            }
+            for (size_t li = 0; li < st.lcol.size(); ++li) {
+                const int l = st.lcol[li], t = st.target[ui][li];
+                if (sp.inv[l] && !sp.has_base[l]) { sp.pre.line(sp.T(l) + " = 0.0;"); sp.has_base[l] = 1; }
+                if (sp.inv[u] && sp.inv[l]) {
+                    // invariant product: into the invariant part of the target, whether the target stays invariant or not
+                    if (!sp.has_base[t]) { sp.pre.line(sp.T(t) + " = -(" + sp.T(u) + " * " + sp.T(l) + ");"); sp.has_base[t] = 1; }
+                    else sp.pre.line(sp.T(t) + " -= " + sp.T(u) + " * " + sp.T(l) + ";");
+                    sp.lit.erase(t);
+                } else {
+                    sp.inv[t] = 0;
+                    sp.sub_variant(t, sp.opnd(u) + " * " + sp.opnd(l));
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
@@ -467,6 +703,11 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line(pl.lu_main.dense ? "return true;" : "return lu_ok;");
     --e.ind;
     e.line("}");
+
+    // ---- fast build: condensed transient elimination ------------------------------------------------------
+    const bool use_tf = pl.has_tranfast && cfg.fast_div && cfg.tranfast;
+    e.line("static constexpr bool HAS_TF = " + std::string(use_tf ? "true" : "false") + ";");
+    if (use_tf) emit_tranfast(e, pl, cfg);
 
     // ---- operator level: the stamped system itself -----------------------------------------------------
     // mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin) as a DENSE n x n matrix + right-hand side written to

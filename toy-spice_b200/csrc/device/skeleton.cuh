@@ -409,7 +409,9 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
                 if ((k & (TSB_TG_PUBLISH_EVERY - 1)) == TSB_TG_PUBLISH_EVERY - 1) tsb_st_release(a.tgrid_pub, (unsigned long long)k + 1);
             }
         };
-        const bool solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0, mid);
+        bool solved;
+        if constexpr (Ckt::HAS_TF) solved = c.template assemble_solve_tf<false>(time, dt, rdt, mid);      // condensed elimination (fast build)
+        else solved = c.template assemble_solve<TSB_MODE_TRAN, false>(TSB_MODE_TRAN, time, dt, rdt, 0.0, mid);
         if (!solved) {
             ++n_bad;
             if (dt > a.minstep) { dt /= 2; ++n_rej; continue; }
@@ -465,7 +467,9 @@ __device__ __forceinline__ void tsb_tran_nonlinear(const TsbArgs& a, Ckt& c, Sin
         while (__any_sync(0xffffffffu, iterating)) {
             if (iterating) {
                 if (iter > 0) c.update_nl(c.xo);
-                const bool solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+                bool solved;
+                if constexpr (Ckt::HAS_TF) solved = c.template assemble_solve_tf<true>(time, dt, rdt, typename Ckt::TsbNoMid());   // condensed elimination
+                else solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
                 ++n_sol;
                 if (!solved) fail = true;
                 else {
@@ -547,6 +551,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
     auto begin_instance = [&]() {
         c.load(a, inst);
         c.init();
+        if constexpr (Ckt::HAS_TF) c.prefactor();
         sink.begin(inst);
         n_acc = n_rej = n_sol_tran = n_sol_op = n_exec = 0;
         op_path = 0; status = TSB_ST_OK; fail_at = 0.0;

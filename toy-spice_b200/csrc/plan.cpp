@@ -279,6 +279,115 @@ void build_lu_program(int n, const std::vector<std::pair<int, int>>& pattern, co
     }
 }
 
+// ---- static condensation order for the transient solves of the fast build ------------------------------------------
+// In a transient run most of the MNA matrix is the same in every solve: resistor conductances and the +-1 incidence
+// entries of sources and inductor branches do not depend on the time step or on device state; only the companion
+// conductances C/dt, L/dt, M/dt (and every entry a nonlinear device stamps) change.  The reference's order (frozen from
+// its operating-point matrix) happens to start with an inductor branch diagonal in the bundled decks, which makes every
+// later operation depend on dt.  Here the pivots whose value is invariant are eliminated FIRST: all their
+// multipliers, and every update between invariant entries, are computed once per instance (Ckt::prefactor), and a solve
+// only factors the Schur complement of the variant entries.  Candidates are taken in Markowitz order (fewest
+// operations; the diagonal on ties), numerically acceptable against the invariant entries of their column on the nominal
+// instance (relative threshold 1e-3 as in Sparse 1.3); the variant remainder is ordered by MarkowitzLU on the nominal
+// transient matrix at a representative step.  A different elimination order is a different rounding pattern — which is
+// what the fast build is allowed (its results are held to the 1e-9 / 1e-12 contract by the parity tests on every deck
+// but the ill-conditioned coupled-inductor ones); the strict build keeps the reference's order.
+static bool stamp_is_variant(const Dev& d, const StampEntry& s) {
+    if (s.col == 0) return true;                                   // right-hand side: sources and state
+    switch (d.kind) {
+    case TSB_R: case TSB_V: case TSB_I: return false;
+    case TSB_L: case TSB_LCORE: return s.out != OUT_CONST;        // the branch diagonal -L/dt
+    default: return true;                                          // C, K, D, Q, M
+    }
+}
+
+static void build_tranfast(Plan& pl, Nominal& nom) {
+    const int n = pl.n();
+    pl.has_tranfast = false;
+    if (pl.has_bjt || n > 48) return;                               // BJT circuits stay dense in the reference's order (Inf / NaN bookkeeping)
+    const double dt_rep = 1e-6;
+    std::vector<std::vector<char>> on(n + 1, std::vector<char>(n + 1, 0)), var(n + 1, std::vector<char>(n + 1, 0));
+    std::vector<std::vector<double>> val(n + 1, std::vector<double>(n + 1, 0.0));
+    {
+        TsbEnv env{TSB_MODE_TRAN, 0.0, dt_rep, 0.0, 1.0 / dt_rep};
+        double o[64];
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            std::vector<double> big;
+            double* op = o;
+            int no = device_num_outputs(d);
+            if (no > 64) { big.resize(no); op = big.data(); }
+            nom.eval(di, env, op);
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (s.col == 0) continue;
+                on[s.row][s.col] = 1;
+                if (stamp_is_variant(d, s)) var[s.row][s.col] = 1;
+                double v = s.out == OUT_CONST ? s.cval : op[s.out];
+                val[s.row][s.col] += s.sign * v;
+            }
+        }
+    }
+    // entry flags by stamp, before any elimination: what the code generator needs
+    std::vector<std::vector<char>> var0 = var;
+    std::vector<char> rdone(n + 1, 0), cdone(n + 1, 0);
+    PivotOrder ord; ord.n = n; ord.ext2int.assign(n + 1, 0); ord.prow.assign(n + 1, 0); ord.pcol.assign(n + 1, 0);
+    int k = 0;
+    for (;;) {
+        int br = 0, bc = 0; long best = -1; double bmag = 0;
+        for (int r = 1; r <= n; ++r) {
+            if (rdone[r]) continue;
+            for (int c = 1; c <= n; ++c) {
+                if (cdone[c] || !on[r][c] || var[r][c] || val[r][c] == 0.0) continue;
+                double colmax = 0;
+                int rc = 0, cc = 0;
+                for (int i = 1; i <= n; ++i) if (!rdone[i] && on[i][c]) { ++cc; if (!var[i][c]) colmax = std::max(colmax, std::fabs(val[i][c])); }
+                for (int j = 1; j <= n; ++j) if (!cdone[j] && on[r][j]) ++rc;
+                if (std::fabs(val[r][c]) < 1e-3 * colmax) continue;
+                // a variant entry in the pivot's column or row may be arbitrarily large: only rows / columns whose other
+                // live entries are all invariant qualify, except that the +-1 incidence pivots of sources are exact
+                bool clean = true;
+                for (int i = 1; i <= n; ++i) if (i != r && !rdone[i] && on[i][c] && var[i][c]) clean = false;
+                for (int j = 1; j <= n; ++j) if (j != c && !cdone[j] && on[r][j] && var[r][j]) clean = false;
+                if (!clean) continue;
+                long cost = (long)(rc - 1) * (cc - 1);
+                double mag = std::fabs(val[r][c]);
+                bool better = best < 0 || cost < best || (cost == best && ((r == c) > (br == bc))) ||
+                              (cost == best && (r == c) == (br == bc) && mag > bmag);
+                if (better) { best = cost; br = r; bc = c; bmag = mag; }
+            }
+        }
+        if (!br) break;
+        ++k; ord.prow[k] = br; ord.pcol[k] = bc; rdone[br] = 1; cdone[bc] = 1;
+        for (int i = 1; i <= n; ++i) {
+            if (rdone[i] || !on[i][bc]) continue;
+            for (int j = 1; j <= n; ++j) {
+                if (cdone[j] || !on[br][j]) continue;
+                on[i][j] = 1;
+                var[i][j] = var[i][j] | var[i][bc] | var[br][j];
+                val[i][j] -= val[i][bc] * val[br][j] / val[br][bc];
+            }
+        }
+    }
+    const int n_inv = k;
+    if (n_inv == 0) return;                                         // nothing to condense
+    if (k < n) {                                                    // the variant remainder: Markowitz / threshold on the nominal values
+        std::vector<int> rows, cols;
+        for (int r = 1; r <= n; ++r) if (!rdone[r]) rows.push_back(r);
+        for (int c = 1; c <= n; ++c) if (!cdone[c]) cols.push_back(c);
+        const int m = (int)rows.size();
+        MarkowitzLU rem(m);
+        for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) if (on[rows[i]][cols[j]]) rem.add(i + 1, j + 1, val[rows[i]][cols[j]]);
+        if (rem.assigned() != m || !rem.order_and_factor()) return;
+        for (int q = 1; q <= m; ++q) { ++k; ord.prow[k] = rows[rem.pivot_row(q) - 1]; ord.pcol[k] = cols[rem.pivot_col(q) - 1]; }
+    }
+    std::vector<std::pair<int, int>> pat = pl.pattern_op;
+    pat.insert(pat.end(), pl.pattern_tran_extra.begin(), pl.pattern_tran_extra.end());
+    build_lu_program(n, pat, ord, false, pl.lu_tf);
+    pl.tf_variant.assign(pl.lu_tf.pos.size(), 0);
+    for (size_t q = 0; q < pl.lu_tf.pos.size(); ++q) pl.tf_variant[q] = var0[pl.lu_tf.pos[q].first][pl.lu_tf.pos[q].second];
+    pl.has_tranfast = true;
+}
+
 }  // namespace
 
 int plan_finalize(Plan& pl) {
@@ -416,6 +525,11 @@ int plan_finalize(Plan& pl) {
         // BJT circuits run dense so that Inf/NaN propagate through the solve exactly as they do
         // through the reference's structurally dense matrix.
         build_lu_program(n, pat, pl.order_main, pl.has_bjt, pl.lu_main);
+    }
+    {
+        Nominal nom2(pl);            // fresh device state: the order must not depend on where the replay above left it
+        nom2.derive();
+        build_tranfast(pl, nom2);
     }
     pl.finalized = true;
     return TSB_OK;

@@ -267,6 +267,7 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
     cfg.tgrid = o.share_time_grid != 0;
+    if (const char* tf = getenv("TSB_TRANFAST")) cfg.tranfast = *tf != '0';       // development knob: A/B of the condensed elimination
     cfg.grid = b->grid_kernel;
     cfg.dc_nested = b->dc_nested; cfg.dc_param2 = b->dc_param2;
     cfg.order = b->d_order != nullptr;
@@ -346,6 +347,7 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
              (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, (int)b->dc_nested, b->dc_param2, ctx->choice_epoch, (void*)ctx);
     sig += tail;
     if (xd) sig += xd;
+    if (const char* tf = getenv("TSB_TRANFAST")) { sig += "|tf"; sig += tf; }
     if (b->memo_module && sig == b->memo_sig) {
         *out = b->memo_module;
         if (autokey_out) *autokey_out = b->memo_autokey;

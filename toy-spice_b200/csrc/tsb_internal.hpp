@@ -85,6 +85,12 @@ struct Plan {
     std::vector<std::pair<int, int>> pattern_op, pattern_tran_extra;   // first-touch order
     PivotOrder order_main, order_init;
     LuProgram lu_main, lu_init;
+    // Transient solves of the fast build (static condensation, plan.cpp: build_tranfast): an elimination order that
+    // takes the pivots whose value is the same in every solve of a run first, and per entry of lu_tf.pos whether its
+    // STAMPED value changes from solve to solve (time step, device state)
+    LuProgram lu_tf;
+    std::vector<char> tf_variant;
+    bool has_tranfast = false;
     bool init_struct_singular = false;
     bool has_nonlinear = false, has_time_dependent = false, has_bjt = false, has_mutual = false;
     std::string error;
@@ -117,6 +123,7 @@ struct CodegenConfig {
     bool order = false;             // kernels that map launch slots to instances through a processing order
     bool lane_refill = false;       // nonlinear circuits: resident grid, finished lanes fetch the next instance
     bool tgrid = false;             // linear circuits: kernels that can read / publish the shared time grid (skeleton.cuh)
+    bool tranfast = true;           // fast build: transient solves use the condensed elimination (lu_tf) where the plan has one
 };
 std::string generate_source(const Plan& plan, const CodegenConfig& cfg);
 
