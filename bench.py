@@ -500,7 +500,7 @@ def main():
                "flops_per_solve": fl["total"], "tflops": tf, "frac": tf / fp64_peak if fp64_peak else None,
                "lane_util": lane_util(cnt[6]) if nl else 1.0,
                "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
-               "nan_instances": int(np.isnan(b.stats_all()[3]).any(axis=0).sum()) if hi - lo <= (1 << 22) else None}
+               "nan_instances": int(np.isnan(b.stats_all()[3]).any(axis=0).sum()) if (an != T.AN_OP and hi - lo <= (1 << 22)) else None}
         del b, keep
         return ent
 

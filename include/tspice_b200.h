@@ -68,7 +68,7 @@ enum {
 };
 
 /* Source waveforms (pkg/device/device.go:58-62).  p layout:
- *   DC    [value]                  SIN   [offset, amplitude, freq, phase_deg]
+ *   DC    [value (, ac_mag, ac_phase_deg)]   SIN   [offset, amplitude, freq, phase_deg]
  *   PULSE [v1, v2, td, tr, tf, pw, per]   PWL [t0, v0, t1, v1, ...] (not sweepable) */
 enum { TSB_SRC_DC = 0, TSB_SRC_SIN = 1, TSB_SRC_PULSE = 2, TSB_SRC_PWL = 3 };
 
@@ -82,7 +82,8 @@ enum {
     TSB_ST_OP_FAILED = 1,    /* "source stepping failed" / "final solution failed"   op.go:216-229 */
     TSB_ST_TRAN_FAILED = 2,  /* "failed to converge at t=%g"                         tran.go:119  */
     TSB_ST_DC_FAILED = 3,    /* "convergence error at %s=%g"                         dc.go:128    */
-    TSB_ST_OVERFLOW = 4      /* more stored rows than the waveform capacity; rows beyond it dropped */
+    TSB_ST_OVERFLOW = 4,     /* more stored rows than the waveform capacity; rows beyond it dropped */
+    TSB_ST_AC_FAILED = 5     /* "matrix solve error at f=%g"                         ac.go:68     */
 };
 
 /* Convergence constants, defaults = NewBaseAnalysis (anlysis.go:35-44) and NewTransient (tran.go:51). */
@@ -184,6 +185,10 @@ int tsb_plan_node_name(const tsb_plan* plan, int node, const char** name);   /* 
 /* What the netlist's dot-cards asked for (from_netlist plans). */
 int tsb_plan_analysis(const tsb_plan* plan, int* analysis, double tran[4] /*tstart,tstop,tstep,tmax*/, int* uic,
                       int* dc_src_dev, double dc[3] /*start,stop,inc*/);
+/* The rest of the dot-cards: the second source of `.dc src1 a b inc src2 a b inc` (-1: none; the reference's parser stops
+ * after the first source, SURVEY Q20 — accepting the second one, `.end` and inline diode parameters `D1 a k MODEL Is=..`
+ * are this front-end's hardenings), and the `.ac` card: sweep type (0 DEC, 1 OCT, 2 LIN), number of points, fstart, fstop. */
+int tsb_plan_analysis2(const tsb_plan* plan, int* dc2_src_dev, double dc2[3], int* ac_sweep, int* ac_points, double ac_f[2]);
 /* Structure (finalized plans).  All index arrays are 1-based with n+1 entries ([0] unused).
  *   ext2int    Sparse `Translate` numbering of the main matrix (first-touch order)
  *   pivot_row / pivot_col   external row / column of the pivot chosen at each elimination step */
@@ -228,6 +233,17 @@ int tsb_run_dc(tsb_batch* batch, int src_dev, double start, double stop, double 
  * status = TSB_ST_DC_FAILED, rows[inst] = index of that point, counters[5] = the outer source's value there. */
 int tsb_run_dc2(tsb_batch* batch, int src1_dev, double start1, double stop1, double inc1, int src2_dev, double start2,
                 double stop2, double inc2, int out_flags, const tsb_opts* opts);
+/* AC analysis (analysis.NewAC(fStart, fStop, nPoints, pType) + Setup + Execute, ac.go:21-126) of circuits WITHOUT nonlinear
+ * devices: n_points frequencies in total between fstart and fstop (sweep_type 0 DEC / 1 OCT: logarithmic, 2 LIN), one complex
+ * solve per frequency and instance with the StampAC values of every device — the reference's quirks included: an inductor is
+ * stamped as the ADMITTANCE j*omega*L between its nodes and leaves its branch row empty (inductor.go:43-57), so a circuit with
+ * an inductor fails with TSB_ST_AC_FAILED at the first frequency, as the reference's "matrix solve error" does.
+ * Rows: [FREQ, V(node)_MAG, V(node)_PHASE (degrees) ..., I(vsource)_MAG, I(vsource)_PHASE ...] (StoreACResult,
+ * anlysis.go:87-111; column names: analysis code TSB_AN_AC).  AC magnitude / phase of a source: parameters 1 and 2 of a DC
+ * source (`V1 1 0 AC mag [phase]`, vsource.go:98-111), sweepable like any other.  Circuits with nonlinear devices:
+ * TSB_E_UNSUPPORTED (their small-signal values come from an operating point the reference solves on a complex matrix with
+ * a real-indexed right-hand side — an artefact of the un-vendored sparse module, not reproduced). */
+int tsb_run_ac(tsb_batch* batch, int sweep_type, int n_points, double fstart, double fstop, int out_flags, const tsb_opts* opts);
 /* Block until the last run has finished (runs are asynchronous on the context's stream). */
 int tsb_batch_sync(tsb_batch* batch);
 

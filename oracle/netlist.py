@@ -59,6 +59,8 @@ class Netlist:
     analysis: int = AN_OP
     tran: dict = field(default_factory=lambda: dict(tstep=0.0, tstop=0.0, tstart=0.0, tmax=0.0, uic=False))
     dc: dict = field(default_factory=lambda: dict(source="", start=0.0, stop=0.0, inc=0.0))
+    dc2: dict = field(default_factory=lambda: dict(source="", start=0.0, stop=0.0, inc=0.0))     # hardening: second .dc source
+    ac: dict = field(default_factory=lambda: dict(sweep="", points=0, fstart=0.0, fstop=0.0))
 
 
 def _fields(s: str) -> list:
@@ -118,6 +120,11 @@ def parse(text: str) -> Netlist:
 
 def _parse_line(nl: Netlist, line: str) -> None:
     line = re.sub(r"\s+", " ", line)
+    if getattr(nl, "_ended", False):
+        return
+    if line.strip().lower() == ".end":          # HARDENING (parser.go:155 "TODO: .END"): the deck ends here; the reference errors
+        nl._ended = True
+        return
     if line.startswith("."):
         _parse_dot(nl, line)
         return
@@ -149,15 +156,27 @@ def _parse_dot(nl: Netlist, line: str) -> None:
                 nl.tran["tmax"] = parse_value(f[i])
         if nl.tran["tmax"] == 0:
             nl.tran["tmax"] = nl.tran["tstep"]
-    elif cmd == ".ac":
+    elif cmd == ".ac":                       # parser.go:238-261
         nl.analysis = AN_AC
         if len(f) < 5:
             raise NetlistError("insufficient AC parameters")
+        sweep = f[1].upper()
+        if sweep not in ("DEC", "OCT", "LIN"):
+            raise NetlistError(f"invalid sweep type: {sweep}")
+        try:
+            pts = int(f[2])
+        except ValueError:
+            raise NetlistError("invalid number of points")
+        nl.ac = dict(sweep=sweep, points=pts, fstart=parse_value(f[3]), fstop=parse_value(f[4]))
     elif cmd == ".dc":
         nl.analysis = AN_DC
         if len(f) < 5:
             raise NetlistError("insufficient DC sweep parameters")
         nl.dc = dict(source=f[1], start=parse_value(f[2]), stop=parse_value(f[3]), inc=parse_value(f[4]))
+        # HARDENING beyond the reference (its parser stops after the first source; cmd/spice/main.go:325 is
+        # ready for DCParam.Source2): `.dc src1 start stop inc src2 start stop inc` -> nested sweep, src1 the outer loop
+        if len(f) >= 9:
+            nl.dc2 = dict(source=f[5], start=parse_value(f[6]), stop=parse_value(f[7]), inc=parse_value(f[8]))
     else:
         raise NetlistError(f"unsupported analysis type: {f[0]}")
 
@@ -289,6 +308,10 @@ def _parse_element(line: str) -> Element:
         e.nodes = f[1:3]
         if len(f) > 3:
             e.params["model"] = f[3]
+        for extra in f[4:]:                      # HARDENING: inline Is= / N= / Tt= overrides (the reference ignores these fields)
+            kv = extra.split("=")
+            if len(kv) == 2:
+                e.params["inline_" + kv[0].lower()] = kv[1]
         return e
     if typ == "Q":
         if len(f) < 4:
@@ -366,7 +389,8 @@ def _src_params(e: Element):
         return SRC_PWL, vals
     if t == "ac":
         parse_value(e.params["phase"])
-        return SRC_DC, [0.0]          # NewACVoltageSource(name, nodes, 0, mag, phase): DC 0 in OP/tran
+        # NewACVoltageSource(name, nodes, 0, mag, phase): DC 0 in OP / DC / tran; magnitude and phase (degrees) ride along
+        return SRC_DC, [0.0, e.value, parse_value(e.params["phase"])]
     raise NetlistError(f"unsupported source type: {t}")
 
 
@@ -433,6 +457,9 @@ def build_plan(nl: Netlist) -> Plan:
                 for k in p:
                     if k in mp:
                         p[k] = mp[k]
+            for k in p:                          # HARDENING (parser.go:530 "TODO: Inline parameters"): D1 a k MODEL Is=.. N=.. Tt=..
+                if "inline_" + k in e.params:
+                    p[k] = parse_value(e.params["inline_" + k])
             if len(e.nodes) != 2:
                 raise NetlistError(f"diode {e.name}: requires exactly 2 nodes")
             row = DeviceRow(K_D, e.name, nodes, 0, [p["is"], p["n"], p["tt"]], [])

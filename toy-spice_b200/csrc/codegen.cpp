@@ -469,6 +469,102 @@ void tranfast_walk(TfSplit& sp, const Plan& pl, std::vector<std::string>& late, 
     }
 }
 
+// ---- AC analysis (ac.go:51-98): one complex solve per frequency, linear circuits ------------------------------------------
+// Complex entries as (Ar[k], Ai[k]); the elimination program is pl.lu_ac: the reference's order (its complex matrix is
+// factored first during the operating point that precedes the sweep, with real values) over the StampAC pattern.
+void emit_ac(Emitter& e, const Plan& pl) {
+    const LuProgram& lu = pl.lu_ac;
+    const int n = lu.n;
+    auto S = [](int k) { return std::to_string(k); };
+    e.line("// mat.Clear(); ckt.Stamp(status{Mode: ACAnalysis, Frequency}); mat.Solve()  ->  xr + j*xi   (ac.go:57-71)");
+    e.line("__device__ __forceinline__ bool solve_ac(double omega, double* xr, double* xi) {");
+    ++e.ind;
+    e.line("double Ar[" + S((int)lu.pos.size()) + "], Ai[" + S((int)lu.pos.size()) + "], br[" + S(n + 1) + "], bi[" + S(n + 1) + "];");
+    for (size_t k = 0; k < lu.pos.size(); ++k) e.line("Ar[" + S((int)k) + "] = 0.0; Ai[" + S((int)k) + "] = 0.0;");
+    for (int i = 0; i <= n; ++i) e.line("br[" + S(i) + "] = 0.0; bi[" + S(i) + "] = 0.0;");
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        std::vector<AcEntry> ae;
+        device_ac_entries(pl, di, ae);
+        e.line("{   // " + std::string(kind_name(d.kind)) + " " + d.name);
+        ++e.ind;
+        for (const AcEntry& a : ae) {
+            const std::string k = S(lu.index.at({a.row, a.col}));
+            const std::string sg = a.sign < 0 ? " -= " : " += ";
+            switch (a.code) {
+            case 0: e.line("Ar[" + k + "]" + sg + "D[" + S(d.d_off) + "];"); break;
+            case 1: e.line("Ai[" + k + "]" + sg + "omega * (P[" + S(d.p_off) + "] * 1.0);"); break;
+            case 2: e.line("Ai[" + k + "]" + sg + "omega * P[" + S(d.p_off) + "];"); break;
+            case 3: e.line("Ar[" + k + "]" + sg + "1.0;"); break;
+            case 4: e.line("Ai[" + k + "]" + sg + "(-1.0 / (omega * D[" + S(d.d_off) + "]));"); break;
+            default: e.line("Ai[" + k + "]" + sg + "omega * D[" + S(d.d_off + a.code - 5) + "];"); break;
+            }
+        }
+        // right-hand sides: AC magnitude / phase of the sources (vsource.go:160-176, isource.go:149-165)
+        if ((d.kind == TSB_V || d.kind == TSB_I) && d.src_type() == TSB_SRC_DC && d.p.size() >= 3) {
+            e.line("const double ph = P[" + S(d.p_off + 2) + "] * TSB_PI / 180.0;");
+            e.line("const double re = P[" + S(d.p_off + 1) + "] * cos(ph), im = P[" + S(d.p_off + 1) + "] * tsb_go_sin(ph);");
+            if (d.kind == TSB_V) e.line("br[" + S(d.branch) + "] += re; bi[" + S(d.branch) + "] += im;");
+            else {
+                if (d.nodes[0] != 0) e.line("br[" + S(d.nodes[0]) + "] += re; bi[" + S(d.nodes[0]) + "] += im;");
+                if (d.nodes[1] != 0) e.line("br[" + S(d.nodes[1]) + "] -= re; bi[" + S(d.nodes[1]) + "] -= im;");
+            }
+        }
+        --e.ind;
+        e.line("}");
+    }
+    e.line("double tr, ti;");
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        const std::string p = S(st.piv);
+        e.line("// step " + S(k) + ": pivot (" + S(lu.prow[k]) + "," + S(lu.pcol[k]) + ")");
+        e.line("if (Ar[" + p + "] == 0.0 && Ai[" + p + "] == 0.0) return false;   // \"matrix factorization failed\"");
+        e.line("tsb_crcp(Ar[" + p + "], Ai[" + p + "]);");
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            const std::string u = S(st.urow[ui]);
+            e.line("tr = Ar[" + u + "] * Ar[" + p + "] - Ai[" + u + "] * Ai[" + p + "]; ti = Ar[" + u + "] * Ai[" + p + "] + Ai[" + u + "] * Ar[" + p + "]; Ar[" + u + "] = tr; Ai[" + u + "] = ti;");
+            for (size_t li = 0; li < st.lcol.size(); ++li) {
+                const std::string l = S(st.lcol[li]), t = S(st.target[ui][li]);
+                e.line("Ar[" + t + "] -= Ar[" + u + "] * Ar[" + l + "] - Ai[" + u + "] * Ai[" + l + "]; Ai[" + t + "] -= Ar[" + u + "] * Ai[" + l + "] + Ai[" + u + "] * Ar[" + l + "];");
+            }
+        }
+    }
+    e.line("double cr[" + S(n + 1) + "], ci[" + S(n + 1) + "];");
+    for (int k = 1; k <= n; ++k) e.line("cr[" + S(k) + "] = br[" + S(lu.prow[k]) + "]; ci[" + S(k) + "] = bi[" + S(lu.prow[k]) + "];");
+    for (int k = 1; k <= n; ++k) {
+        const LuProgram::Step& st = lu.steps[k];
+        const std::string p = S(st.piv), ck = S(k);
+        e.line("tr = cr[" + ck + "] * Ar[" + p + "] - ci[" + ck + "] * Ai[" + p + "]; ti = cr[" + ck + "] * Ai[" + p + "] + ci[" + ck + "] * Ar[" + p + "]; cr[" + ck + "] = tr; ci[" + ck + "] = ti;");
+        for (size_t li = 0; li < st.lcol.size(); ++li) {
+            const std::string j = S(st.lrow_step[li]), l = S(st.lcol[li]);
+            e.line("cr[" + j + "] -= cr[" + ck + "] * Ar[" + l + "] - ci[" + ck + "] * Ai[" + l + "]; ci[" + j + "] -= cr[" + ck + "] * Ai[" + l + "] + ci[" + ck + "] * Ar[" + l + "];");
+        }
+    }
+    for (int k = n; k >= 1; --k) {
+        const LuProgram::Step& st = lu.steps[k];
+        for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+            const std::string j = S(st.ucol_step[ui]), u = S(st.urow[ui]), ck = S(k);
+            e.line("cr[" + ck + "] -= Ar[" + u + "] * cr[" + j + "] - Ai[" + u + "] * ci[" + j + "]; ci[" + ck + "] -= Ar[" + u + "] * ci[" + j + "] + Ai[" + u + "] * cr[" + j + "];");
+        }
+    }
+    for (int k = 1; k <= n; ++k) e.line("xr[" + S(lu.pcol[k]) + "] = cr[" + S(k) + "]; xi[" + S(lu.pcol[k]) + "] = ci[" + S(k) + "];");
+    e.line("return true;");
+    --e.ind;
+    e.line("}");
+    // result row of one frequency (ac.go:73-95, StoreACResult anlysis.go:87-111): magnitude = cmplx.Abs, phase in degrees
+    e.line("__device__ __forceinline__ void signals_ac(const double* xr, const double* xi, double* out) const {");
+    ++e.ind;
+    int c = 0;
+    auto emit_mp = [&](int idx) {
+        e.line("out[" + S(c) + "] = hypot(xr[" + S(idx) + "], xi[" + S(idx) + "]); out[" + S(c + 1) + "] = atan2(xi[" + S(idx) + "], xr[" + S(idx) + "]) * 180.0 / TSB_PI;");
+        c += 2;
+    };
+    for (int i = 1; i <= pl.n_nodes; ++i) emit_mp(i);
+    for (const Dev& d : pl.devs) if (d.kind == TSB_V) emit_mp(d.branch);
+    --e.ind;
+    e.line("}");
+}
+
 }  // namespace
 
 std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
@@ -709,6 +805,11 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("static constexpr bool HAS_TF = " + std::string(use_tf ? "true" : "false") + ";");
     if (use_tf) emit_tranfast(e, pl, cfg);
 
+    // ---- AC analysis (linear circuits) ----------------------------------------------------------------------
+    e.line("static constexpr int NCOL_AC = " + std::to_string(pl.num_columns(TSB_AN_AC)) + ";");
+    e.line("static constexpr bool HAS_AC = " + std::string(pl.has_nonlinear ? "false" : "true") + ";");
+    if (!pl.has_nonlinear) emit_ac(e, pl);
+
     // ---- operator level: the stamped system itself -----------------------------------------------------
     // mat.Clear(); ckt.Stamp(status); mat.LoadGmin(gmin) as a DENSE n x n matrix + right-hand side written to
     // global memory, instance-major (A[inst][row][col], b[inst][row], 0-based = external index - 1): what a
@@ -780,6 +881,26 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     --e.ind;
     e.line("}");
 
+    // the same as two decisions, without materialising the maximum: gt = maxLTE > trtol (reject), small = maxLTE < thr (the
+    // step may double).  maxLTE is the largest device LTE that is not NaN (a NaN never wins `lte > maxLTE`), or 0; the
+    // inductor's own LTE is math.Max(current, voltage): NaN when either is NaN unless the other is +Inf.
+    e.line("__device__ __forceinline__ void lte_flags(double dt, double rdt, double trtol, double thr, bool& gt, bool& small) {");
+    ++e.ind;
+    e.line("gt = false; small = 0.0 < thr;");
+    for (int di : pl.stamp_order) {
+        const Dev& d = pl.devs[di];
+        if (d.kind == TSB_C) {
+            e.line("{ const double l = tsb_cap_lte(P + " + std::to_string(d.p_off) + ", S + " + std::to_string(d.s_off) + ", dt, rdt); gt = gt | (l > trtol); small = small & !(l >= thr); }");
+        } else if (d.kind == TSB_L) {
+            e.line("{ double cu, vo; tsb_ind_lte2(S + " + std::to_string(d.s_off) + ", dt, rdt, cu, vo);");
+            e.line("  const bool nan = ((cu != cu) | (vo != vo)) & !((cu == TSB_INF) | (vo == TSB_INF));");
+            e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol))); small = small & !(!nan & ((cu >= thr) | (vo >= thr))); }");
+        }
+    }
+    e.line("(void)dt; (void)rdt; (void)trtol;");
+    --e.ind;
+    e.line("}");
+
     // ---- signals -----------------------------------------------------------------------------------
     e.line("__device__ __forceinline__ void signals(double* out) const {   // circuit.GetSolution (circuit.go:242-273)");
     ++e.ind;
@@ -840,6 +961,10 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("}");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_stamp(TsbArgs a) { tsb_stamp_body<false>(a); }");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_stamp_staged(TsbArgs a) { tsb_stamp_body<true>(a); }");
+    e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_ac(TsbArgs a) {");
+    e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
+    e.line("        if (base + threadIdx.x < a.n_run) tsb_run_ac_instance<Ckt>(a, tsb_slot_instance(a, base + threadIdx.x, true));");
+    e.line("}");
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK) tsb_dc(TsbArgs a) {");
     e.line("    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n_run; base += (long long)gridDim.x * blockDim.x)");
     e.line("        tsb_run_dc_instance<Ckt>(a, tsb_slot_instance(a, base + threadIdx.x, base + threadIdx.x < a.n_run), base + threadIdx.x < a.n_run);");

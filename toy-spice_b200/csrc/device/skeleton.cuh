@@ -85,6 +85,12 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #define TSB_OUT_STATS 2
 #define TSB_OUT_GRID 4
 
+#ifndef TSB_X_STATS_PRED
+#define TSB_X_STATS_PRED 1
+#endif
+#ifndef TSB_X_LTEFLAGS
+#define TSB_X_LTEFLAGS 1            // linear loop: truncation-error DECISIONS from predicates instead of selecting the maximum
+#endif
 extern __shared__ double tsb_smem[];
 
 // op.go:67-77 / tran.go:192-207: |new-old| <= reltol*max(|new|,|old|) + abstol for i = 1..n.
@@ -190,9 +196,17 @@ struct TsbSink {
                 for (int j = 1; j < NCOL; ++j) {
                     const double v = row[j];
                     double2 mm = sm[(2 * j) * TSB_BLOCK];
-                    mm.x = v < mm.x ? v : mm.x;
-                    mm.y = v > mm.y ? v : mm.y;
-                    sm[(2 * j) * TSB_BLOCK] = mm;
+                    if (TSB_X_STATS_PRED) {
+                        // two predicated 8-byte stores instead of four selects and an unconditional 16-byte store: an extreme
+                        // seldom moves, so most of them are predicated off (no shared-memory traffic at all)
+                        double* slot = reinterpret_cast<double*>(&sm[(2 * j) * TSB_BLOCK]);
+                        if (v < mm.x) slot[0] = v;
+                        if (v > mm.y) slot[1] = v;
+                    } else {
+                        mm.x = v < mm.x ? v : mm.x;
+                        mm.y = v > mm.y ? v : mm.y;
+                        sm[(2 * j) * TSB_BLOCK] = mm;
+                    }
                 }
             }
 #pragma unroll
@@ -250,6 +264,9 @@ struct TsbSink {
 #ifndef TSB_TGRID
 #define TSB_TGRID 0
 #endif
+#ifndef TSB_X_TG_EARLY
+#define TSB_X_TG_EARLY 1            // issue the table loads at the top of the attempt (in flight during the LTE test and the
+#endif                              // factorisation) instead of where their values are consumed
 // entry = [time, dt | key, SV[0] | SV[1], SV[2] | ...]: 32 bytes for a circuit with one source
 #define TSB_TG_HDR 3
 #define TSB_TG_NO_KEY (-3.0)       // key slot of an attempt the pilot rejected before it needed sources and key
@@ -278,10 +295,10 @@ __device__ __forceinline__ void tsb_prefetch_l1(const void* p) { asm volatile("p
 #define TSB_TG_LOOK_EVERY 16        // a reader that has caught up with the published count looks again every 16 attempts
 #endif
 #ifndef TSB_TG_CACHED
-#define TSB_TG_CACHED 1             // entries are read through L1 (published entries are immutable and a reader only ever
-#endif                              // requests sectors of published entries), optionally prefetched one attempt ahead
+#define TSB_TG_CACHED 0             // 0: entries are read from L2 (ld.global.cg) — measured FASTER than through L1 (rlc, 2^20
+#endif                              // instances: 219 vs 236 ms): the block's spilled registers live in L1 and table lines evict them
 #ifndef TSB_TG_PREFETCH
-#define TSB_TG_PREFETCH 1
+#define TSB_TG_PREFETCH 0           // L1 prefetch one attempt ahead (only with TSB_TG_CACHED)
 #endif
 #if TSB_TG_CACHED
 #define TSB_TG_LD(p) __ldca(p)
@@ -294,9 +311,10 @@ __device__ __forceinline__ void tsb_prefetch_l1(const void* p) { asm volatile("p
 // formatted-time de-duplication (anlysis.go:61-85; `last_key` < 0 = nothing stored yet), step growth.
 // HAVE_KEY: the caller already holds key(next_time) (tsb_tran_linear computes or looks it up with the step's other
 // time-only quantities); otherwise it is computed here.
-template <bool HAVE_KEY = false, class Ckt, class Sink>
+template <bool HAVE_KEY = false, bool HAVE_SMALL = false, class Ckt, class Sink>
 __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& sink, double& time, double& dt,
-                                                double next_time, double lte, TsbTimeKeyer& keyer, double& last_key, double key_in = 0.0) {
+                                                double next_time, double lte, TsbTimeKeyer& keyer, double& last_key, double key_in = 0.0,
+                                                bool lte_small = false) {
     c.load_state(dt);
     c.update_state();
     time = next_time;
@@ -312,7 +330,7 @@ __device__ __forceinline__ void tsb_accept_step(const TsbArgs& a, Ckt& c, Sink& 
     }
     if (time < a.tstop && dt < a.maxstep) {
         // math.Min of two finite positive numbers (dt is never NaN): a plain select
-        const double grown = lte < a.trtol / 100 ? dt * 2 : dt * 1.1;
+        const double grown = (HAVE_SMALL ? lte_small : lte < a.trtol / 100) ? dt * 2 : dt * 1.1;
         dt = grown < a.maxstep ? grown : a.maxstep;
     }
 }
@@ -358,12 +376,21 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
             look = k < tg_limit;
             if (TSB_TG_PREFETCH && look) tsb_prefetch_l1(a.tgrid + (long long)k * ND);      // consumed after the factorisation
         }
+        double2 e0 = make_double2(0.0, 0.0), e1 = make_double2(0.0, 0.0);
+        if (TSB_TGRID && TSB_X_TG_EARLY && look) {          // in flight during the LTE test and the factorisation
+            const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)k * ND);
+            e0 = TSB_TG_LD(e); e1 = TSB_TG_LD(e + 1);
+        }
         double next_time = time + dt;
         if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
         __builtin_assume(dt > 0.0);               // time < tstop and dt only halves while > minstep: lets the dt > 0 guards fold
         const double rdt = tsb_rcp_dt(dt);        // the one division by the time step of this attempt
-        const double lte = c.lte(dt, rdt);
-        if (lte > a.trtol && dt > a.minstep) {
+        // the two decisions the truncation error feeds (reject; how the step grows), NaN semantics of the reference's maximum kept
+        double lte = 0.0;
+        bool lte_gt, lte_small;
+        if (TSB_X_LTEFLAGS) c.lte_flags(dt, rdt, a.trtol, a.trtol / 100, lte_gt, lte_small);
+        else { lte = c.lte(dt, rdt); lte_gt = lte > a.trtol; lte_small = lte < a.trtol / 100; }
+        if (lte_gt && dt > a.minstep) {
             if (tg_pub && k < a.tgrid_cap) {      // the pilot rejected this attempt before it needed sources or key
                 double2* e = reinterpret_cast<double2*>(a.tgrid + (long long)k * ND);
                 __stcg(e, make_double2(t_tag, dt_tag));
@@ -381,7 +408,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
             bool hit = false;
             if (TSB_TGRID && look) {
                 const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)k * ND);
-                const double2 e0 = TSB_TG_LD(e), e1 = TSB_TG_LD(e + 1);
+                if (!TSB_X_TG_EARLY) { e0 = TSB_TG_LD(e); e1 = TSB_TG_LD(e + 1); }
                 hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(t_tag)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt_tag))) == 0;
                 if (!hit) tg_limit = -1;                    // this instance has left the pilot's grid: stop looking
                 hit = hit && e1.x != TSB_TG_NO_KEY;
@@ -418,7 +445,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
             status = TSB_ST_TRAN_FAILED; fail_at = time;
             break;
         }
-        tsb_accept_step<true>(a, c, sink, time, dt, next_time, lte, keyer, last_key, key);
+        tsb_accept_step<true, true>(a, c, sink, time, dt, next_time, lte, keyer, last_key, key, lte_small);
         ++n_acc;
     }
     if (tg_pub) { const int k = n_acc + n_rej; tsb_st_release(a.tgrid_pub, (unsigned long long)(k < a.tgrid_cap ? k : a.tgrid_cap)); }
@@ -823,6 +850,44 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
     a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
     a.counters[6 * a.n_inst + inst] = n_sol;                  // factor + solve passes executed (the discarded pass solves nothing)
     a.counters[7 * a.n_inst + inst] = sink.n_rows;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AC analysis (ac.go:51-98): for every frequency of the sweep (the same list for every instance) one complex solve of
+// the small-signal system; a row is [FREQ, |V(n)|, phase(V(n)) in degrees ..., |I(Vsrc)|, phase ...].  Linear circuits
+// only (see plan.cpp: device_ac_entries).  A zero pivot is the reference's "matrix solve error at f=...": the instance
+// keeps the rows stored so far and fails there.
+#define TSB_ST_AC_FAILED 5
+template <class Ckt>
+__device__ __forceinline__ void tsb_run_ac_instance(const TsbArgs& a, long long inst) {
+    if constexpr (Ckt::HAS_AC) {
+        constexpr int N = Ckt::N;
+        Ckt c;
+        TsbSink<Ckt::NCOL_AC> sink(a, inst);
+        c.load(a, inst);
+        sink.begin(inst);
+        int status = TSB_ST_OK, n_sol = 0;
+        double fail_at = 0.0;
+        for (int k = 0; k < a.n_sweep; ++k) {
+            const double freq = a.sweep[k];
+            const double omega = 6.283185307179586 * freq;           // 2 * math.Pi * status.Frequency
+            double xr[N + 1], xi[N + 1];
+            ++n_sol;
+            if (!c.solve_ac(omega, xr, xi)) { status = TSB_ST_AC_FAILED; fail_at = freq; break; }
+            double row[Ckt::NCOL_AC];
+            row[0] = freq;
+            c.signals_ac(xr, xi, row + 1);
+            sink.push(row);
+        }
+        if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
+        sink.finish();
+        a.status[inst] = status;
+        for (int q = 0; q < 5; ++q) a.counters[q * a.n_inst + inst] = 0;
+        a.counters[3 * a.n_inst + inst] = n_sol;
+        a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+        a.counters[6 * a.n_inst + inst] = n_sol;
+        a.counters[7 * a.n_inst + inst] = sink.n_rows;
+    }
 }
 
 #endif  // TSB_SKELETON_CUH

@@ -103,6 +103,12 @@ struct Deck {
     bool uic = false;
     std::string dc_src;
     double dc_start = 0, dc_stop = 0, dc_inc = 0;
+    std::string dc2_src;                       // hardening: second .dc source (nested sweep)
+    double dc2_start = 0, dc2_stop = 0, dc2_inc = 0;
+    std::string ac_sweep;
+    int ac_points = 0;
+    double ac_fstart = 0, ac_fstop = 0;
+    bool ended = false;                        // hardening: .end seen
 };
 
 void parse_model(Deck& d, std::vector<std::string> f) {   // parser.go:285-451
@@ -177,9 +183,16 @@ void parse_dot(Deck& d, const std::string& line) {   // parser.go:176-283
         if (d.tmax == 0) d.tmax = d.tstep;
         return;
     }
-    if (cmd == ".ac") {
+    if (cmd == ".ac") {                       // parser.go:238-261
         d.analysis = TSB_AN_AC;
         if (f.size() < 5) throw ParseError{"insufficient AC parameters, need sweep type, points, fstart, and fstop"};
+        d.ac_sweep = upper(f[1]);
+        if (d.ac_sweep != "DEC" && d.ac_sweep != "OCT" && d.ac_sweep != "LIN") throw ParseError{"invalid sweep type: " + d.ac_sweep};
+        char* endp = nullptr;
+        long pts = strtol(f[2].c_str(), &endp, 10);
+        if (endp == f[2].c_str() || *endp) throw ParseError{"invalid number of points: " + f[2]};
+        d.ac_points = (int)pts;
+        d.ac_fstart = parse_value(f[3]); d.ac_fstop = parse_value(f[4]);
         return;
     }
     if (cmd == ".dc") {
@@ -187,6 +200,9 @@ void parse_dot(Deck& d, const std::string& line) {   // parser.go:176-283
         if (f.size() < 5) throw ParseError{"insufficient DC sweep parameters"};
         d.dc_src = f[1];
         d.dc_start = parse_value(f[2]); d.dc_stop = parse_value(f[3]); d.dc_inc = parse_value(f[4]);
+        // HARDENING beyond the reference (its parser stops after the first source; cmd/spice/main.go:325 is ready for
+        // DCParam.Source2): `.dc src1 start stop inc src2 start stop inc` -> nested sweep, src1 the outer loop
+        if (f.size() >= 9) { d.dc2_src = f[5]; d.dc2_start = parse_value(f[6]); d.dc2_stop = parse_value(f[7]); d.dc2_inc = parse_value(f[8]); }
         return;
     }
     throw ParseError{"unsupported analysis type: " + f[0]};
@@ -244,6 +260,10 @@ Element parse_element(const std::string& line) {   // parser.go:453-561
     if (t == "D") {
         e.nodes = {f[1], f[2]};
         if (f.size() > 3) e.params["model"] = f[3];
+        for (size_t i = 4; i < f.size(); ++i) {      // HARDENING (parser.go:530 "TODO: Inline parameters"): D1 a k MODEL Is=.. N=.. Tt=..
+            std::vector<std::string> kv = split(f[i], '=');
+            if (kv.size() == 2) e.params["inline_" + lower(kv[0])] = kv[1];
+        }
         return e;
     }
     if (t == "Q") {
@@ -269,6 +289,12 @@ Element parse_element(const std::string& line) {   // parser.go:453-561
 
 void parse_line(Deck& d, const std::string& line_in) {   // parser.go:160-174
     std::string line = std::regex_replace(line_in, std::regex(R"(\s+)"), " ");
+    if (d.ended) return;
+    {   // HARDENING (parser.go:155 "TODO: .END"): the deck ends here; the reference reports "unsupported analysis type: .end"
+        std::string t = lower(line);
+        while (!t.empty() && t.back() == ' ') t.pop_back();
+        if (t == ".end") { d.ended = true; return; }
+    }
     if (starts_with(line, ".")) { parse_dot(d, line); return; }
     d.elements.push_back(parse_element(line));
 }
@@ -345,8 +371,8 @@ void source_params(const Element& e, Dev& dev) {   // parser.go:836-911, 917-103
         return;
     }
     if (t == "ac") {          // NewACVoltageSource(name, nodes, 0, mag, phase): a DC 0 source in OP/DC/tran
-        parse_value(e.params.at("phase"));
-        dev.ip = {TSB_SRC_DC}; dev.p = {0.0};
+        // magnitude and phase (degrees) ride along behind the DC value: the AC analysis reads them (vsource.go:155-177)
+        dev.ip = {TSB_SRC_DC}; dev.p = {0.0, e.value, parse_value(e.params.at("phase"))};
         return;
     }
     throw ParseError{"unsupported source type: " + t};
@@ -416,6 +442,8 @@ int plan_from_netlist(const std::string& text, Plan& plan, std::string& err) {
                 double is = 1e-14, n = 1.0, tt = 0.0;              // diode.go:66-84
                 const Model* m; model_of(m);
                 if (m) { is = getp(m->params, "is", is); n = getp(m->params, "n", n); tt = getp(m->params, "tt", tt); }
+                auto inl = [&](const char* k, double& v) { auto it = e.params.find(std::string("inline_") + k); if (it != e.params.end()) v = parse_value(it->second); };
+                inl("is", is); inl("n", n); inl("tt", tt);
                 dev.p = {is, n, tt};
             } else if (t == "Q") {
                 dev.kind = TSB_Q;
@@ -481,12 +509,20 @@ int plan_from_netlist(const std::string& text, Plan& plan, std::string& err) {
         plan.uic = d.uic ? 1 : 0;
         plan.dc[0] = d.dc_start; plan.dc[1] = d.dc_stop; plan.dc[2] = d.dc_inc;
         plan.dc_src_name = d.dc_src;
-        plan.dc_src_dev = -1;
+        plan.dc_src_dev = -1; plan.dc2_src_dev = -1;
         if (d.analysis == TSB_AN_DC) {
             auto di = index_of.find(d.dc_src);
             if (di == index_of.end() || plan.devs[di->second].kind != TSB_V) throw ParseError{"source " + d.dc_src + " not found"};
             plan.dc_src_dev = di->second;
+            if (!d.dc2_src.empty()) {
+                auto d2 = index_of.find(d.dc2_src);
+                if (d2 == index_of.end() || plan.devs[d2->second].kind != TSB_V) throw ParseError{"source " + d.dc2_src + " not found"};
+                plan.dc2_src_dev = d2->second;
+                plan.dc2[0] = d.dc2_start; plan.dc2[1] = d.dc2_stop; plan.dc2[2] = d.dc2_inc;
+            }
         }
+        plan.ac_sweep = d.ac_sweep == "DEC" ? 0 : d.ac_sweep == "OCT" ? 1 : 2;
+        plan.ac_points = d.ac_points; plan.ac_f[0] = d.ac_fstart; plan.ac_f[1] = d.ac_fstop;
         return TSB_OK;
     } catch (ParseError& e) {
         err = e.msg;

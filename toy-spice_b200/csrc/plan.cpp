@@ -116,8 +116,59 @@ void device_stamp_entries(const Plan& plan, int di, std::vector<StampEntry>& out
     }
 }
 
+// StampAC of every device kind (AddComplexElement calls, ground rows / columns skipped like the reference's guards).
+//   code 0: (+-g, 0)            resistor.go:41-54
+//   code 1: (0, +-omega*C)      capacitor.go:48-66
+//   code 2: (0, +-omega*L)      inductor.go:43-57 — an ADMITTANCE j*omega*L between the nodes; the branch row stays empty,
+//                               so every circuit with an inductor is singular in the reference's AC analysis
+//   code 3: (+-1, 0)            vsource.go:155-177 incidence
+//   code 4: (0, -+1/(omega*L0)) magnetic.go:276-300 (air-core value); branch row empty as well
+//   code 5 + q: (0, +-omega*M_q) mutual.go:122-185, pair q of the coupling
+// Nonlinear devices stamp small-signal values taken from the state their operating point left behind — which the
+// reference computes on a COMPLEX matrix with a real-indexed right-hand side (matrix/circuit.go:99-105 vs :126-150):
+// not reproducible without the un-vendored module's vector layout, so AC analysis is offered for linear circuits only.
+void device_ac_entries(const Plan& plan, int di, std::vector<AcEntry>& out) {
+    const Dev& d = plan.devs[di];
+    auto quad = [&](int n1, int n2, int code) {          // (n1,n1) (n1,n2) | (n2,n1) (n2,n2) in the resistor's call order
+        if (n1 != 0) { out.push_back({n1, n1, code, +1}); if (n2 != 0) out.push_back({n1, n2, code, -1}); }
+        if (n2 != 0) { if (n1 != 0) out.push_back({n2, n1, code, -1}); out.push_back({n2, n2, code, +1}); }
+    };
+    auto quad_c = [&](int n1, int n2, int code) {        // capacitor / inductor order: (n1,n1) (n1,n2) | (n2,n2) (n2,n1)
+        if (n1 != 0) { out.push_back({n1, n1, code, +1}); if (n2 != 0) out.push_back({n1, n2, code, -1}); }
+        if (n2 != 0) { out.push_back({n2, n2, code, +1}); if (n1 != 0) out.push_back({n2, n1, code, -1}); }
+    };
+    const int* n = d.nodes;
+    switch (d.kind) {
+    case TSB_R: quad(n[0], n[1], 0); break;
+    case TSB_C: quad_c(n[0], n[1], 1); break;
+    case TSB_L: quad_c(n[0], n[1], 2); break;
+    case TSB_LCORE: quad(n[0], n[1], 4); break;
+    case TSB_V:
+        if (n[0] != 0) { out.push_back({d.branch, n[0], 3, +1}); out.push_back({n[0], d.branch, 3, +1}); }
+        if (n[1] != 0) { out.push_back({d.branch, n[1], 3, -1}); out.push_back({n[1], d.branch, 3, -1}); }
+        break;
+    case TSB_K: {
+        int m = (int)d.ip.size(), q = 0;
+        for (int i = 0; i < m; ++i)
+            for (int j = i + 1; j < m; ++j, ++q) {
+                const int* a = plan.devs[d.ip[i]].nodes; const int* b = plan.devs[d.ip[j]].nodes;
+                auto el = [&](int r, int c, double sg) { if (r > 0 && c > 0) out.push_back({r, c, 5 + q, sg}); };
+                el(a[0], b[0], +1); el(a[0], b[1], -1); el(a[1], b[0], -1); el(a[1], b[1], +1);
+                el(b[0], a[0], +1); el(b[0], a[1], -1); el(b[1], a[0], -1); el(b[1], a[1], +1);
+            }
+        break;
+    }
+    default: break;
+    }
+}
+
 int Plan::num_columns(int an) const {
     if (an == TSB_AN_OP) return n_nodes + n_branches;
+    if (an == TSB_AN_AC) {            // FREQ, then magnitude and phase of every node voltage and voltage-source current (ac.go:76-95)
+        int nv = 0;
+        for (const Dev& d : devs) if (d.kind == TSB_V) ++nv;
+        return 1 + 2 * (n_nodes + nv);
+    }
     int nr = 0;
     for (const Dev& d : devs) if (d.kind == TSB_R) ++nr;
     return (an == TSB_AN_DC2 ? 2 : 1) + n_nodes + n_branches + nr;     // nested sweep: SWEEP1, SWEEP2 (dc.go:272-288)
@@ -125,6 +176,16 @@ int Plan::num_columns(int an) const {
 
 std::string Plan::column_name(int an, int col) const {
     int k = col;
+    if (an == TSB_AN_AC) {            // StoreACResult (anlysis.go:87-111): <key>_MAG, <key>_PHASE
+        if (k == 0) return "FREQ";
+        --k;
+        const char* suffix = (k & 1) ? "_PHASE" : "_MAG";
+        k /= 2;
+        if (k < n_nodes) return ((int)node_names.size() > k + 1 ? "V(" + node_names[k + 1] + ")" : "V(" + std::to_string(k + 1) + ")") + suffix;
+        k -= n_nodes;
+        for (const Dev& d : devs) if (d.kind == TSB_V) { if (k == 0) return "I(" + d.name + ")" + suffix; --k; }
+        return "?";
+    }
     if (an != TSB_AN_OP) {
         if (k == 0) return an == TSB_AN_TRAN ? "TIME" : "SWEEP1";
         --k;
@@ -345,11 +406,12 @@ static void build_tranfast(Plan& pl, Nominal& nom) {
                 if (std::fabs(val[r][c]) < 1e-3 * colmax) continue;
                 // a variant entry in the pivot's column or row may be arbitrarily large: only rows / columns whose other
                 // live entries are all invariant qualify, except that the +-1 incidence pivots of sources are exact
+                // (a row or column singleton needs no such care: eliminating it updates no other matrix entry at all)
+                long cost = (long)(rc - 1) * (cc - 1);
                 bool clean = true;
                 for (int i = 1; i <= n; ++i) if (i != r && !rdone[i] && on[i][c] && var[i][c]) clean = false;
                 for (int j = 1; j <= n; ++j) if (j != c && !cdone[j] && on[r][j] && var[r][j]) clean = false;
-                if (!clean) continue;
-                long cost = (long)(rc - 1) * (cc - 1);
+                if (!clean && cost != 0) continue;
                 double mag = std::fabs(val[r][c]);
                 bool better = best < 0 || cost < best || (cost == best && ((r == c) > (br == bc))) ||
                               (cost == best && (r == c) == (br == bc) && mag > bmag);
@@ -525,6 +587,19 @@ int plan_finalize(Plan& pl) {
         // BJT circuits run dense so that Inf/NaN propagate through the solve exactly as they do
         // through the reference's structurally dense matrix.
         build_lu_program(n, pat, pl.order_main, pl.has_bjt, pl.lu_main);
+    }
+    {   // AC analysis: same order, pattern = what StampAC touches
+        std::vector<std::pair<int, int>> pat;
+        std::set<std::pair<int, int>> seen;
+        for (int di : pl.stamp_order) {
+            std::vector<AcEntry> ae;
+            device_ac_entries(pl, di, ae);
+            for (const AcEntry& a : ae) if (seen.insert({a.row, a.col}).second) pat.push_back({a.row, a.col});
+        }
+        // the pivots of the frozen order exist in the reference's (structurally dense) matrix whether StampAC touches them or
+        // not: an untouched pivot is an exact zero, "matrix factorization failed"
+        for (int k = 1; k <= n; ++k) if (seen.insert({pl.order_main.prow[k], pl.order_main.pcol[k]}).second) pat.push_back({pl.order_main.prow[k], pl.order_main.pcol[k]});
+        build_lu_program(n, pat, pl.order_main, false, pl.lu_ac);
     }
     {
         Nominal nom2(pl);            // fresh device state: the order must not depend on where the replay above left it

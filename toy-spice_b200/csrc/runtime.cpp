@@ -70,7 +70,7 @@ struct TsbArgsHost {
 
 struct KernelModule {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t optran = nullptr, dc = nullptr, stamp = nullptr, stamp_staged = nullptr;
+    cudaKernel_t optran = nullptr, dc = nullptr, stamp = nullptr, stamp_staged = nullptr, ac = nullptr;
     int info_regs = -1, info_spill = -1, min_blocks = 0;
 };
 
@@ -413,6 +413,7 @@ int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** o
     CU(ctx, cudaLibraryGetKernel(&m.dc, m.lib, "tsb_dc"));
     CU(ctx, cudaLibraryGetKernel(&m.stamp, m.lib, "tsb_stamp"));
     CU(ctx, cudaLibraryGetKernel(&m.stamp_staged, m.lib, "tsb_stamp_staged"));
+    CU(ctx, cudaLibraryGetKernel(&m.ac, m.lib, "tsb_ac"));
     m.info_regs = info.regs; m.info_spill = info.spill_st; m.min_blocks = o.min_blocks;
     ctx->modules[key] = m;
     *out = &ctx->modules[key];
@@ -510,7 +511,7 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
 int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args, bool persistent = false, int min_blocks = 0) {
     tsb_ctx* ctx = b->ctx;
     int block = o.block_size > 0 ? o.block_size : 128;
-    const int ncol_smem = b->plan->p.num_columns(b->analysis == TSB_AN_DC2 ? TSB_AN_DC2 : TSB_AN_TRAN);
+    const int ncol_smem = b->plan->p.num_columns(b->analysis == TSB_AN_DC2 ? TSB_AN_DC2 : b->analysis == TSB_AN_AC ? TSB_AN_AC : TSB_AN_TRAN);
     size_t smem = (args.out_flags & (TSB_OUT_STATS | TSB_OUT_GRID)) ? (size_t)4 * ncol_smem * block * sizeof(double) : 0;
     if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = (args.n_run + block - 1) / block;
@@ -889,6 +890,15 @@ int tsb_plan_analysis(const tsb_plan* plan, int* analysis, double tran[4], int* 
     if (dc) for (int i = 0; i < 3; ++i) dc[i] = plan->p.dc[i];
     return TSB_OK;
 }
+int tsb_plan_analysis2(const tsb_plan* plan, int* dc2_src_dev, double dc2[3], int* ac_sweep, int* ac_points, double ac_f[2]) {
+    if (!plan) return TSB_E_INVALID;
+    if (dc2_src_dev) *dc2_src_dev = plan->p.dc2_src_dev;
+    if (dc2) for (int i = 0; i < 3; ++i) dc2[i] = plan->p.dc2[i];
+    if (ac_sweep) *ac_sweep = plan->p.ac_sweep;
+    if (ac_points) *ac_points = plan->p.ac_points;
+    if (ac_f) { ac_f[0] = plan->p.ac_f[0]; ac_f[1] = plan->p.ac_f[1]; }
+    return TSB_OK;
+}
 int tsb_plan_structure(const tsb_plan* plan, int* ext2int, int* pivot_row, int* pivot_col) {
     if (!plan || !plan->p.finalized) return TSB_E_INVALID;
     int n = plan->p.n();
@@ -1153,6 +1163,44 @@ int tsb_run_dc2(tsb_batch* b, int src1_dev, double start1, double stop1, double 
                 double inc2, int out_flags, const tsb_opts* opts) {
     if (src2_dev < 0) return fail(b ? b->ctx : nullptr, TSB_E_INVALID, "source not found");
     return run_dc_impl(b, src1_dev, start1, stop1, inc1, src2_dev, start2, stop2, inc2, out_flags, opts);
+}
+
+// AC analysis (analysis.NewAC + Setup + Execute, ac.go:21-126): frequency points as generateFrequencyPoints makes them
+// (n_points in TOTAL between fstart and fstop, on a logarithmic or linear axis), one complex solve per point and instance.
+int tsb_run_ac(tsb_batch* b, int sweep_type, int n_points, double fstart, double fstop, int out_flags, const tsb_opts* opts) {
+    int rc = check_batch(b); if (rc != TSB_OK) return rc;
+    tsb_ctx* ctx = b->ctx;
+    const Plan& p = b->plan->p;
+    if (p.has_nonlinear)
+        return fail(ctx, TSB_E_UNSUPPORTED, "AC analysis of a circuit with nonlinear devices: the reference takes their small-signal values from an "
+                                             "operating point it solves on a complex matrix with a real-indexed right-hand side (matrix/circuit.go:99-105, "
+                                             ":126-150); that state is an artefact of the un-vendored sparse module and is not reproduced");
+    if (sweep_type < 0 || sweep_type > 2 || n_points < 1 || n_points > (1 << 20)) return fail(ctx, TSB_E_INVALID, "invalid sweep type or number of points");
+    if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID applies to transient analysis only");
+    if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
+    std::vector<double> f((size_t)n_points);
+    // ac.go:100-126 (a single point divides by zero there: step = NaN, the one frequency is NaN; kept)
+    if (sweep_type == 0) {
+        const double ls = log10(fstart), le = log10(fstop), step = (le - ls) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = pow(10.0, ls + (double)i * step);
+    } else if (sweep_type == 1) {
+        const double ls = log2(fstart), le = log2(fstop), step = (le - ls) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = pow(2.0, ls + (double)i * step);
+    } else {
+        const double step = (fstop - fstart) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = fstart + (double)i * step;
+    }
+    tsb_opts o = resolve(opts, p);
+    CU(ctx, cudaSetDevice(ctx->device));
+    KernelModule* m = nullptr;
+    if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
+    if ((rc = alloc_results(b, TSB_AN_AC, out_flags, (out_flags & TSB_OUT_WAVE) ? (int64_t)n_points : 0, n_points)) != TSB_OK) return rc;
+    TsbArgsHost a;
+    if ((rc = fill_common(b, o, a)) != TSB_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(b->d_sweep, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));     // `f` is a stack vector
+    a.analysis = TSB_AN_AC; a.sweep = b->d_sweep; a.n_sweep = n_points;
+    return launch(b, o, m->ac, a);
 }
 
 // Operator level: the device-stamp kernel on its own.  Writes, for every instance, the dense MNA system the reference

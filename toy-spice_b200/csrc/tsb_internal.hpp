@@ -76,6 +76,10 @@ struct Plan {
     int dc_src_dev = -1;
     double dc[3] = {0, 0, 0};
     std::string dc_src_name;
+    int dc2_src_dev = -1;                           // second .dc source (nested sweep), -1: none
+    double dc2[3] = {0, 0, 0};
+    int ac_sweep = 0, ac_points = 0;                // .ac card: 0 DEC, 1 OCT, 2 LIN; total number of points; fstart, fstop
+    double ac_f[2] = {0, 0};
     // finalize results
     bool finalized = false;
     int n_params = 0, n_state = 0, n_src = 0, n_derived = 0;
@@ -88,6 +92,7 @@ struct Plan {
     // Transient solves of the fast build (static condensation, plan.cpp: build_tranfast): an elimination order that
     // takes the pivots whose value is the same in every solve of a run first, and per entry of lu_tf.pos whether its
     // STAMPED value changes from solve to solve (time step, device state)
+    LuProgram lu_ac;                                // AC analysis: the OP order (the reference factors first in its OP) over the StampAC pattern
     LuProgram lu_tf;
     std::vector<char> tf_variant;
     bool has_tranfast = false;
@@ -105,6 +110,9 @@ int plan_from_netlist(const std::string& text, Plan& plan, std::string& err);
 // plan.cpp
 int plan_finalize(Plan& plan);
 void device_stamp_entries(const Plan& plan, int dev_index, std::vector<StampEntry>& out);
+// AddComplexElement calls of one device's StampAC in call order: (row, col, code); codes are listed at the definition.
+struct AcEntry { int row, col, code; double sign; };
+void device_ac_entries(const Plan& plan, int dev_index, std::vector<AcEntry>& out);
 int device_num_outputs(const Dev& d);
 // codegen.cpp
 struct CodegenConfig {
