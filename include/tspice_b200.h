@@ -128,13 +128,19 @@ typedef struct tsb_opts {
 enum {
     TSB_OUT_WAVE = 1,   /* every stored row: wave[row][column][instance]          */
     TSB_OUT_STATS = 2,  /* min / max / sum / last per column over the stored rows */
-    TSB_OUT_GRID = 4    /* transient only: the reference's result series resampled ON THE DEVICE onto the fixed grid
+    TSB_OUT_GRID = 4,   /* transient only: the reference's result series resampled ON THE DEVICE onto the fixed grid
                            t_k = tstart + (k+1)*grid_dt <= tstop (k = 0..), by linear interpolation between
                            consecutive stored rows (constant before the first / after the last one):
                            wave[k][column][instance], column 0 = t_k.  This is how instances whose adaptive step
                            sequences differ are compared point by point, and what makes waveform output of the
                            ~2e4-step inductor decks fit in HBM for 1M+ instances.  Implies TSB_OUT_STATS; excludes
                            TSB_OUT_WAVE.  rows[inst] = grid rows written; counters[7] = rows of the reference series */
+    TSB_OUT_AC_REFREAD = 8  /* AC analysis only, a modifier: read the solution out as the reference's accessor does when the
+                           un-vendored sparse module follows Sparse 1.3's interleaved vectors — GetComplexSolution(i) returns
+                           (solution[i], solution[i+Size]) (matrix/circuit.go:168-173) while the vector is laid out
+                           solution[2k] = re x_k, solution[2k+1] = im x_k (:41-44, :85-97).  Default (flag clear): entry i is
+                           (re x_i, im x_i) — what the accessor means if the module returns split halves.  The module's
+                           source is not available, so both read-outs are offered. */
 };
 
 void tsb_default_opts(tsb_opts* o);
@@ -234,15 +240,22 @@ int tsb_run_dc(tsb_batch* batch, int src_dev, double start, double stop, double 
 int tsb_run_dc2(tsb_batch* batch, int src1_dev, double start1, double stop1, double inc1, int src2_dev, double start2,
                 double stop2, double inc2, int out_flags, const tsb_opts* opts);
 /* AC analysis (analysis.NewAC(fStart, fStop, nPoints, pType) + Setup + Execute, ac.go:21-126) of circuits WITHOUT nonlinear
- * devices: n_points frequencies in total between fstart and fstop (sweep_type 0 DEC / 1 OCT: logarithmic, 2 LIN), one complex
- * solve per frequency and instance with the StampAC values of every device — the reference's quirks included: an inductor is
- * stamped as the ADMITTANCE j*omega*L between its nodes and leaves its branch row empty (inductor.go:43-57), so a circuit with
- * an inductor fails with TSB_ST_AC_FAILED at the first frequency, as the reference's "matrix solve error" does.
+ * devices: n_points frequencies in total between fstart and fstop (sweep_type 0 DEC / 1 OCT: logarithmic, 2 LIN; Go's
+ * math.Log10 / Log2 / Pow restated for the point values), one complex solve per frequency and instance in the pivot order the
+ * operating point of ACAnalysis.Setup froze, with what every device's Stamp does in Mode == ACAnalysis — quirks included:
+ *   - an inductor is stamped as the ADMITTANCE j*omega*L between its nodes and leaves its branch row empty (inductor.go:43-57);
+ *   - Mutual and MagneticInductor stamp nothing at all (their Stamp has no AC case, mutual.go:63-65, magnetic.go:205-273; the
+ *     StampAC methods they define are never called by circuit.Stamp, circuit.go:165-176);
+ *   so a circuit with any inductor fails with TSB_ST_AC_FAILED at the first frequency, as the reference's "matrix solve error
+ *   at f=..." does (rows stored so far are kept; counters[5] = that frequency).  RC networks with V / I sources work.
  * Rows: [FREQ, V(node)_MAG, V(node)_PHASE (degrees) ..., I(vsource)_MAG, I(vsource)_PHASE ...] (StoreACResult,
- * anlysis.go:87-111; column names: analysis code TSB_AN_AC).  AC magnitude / phase of a source: parameters 1 and 2 of a DC
- * source (`V1 1 0 AC mag [phase]`, vsource.go:98-111), sweepable like any other.  Circuits with nonlinear devices:
- * TSB_E_UNSUPPORTED (their small-signal values come from an operating point the reference solves on a complex matrix with
- * a real-indexed right-hand side — an artefact of the un-vendored sparse module, not reproduced). */
+ * anlysis.go:87-111: cmplx.Abs = Go's math.Hypot, cmplx.Phase*180/pi; column names: analysis code TSB_AN_AC).  AC magnitude /
+ * phase of a source: parameters 1 and 2 of a DC source (`V1 1 0 AC mag [phase]`, vsource.go:98-111), sweepable per instance
+ * like any other parameter.  out_flags: TSB_OUT_WAVE and / or TSB_OUT_STATS, optionally | TSB_OUT_AC_REFREAD.
+ * Circuits with nonlinear devices: TSB_E_UNSUPPORTED.  The reference runs their operating point on the COMPLEX matrix with a
+ * real-indexed right-hand side (AddRHS writes rhs[i], SolveComplex reads re/im pairs; matrix/circuit.go:99-105 vs :126-150),
+ * Bjt.Stamp never dispatches to StampAC (bjt.go:315-374), and the small-signal values of diodes and MOSFETs come from that
+ * scrambled point: a result that depends on the vector layout of a module whose source is not available. */
 int tsb_run_ac(tsb_batch* batch, int sweep_type, int n_points, double fstart, double fstop, int out_flags, const tsb_opts* opts);
 /* Block until the last run has finished (runs are asynchronous on the context's stream). */
 int tsb_batch_sync(tsb_batch* batch);

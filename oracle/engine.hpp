@@ -31,7 +31,7 @@ enum Mode { OP_MODE = 0, TRAN_MODE = 1, AC_MODE = 2, DC_MODE = 3 };   // device.
 
 // device.go:83-94 (only the fields that are ever read)
 struct Status {
-    double Time = 0, TimeStep = 0, Gmin = 0;
+    double Time = 0, TimeStep = 0, Gmin = 0, Frequency = 0;
     int Mode = OP_MODE;
     double Temp = 0;
 };
@@ -41,8 +41,12 @@ struct CircuitMatrix {
     int Size;
     Sparse13 m;
     std::vector<double> rhs, sol;
+    // AC analysis (a circuit built with isComplex, matrix/circuit.go:20-55): the LOGICAL complex right-hand side and solution,
+    // entry i = re[i] + j*im[i].  The reference keeps them interleaved in one float64 slice (AddComplexRHS: rhs[2i], rhs[2i+1]);
+    // what that does to its read-out is in ACAnalysis::Execute.
+    std::vector<double> rhs_im, sol_re, sol_im;
     long n_solves = 0;
-    explicit CircuitMatrix(int size) : Size(size), m(size), rhs(size + 1, 0.0), sol(size + 1, 0.0) {}
+    explicit CircuitMatrix(int size) : Size(size), m(size), rhs(size + 1, 0.0), sol(size + 1, 0.0), rhs_im(size + 1, 0.0) {}
     void SetupElements() {                       // circuit.go:57-63
         for (int i = 1; i <= Size; ++i) for (int j = 1; j <= Size; ++j) m.get_element(i, j);
     }
@@ -54,12 +58,29 @@ struct CircuitMatrix {
         if (i <= 0 || i > Size) return;
         rhs[i] += v;
     }
+    void AddComplexElement(int i, int j, double re, double im) {   // :73-83
+        if (i <= 0 || j <= 0 || i > Size || j > Size) return;
+        m.get_element(i, j) += re;
+        m.get_element_imag(i, j) += im;
+    }
+    void AddComplexRHS(int i, double re, double im) {              // :85-97
+        if (i <= 0 || i > Size) return;
+        rhs[i] += re;
+        rhs_im[i] += im;
+    }
+    bool SolveComplex() {                        // :126-150 with config.Complex
+        ++n_solves;
+        if (m.factor_complex() >= SP_ZERO_DIAG) return false;
+        m.solve_complex(rhs, rhs_im, sol_re, sol_im);
+        return true;
+    }
     void LoadGmin(double gmin) {                 // :107-114
         for (int i = 1; i <= Size; ++i) if (double* d = m.diag(i)) *d += gmin;
     }
     void Clear() {                               // :116-124
         m.clear();
         std::fill(rhs.begin(), rhs.end(), 0.0);
+        std::fill(rhs_im.begin(), rhs_im.end(), 0.0);
     }
     bool Solve() {                               // :126-150
         ++n_solves;
@@ -103,6 +124,11 @@ struct Resistor : Device {
     void Stamp(CircuitMatrix& mx, const Status& st) override {   // :32-75
         int n1 = n[0], n2 = n[1];
         double g = 1.0 / temperatureAdjustedValue(st.Temp);
+        if (st.Mode == AC_MODE) {                          // :43-54
+            if (n1 != 0) { mx.AddComplexElement(n1, n1, g, 0); if (n2 != 0) mx.AddComplexElement(n1, n2, -g, 0); }
+            if (n2 != 0) { if (n1 != 0) mx.AddComplexElement(n2, n1, -g, 0); mx.AddComplexElement(n2, n2, g, 0); }
+            return;
+        }
         if (n1 != 0) { mx.AddElement(n1, n1, g); if (n2 != 0) mx.AddElement(n1, n2, -g); }
         if (n2 != 0) { if (n1 != 0) mx.AddElement(n2, n1, -g); mx.AddElement(n2, n2, g); }
     }
@@ -122,7 +148,12 @@ struct Capacitor : Device {
     void Stamp(CircuitMatrix& mx, const Status& st) override {   // :43-109
         int n1 = n[0], n2 = n[1];
         double adjustedC = temperatureAdjustedValue(st.Temp);
-        if (st.Mode == OP_MODE) {
+        if (st.Mode == AC_MODE) {                          // :48-66
+            double omega = 2 * M_PI * st.Frequency;
+            double im = omega * adjustedC;
+            if (n1 != 0) { mx.AddComplexElement(n1, n1, 0.0, im); if (n2 != 0) mx.AddComplexElement(n1, n2, -0.0, -im); }
+            if (n2 != 0) { mx.AddComplexElement(n2, n2, 0.0, im); if (n1 != 0) mx.AddComplexElement(n2, n1, -0.0, -im); }
+        } else if (st.Mode == OP_MODE) {
             double gmin = st.Gmin;
             if (gmin < 1e-12) gmin = 1e-12;
             if (n1 != 0) { mx.AddElement(n1, n1, gmin); if (n2 != 0) mx.AddElement(n1, n2, -gmin); }
@@ -182,6 +213,14 @@ struct Inductor : Device {
     int BranchIndex() const override { return branchIdx; }
     void Stamp(CircuitMatrix& mx, const Status& st) override {   // :38-79
         int n1 = n[0], n2 = n[1], b = branchIdx;
+        if (st.Mode == AC_MODE) {
+            // :43-57 — j*omega*L as an ADMITTANCE between the nodes; the branch row and column stay empty, so the matrix of
+            // any circuit with an inductor is singular in the reference's AC analysis (kept: a quirk, like Q9)
+            double omega = 2 * M_PI * st.Frequency;
+            if (n1 != 0) { mx.AddComplexElement(n1, n1, 0, omega * Value); if (n2 != 0) mx.AddComplexElement(n1, n2, 0, -omega * Value); }
+            if (n2 != 0) { mx.AddComplexElement(n2, n2, 0, omega * Value); if (n1 != 0) mx.AddComplexElement(n2, n1, 0, -omega * Value); }
+            return;
+        }
         if (n1 != 0) { mx.AddElement(n1, b, -1); mx.AddElement(b, n1, -1); }
         if (n2 != 0) { mx.AddElement(n2, b, 1); mx.AddElement(b, n2, 1); }
         double dt = st.TimeStep;
@@ -269,8 +308,19 @@ struct VSource : Device {
     Waveform w;
     int branchIdx = 0;
     VSource() { type = 'V'; }
+    double acMag = 0, acPhase = 0;                               // NewACVoltageSource (vsource.go:98-111); 0 for every other kind
+    int BranchIndex() const override { return branchIdx; }
     void Stamp(CircuitMatrix& mx, const Status& st) override {   // vsource.go:131-152
         int n1 = n[0], n2 = n[1], b = branchIdx;
+        if (st.Mode == AC_MODE) {                                // StampAC, :155-177
+            double phaseRad = acPhase * M_PI / 180.0;
+            double voltageReal = acMag * std::cos(phaseRad);
+            double voltageImag = acMag * go_sin(phaseRad);
+            if (n1 != 0) { mx.AddComplexElement(b, n1, 1.0, 0.0); mx.AddComplexElement(n1, b, 1.0, 0.0); }
+            if (n2 != 0) { mx.AddComplexElement(b, n2, -1.0, 0.0); mx.AddComplexElement(n2, b, -1.0, 0.0); }
+            mx.AddComplexRHS(b, voltageReal, voltageImag);
+            return;
+        }
         if (n1 != 0) { mx.AddElement(b, n1, 1); mx.AddElement(n1, b, 1); }
         if (n2 != 0) { mx.AddElement(b, n2, -1); mx.AddElement(n2, b, -1); }
         mx.AddRHS(b, w.eval(st.Time));
@@ -281,8 +331,17 @@ struct VSource : Device {
 struct ISource : Device {
     Waveform w;
     ISource() { type = 'I'; }
+    double acMag = 0, acPhase = 0;
     void Stamp(CircuitMatrix& mx, const Status& st) override {   // isource.go:130-147
         int n1 = n[0], n2 = n[1];
+        if (st.Mode == AC_MODE) {                                // StampAC, :149-165
+            double acPhaseRad = acPhase * M_PI / 180.0;
+            double currentReal = acMag * std::cos(acPhaseRad);
+            double currentImag = acMag * go_sin(acPhaseRad);
+            if (n1 != 0) mx.AddComplexRHS(n1, currentReal, currentImag);
+            if (n2 != 0) mx.AddComplexRHS(n2, -currentReal, -currentImag);
+            return;
+        }
         double current = w.eval(st.Time);
         if (n1 != 0) mx.AddRHS(n1, current);
         if (n2 != 0) mx.AddRHS(n2, -current);
@@ -1076,6 +1135,91 @@ struct DCSweep {
         }
         source->SetValue(origVal);
         source2->SetValue(origVal2);
+        return RUN_OK;
+    }
+};
+
+// ---------------------------------------------------------------- ac.go
+// ACAnalysis of a circuit WITHOUT nonlinear devices.  What the reference does with one (ac.go:33-98):
+//   Setup    the circuit's matrix is complex from the start (cmd/spice/main.go:380-381); the operating point runs on it.  Its
+//            values are real, so the first FactorComplex chooses the same pivots as a real matrix would (|re| + |im| = |re|)
+//            and the order is frozen there.  The operating point's OWN numbers are scrambled — its real-indexed right-hand
+//            side rhs[i] (AddRHS) is read by SolveComplex as interleaved re/im pairs — but a linear circuit converges on
+//            whatever comes out (the second iteration repeats the first bit for bit), and no device of a linear circuit
+//            carries operating-point state into StampAC.  So for linear circuits the sweep is independent of that artefact;
+//            for nonlinear ones it is not (their gd / gm come from the scrambled point, and Bjt.Stamp never dispatches to
+//            StampAC at all): those are refused, here and in the product.
+//   Execute  per frequency Clear / Stamp(Mode: ACAnalysis) / Solve.  Devices whose Stamp has no AC case stamp NOTHING:
+//            Mutual (mutual.go:63-65 "only for transient") and MagneticInductor (magnetic.go:205-273 switch without an AC
+//            case) — their StampAC methods exist but circuit.Stamp never calls them (circuit.go:165-176).  An inductor
+//            stamps j*omega*L as an admittance and leaves its branch row empty.  Either way the matrix is singular:
+//            "matrix solve error at f=...".
+//   Read-out GetComplexSolution(i) returns (solution[i], solution[i+Size]) (matrix/circuit.go:168-173) although the vectors are
+//            interleaved (SeparatedComplexVectors: false, :41-44).  interleaved_readout = true restates that literally under
+//            Sparse 1.3's layout (solution[2i] = re x_i, solution[2i+1] = im x_i, entries 0 and 1 unused = 0); false reads
+//            entry i as (re x_i, im x_i) — what the accessor means if the un-vendored module returns split halves.  The module
+//            is not inspectable, so both are offered; the product's default is the second.
+enum { RUN_AC_FAILED = 5 };
+struct ACAnalysis {
+    Circuit* ckt = nullptr;
+    double startFreq, stopFreq;
+    int numPoints, pType;                   // 0 DEC, 1 OCT, 2 LIN
+    bool interleaved_readout = false;
+    std::vector<double> frequencies;
+    double fail_freq = 0;
+    ACAnalysis(double fStart, double fStop, int nPoints, int ptype) : startFreq(fStart), stopFreq(fStop), numPoints(nPoints), pType(ptype) {}
+    void generateFrequencyPoints() {        // ac.go:100-126
+        frequencies.assign(numPoints, 0.0);
+        if (pType == 0) {
+            double logStart = go_log10(startFreq), logStop = go_log10(stopFreq);
+            double step = (logStop - logStart) / double(numPoints - 1);
+            for (int i = 0; i < numPoints; ++i) frequencies[i] = go_pow(10, logStart + double(i) * step);
+        } else if (pType == 1) {
+            double logStart = go_log2(startFreq), logStop = go_log2(stopFreq);
+            double step = (logStop - logStart) / double(numPoints - 1);
+            for (int i = 0; i < numPoints; ++i) frequencies[i] = go_pow(2, logStart + double(i) * step);
+        } else {
+            double step = (stopFreq - startFreq) / double(numPoints - 1);
+            for (int i = 0; i < numPoints; ++i) frequencies[i] = startFreq + double(i) * step;
+        }
+    }
+    int n_signals() const {
+        int nv = 0;
+        for (auto& d : ckt->devices) if (d->type == 'V') ++nv;
+        return 1 + 2 * (ckt->numNodes + nv);
+    }
+    int Setup() {                           // ac.go:33-49
+        OperatingPoint op; op.ckt = ckt;
+        if (!op.Execute()) return RUN_OP_FAILED;
+        generateFrequencyPoints();
+        return RUN_OK;
+    }
+    int Execute(ResultStore& rs) {          // ac.go:51-98, StoreACResult anlysis.go:87-111
+        CircuitMatrix& mat = *ckt->Matrix;
+        const int n = mat.Size;
+        for (double freq : frequencies) {
+            Status st; st.Frequency = freq; st.Mode = AC_MODE; st.Temp = 300.15;
+            mat.Clear();
+            ckt->Stamp(st);
+            if (!mat.SolveComplex()) { fail_freq = freq; return RUN_AC_FAILED; }
+            std::vector<double> flat(2 * (n + 1) + n + 2, 0.0);
+            for (int i = 1; i <= n; ++i) { flat[2 * i] = mat.sol_re[i]; flat[2 * i + 1] = mat.sol_im[i]; }
+            auto get = [&](int i, double& re, double& im) {
+                if (interleaved_readout) { re = flat[i]; im = flat[i + n]; }
+                else { re = mat.sol_re[i]; im = mat.sol_im[i]; }
+            };
+            std::vector<double> row(rs.nsig);
+            int k = 0;
+            row[k++] = freq;
+            auto put = [&](int idx) {
+                double re, im; get(idx, re, im);
+                row[k++] = go_hypot(re, im);                            // cmplx.Abs = math.Hypot
+                row[k++] = std::atan2(im, re) * 180.0 / M_PI;           // cmplx.Phase * 180 / math.Pi
+            };
+            for (int i = 1; i <= ckt->numNodes; ++i) put(i);
+            for (auto& d : ckt->devices) if (d->type == 'V') put(d->BranchIndex());
+            rs.push(row.data());
+        }
         return RUN_OK;
     }
 };

@@ -122,4 +122,27 @@ inline double go_pow(double x, double y) {
     return std::ldexp(a1, ae);
 }
 
+// math.Log2 / math.Log10 (src/math/log10.go): log2(x) = Log(frac) * (1/Ln2) + exp with Frexp's split (exact for powers of
+// two), log10(x) = log2(x) * (Ln2/Ln10).  Log itself from libm (<= 1 ulp from Go's FreeBSD-derived routine).  They place the
+// points of a DEC / OCT frequency sweep (ac.go:100-119).
+inline double go_log2(double x) {
+    int e;
+    double frac = std::frexp(x, &e);
+    if (frac == 0.5) return double(e - 1);
+    return std::log(frac) * (1 / 0.693147180559945309417232121458176568) + double(e);
+}
+inline double go_log10(double x) { return go_log2(x) * (0.693147180559945309417232121458176568 / 2.30258509299404568401799145468436421); }
+
+// math.Hypot (src/math/hypot.go; the amd64 assembly follows the same steps): p * Sqrt(1 + (q/p)^2) with p the larger
+// magnitude — NOT the correctly rounded hypot of libm.  cmplx.Abs is this (anlysis.go:100).
+inline double go_hypot(double p, double q) {
+    p = std::fabs(p); q = std::fabs(q);
+    if (std::isinf(p) || std::isinf(q)) return INFINITY;
+    if (std::isnan(p) || std::isnan(q)) return std::nan("");
+    if (p < q) { double t = p; p = q; q = t; }
+    if (p == 0) return 0;
+    q = q / p;
+    return p * std::sqrt(1 + q * q);
+}
+
 }  // namespace orc

@@ -525,6 +525,9 @@ def signal_names(plan: Plan, analysis: int) -> list:
     """Canonical column order used by the oracle core and the product (the reference returns
     a map, circuit.go:242-273 / op.go:235-248; only key -> series matters)."""
     by_idx = sorted(plan.node_map.items(), key=lambda kv: kv[1])
+    if analysis == AN_AC:        # StoreACResult (anlysis.go:87-111): <key>_MAG, <key>_PHASE for node voltages and V-source currents
+        keys = [f"V({k})" for k, _ in by_idx] + [f"I({r.name})" for r in plan.devices if r.kind == K_V]
+        return ["FREQ"] + [k + sfx for k in keys for sfx in ("_MAG", "_PHASE")]
     names = [f"V({k})" for k, _ in by_idx]
     names += [f"I({k})" for k, _ in sorted(plan.branch_map.items(), key=lambda kv: kv[1])]
     if analysis == AN_OP:

@@ -22,7 +22,8 @@ class OrcJob(C.Structure):
     _fields_ = [("analysis", C.c_int), ("tstart", C.c_double), ("tstop", C.c_double), ("tstep", C.c_double),
                 ("tmax", C.c_double), ("uic", C.c_int), ("dc_src_dev", C.c_int), ("dc_start", C.c_double),
                 ("dc_stop", C.c_double), ("dc_inc", C.c_double), ("dc2_src_dev", C.c_int), ("dc2_start", C.c_double),
-                ("dc2_stop", C.c_double), ("dc2_inc", C.c_double)]
+                ("dc2_stop", C.c_double), ("dc2_inc", C.c_double), ("ac_sweep", C.c_int), ("ac_points", C.c_int),
+                ("ac_fstart", C.c_double), ("ac_fstop", C.c_double), ("ac_refread", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -102,7 +103,7 @@ class OracleCircuit:
         return dict(rc=rc, ext2int=list(e2i)[1:], pivot_row=list(pr)[1:], pivot_col=list(pc)[1:])
 
     def run(self, n_inst=1, overrides=None, analysis=None, tran=None, dc=None, threads=1, cap_rows=None,
-            want_wave=True, want_stats=False, dc2=None):
+            want_wave=True, want_stats=False, dc2=None, ac=None, ac_refread=False):
         """overrides: {(device_name_or_index, param_index): array[n_inst]}.
         Returns dict(wave [n_inst, cap, ncol], n_rows, status, counters, stats, signals)."""
         nl = self.netlist
@@ -124,6 +125,13 @@ class OracleCircuit:
             if dc2:         # nested sweep (dc.go:205-270): dict(source, start, stop, inc) of the INNER source
                 job.dc2_src_dev = self.dev_index(dc2["source"])
                 job.dc2_start, job.dc2_stop, job.dc2_inc = dc2["start"], dc2["stop"], dc2["inc"]
+        elif an == nlmod.AN_AC:
+            a = dict(nl.ac)
+            if ac:
+                a.update(ac)
+            job.ac_sweep = {"DEC": 0, "OCT": 1, "LIN": 2}[a["sweep"].upper()]
+            job.ac_points, job.ac_fstart, job.ac_fstop = int(a["points"]), a["fstart"], a["fstop"]
+            job.ac_refread = int(bool(ac_refread))
         overrides = overrides or {}
         keys = list(overrides.keys())
         ov_dev = [self.dev_index(k[0]) if isinstance(k[0], str) else int(k[0]) for k in keys]
@@ -134,7 +142,7 @@ class OracleCircuit:
         ncol = lib().orc_n_columns(self.h, 4 if nested else an)
         if cap_rows is None:
             cap_rows = 1 if an == nlmod.AN_OP else (int(round((job.dc_stop - job.dc_start) / job.dc_inc)) + 3
-                                                     if an == nlmod.AN_DC else 65536)
+                                                     if an == nlmod.AN_DC else job.ac_points if an == nlmod.AN_AC else 65536)
             if nested:
                 cap_rows *= int(round((job.dc2_stop - job.dc2_start) / job.dc2_inc)) + 3
         wave = np.full((n_inst, cap_rows, ncol), np.nan) if want_wave else None

@@ -904,3 +904,91 @@ class DCSweep:                                                      # dc.go
                 if done:
                     break
         return np.array(self.rows)
+
+
+# ------------------------------------------------------------------------------------------- AC analysis (ac.go)
+def ac_frequencies(sweep, points, fstart, fstop):                   # ac.go:100-126
+    if sweep == "DEC":
+        a, b = math.log10(fstart), math.log10(fstop)
+        return [10.0 ** (a + i * ((b - a) / (points - 1))) for i in range(points)]
+    if sweep == "OCT":
+        a, b = math.log2(fstart), math.log2(fstop)
+        return [2.0 ** (a + i * ((b - a) / (points - 1))) for i in range(points)]
+    return [fstart + i * ((fstop - fstart) / (points - 1)) for i in range(points)]
+
+
+def ac_sweep(plan, sweep, points, fstart, fstop, overrides=None, refread=False):
+    """ACAnalysis.Execute (ac.go:51-98) for a circuit without nonlinear devices, written from the device files' AC cases:
+    per frequency a complex MNA system solved with numpy.linalg.solve.  What each device's Stamp does in Mode == ACAnalysis:
+    resistor.go:43-54 (g), capacitor.go:48-66 (j*omega*C), inductor.go:43-57 (j*omega*L between the NODES, branch row left
+    empty), vsource.go:155-177 / isource.go:149-165 (incidence, magnitude and phase), mutual.go:63-65 and magnetic.go:205-273
+    (nothing).  Returns (rows, fail_freq): rows = [FREQ, mag, phase_deg per node voltage, then per V-source current];
+    fail_freq = the frequency of the first singular system (the reference's "matrix solve error at f=..."), else None."""
+    rows_in = [dict(kind=r.kind, name=r.name, nodes=list(r.nodes), branch=r.branch, p=list(r.p), ip=list(r.ip)) for r in plan.devices]
+    for (dev, par), val in (overrides or {}).items():
+        idx = dev if isinstance(dev, int) else [r["name"] for r in rows_in].index(dev)
+        rows_in[idx]["p"][par] = float(val)
+    n_nodes, n = plan.n_nodes, plan.n_nodes + plan.n_branches
+    vsrc = [r for r in rows_in if r["kind"] == K_V]
+    out, fail = [], None
+    for f in ac_frequencies(sweep, points, fstart, fstop):
+        omega = 2 * math.pi * f
+        A = np.zeros((n + 1, n + 1), dtype=complex)
+        rhs = np.zeros(n + 1, dtype=complex)
+
+        def two_terminal(n1, n2, y):
+            if n1:
+                A[n1, n1] += y
+            if n2:
+                A[n2, n2] += y
+            if n1 and n2:
+                A[n1, n2] -= y
+                A[n2, n1] -= y
+
+        for r in rows_in:
+            k, nd, p = r["kind"], r["nodes"], r["p"]
+            if k == K_R:
+                two_terminal(nd[0], nd[1], 1.0 / p[0])
+            elif k == K_C:
+                two_terminal(nd[0], nd[1], 1j * omega * p[0])
+            elif k == K_L:
+                two_terminal(nd[0], nd[1], 1j * omega * p[0])
+            elif k == K_V:
+                b = r["branch"]
+                if nd[0]:
+                    A[b, nd[0]] += 1
+                    A[nd[0], b] += 1
+                if nd[1]:
+                    A[b, nd[1]] -= 1
+                    A[nd[1], b] -= 1
+                if (not r["ip"] or r["ip"][0] == 0) and len(p) >= 3:
+                    rhs[b] += p[1] * complex(math.cos(p[2] * math.pi / 180.0), math.sin(p[2] * math.pi / 180.0))
+            elif k == K_I:
+                if (not r["ip"] or r["ip"][0] == 0) and len(p) >= 3:
+                    cur = p[1] * complex(math.cos(p[2] * math.pi / 180.0), math.sin(p[2] * math.pi / 180.0))
+                    if nd[0]:
+                        rhs[nd[0]] += cur
+                    if nd[1]:
+                        rhs[nd[1]] -= cur
+            elif k in (K_K, K_LCORE):
+                pass
+            else:
+                raise ValueError("AC analysis of nonlinear circuits is outside this pin")
+        M = A[1:, 1:]
+        if np.linalg.matrix_rank(M) < n:                            # an empty branch row: exactly singular
+            fail = f
+            break
+        x = np.concatenate([[0.0], np.linalg.solve(M, rhs[1:])])
+        flat = np.zeros(3 * n + 4)
+        flat[2:2 * n + 2:2] = x[1:].real
+        flat[3:2 * n + 3:2] = x[1:].imag
+
+        def get(i):
+            return complex(flat[i], flat[i + n]) if refread else x[i]
+
+        row = [f]
+        for i in list(range(1, n_nodes + 1)) + [r["branch"] for r in vsrc]:
+            z = get(i)
+            row += [abs(z), math.degrees(math.atan2(z.imag, z.real))]
+        out.append(row)
+    return np.array(out), fail

@@ -50,9 +50,19 @@ public:
         return v_[idx(r, c)];
     }
 
+    // element.Imag of the same element (matrix/circuit.go:73-83 AddComplexElement): only the AC analysis writes it
+    double& get_element_imag(int ext_row, int ext_col) {
+        get_element(ext_row, ext_col);
+        int r, c;
+        translate(ext_row, ext_col, r, c);
+        if (vi_.empty()) vi_.assign(v_.size(), 0.0);
+        return vi_[idx(r, c)];
+    }
+
     // spClear: zero all values, keep structure and ordering.
     void clear() {
         std::fill(v_.begin(), v_.end(), 0.0);
+        std::fill(vi_.begin(), vi_.end(), 0.0);
         factored_ = false;
         error_ = SP_OKAY;
     }
@@ -107,6 +117,84 @@ public:
         for (int i = n_; i > 0; --i) sol[i2e_col_[i]] = c[i];
     }
 
+    // ---- complex matrices (AC analysis; matrix/circuit.go:130,140 FactorComplex / SolveComplex) -----------------------
+    // spFactor of a complex matrix whose pivot order exists already (FactorComplexMatrix, direct-addressing form: column by
+    // column, Mult = Dest[row] * (1/pivot), Dest[below] -= Mult * L; the pivot is stored as its reciprocal, formed by
+    // CMPLX_RECIPROCAL = Smith's scaled division).  In the reference the order always exists when the AC sweep starts: the
+    // operating point of ACAnalysis.Setup (ac.go:33-49) went through the same matrix first.
+    static void crecip(double& re, double& im) {
+        if ((re >= im && re > -im) || (re < im && re <= -im)) {
+            double r = im / re;
+            double t = 1.0 / (re + r * im);
+            re = t; im = -r * t;
+        } else {
+            double r = re / im;
+            double t = -1.0 / (im + r * re);
+            im = t; re = -r * t;
+        }
+    }
+    int factor_complex() {
+        if (needs_ordering_) return (error_ = SP_SINGULAR);          // not reachable from the analyses (see above)
+        if (vi_.empty()) vi_.assign(v_.size(), 0.0);
+        if (!ex_[idx(1, 1)] || (std::fabs(v_[idx(1, 1)]) + std::fabs(vi_[idx(1, 1)]) == 0.0)) return zero_pivot(1);
+        crecip(v_[idx(1, 1)], vi_[idx(1, 1)]);
+        std::vector<double> dr(n_ + 2, 0.0), di(n_ + 2, 0.0);
+        for (int step = 2; step <= n_; ++step) {
+            for (int r = 1; r <= n_; ++r) if (ex_[idx(r, step)]) { dr[r] = v_[idx(r, step)]; di[r] = vi_[idx(r, step)]; }
+            for (int r = 1; r < step; ++r) {
+                if (!ex_[idx(r, step)]) continue;
+                const double pr = v_[idx(r, r)], pi = vi_[idx(r, r)];               // reciprocal pivot
+                const double mr = dr[r] * pr - di[r] * pi, mi = dr[r] * pi + di[r] * pr;   // CMPLX_MULT(Mult, Dest, *pPivot)
+                v_[idx(r, step)] = mr; vi_[idx(r, step)] = mi;
+                for (int l = r + 1; l <= n_; ++l)
+                    if (ex_[idx(l, r)]) {                                               // CMPLX_MULT_SUBT_ASSIGN(Dest, Mult, *pElement)
+                        const double er = v_[idx(l, r)], ei = vi_[idx(l, r)];
+                        dr[l] -= mr * er - mi * ei;
+                        di[l] -= mr * ei + mi * er;
+                    }
+            }
+            for (int r = step + 1; r <= n_; ++r) if (ex_[idx(r, step)]) { v_[idx(r, step)] = dr[r]; vi_[idx(r, step)] = di[r]; }
+            if (!ex_[idx(step, step)] || (std::fabs(dr[step]) + std::fabs(di[step]) == 0.0)) return zero_pivot(step);
+            double pr = dr[step], pi = di[step];
+            crecip(pr, pi);
+            v_[idx(step, step)] = pr; vi_[idx(step, step)] = pi;
+        }
+        factored_ = true;
+        return (error_ = SP_OKAY);
+    }
+    // SolveComplexMatrix: logical vectors (entry i = re[i] + j*im[i], 1-based external); how the reference lays them out in
+    // its float64 slices is the caller's concern (engine.hpp: ACAnalysis).
+    void solve_complex(const std::vector<double>& rre, const std::vector<double>& rim, std::vector<double>& sre, std::vector<double>& sim) {
+        std::vector<double> cr(n_ + 2, 0.0), ci(n_ + 2, 0.0);
+        for (int i = n_; i > 0; --i) { cr[i] = rre[i2e_row_[i]]; ci[i] = rim[i2e_row_[i]]; }
+        for (int i = 1; i <= n_; ++i) {
+            double tr = cr[i], ti = ci[i];
+            if (tr != 0.0 || ti != 0.0) {
+                const double pr = v_[idx(i, i)], pi = vi_[idx(i, i)];
+                const double mr = tr * pr - ti * pi, mi = tr * pi + ti * pr;           // CMPLX_MULT_ASSIGN(Temp, *pPivot)
+                cr[i] = mr; ci[i] = mi;
+                for (int r = i + 1; r <= n_; ++r)
+                    if (ex_[idx(r, i)]) {                                              // CMPLX_MULT_SUBT_ASSIGN(Intermediate[row], Temp, *pElement)
+                        const double er = v_[idx(r, i)], ei = vi_[idx(r, i)];
+                        cr[r] -= mr * er - mi * ei;
+                        ci[r] -= mr * ei + mi * er;
+                    }
+            }
+        }
+        for (int i = n_; i > 0; --i) {
+            double tr = cr[i], ti = ci[i];
+            for (int col = i + 1; col <= n_; ++col)
+                if (ex_[idx(i, col)]) {                                                // CMPLX_MULT_SUBT_ASSIGN(Temp, *pElement, Intermediate[col])
+                    const double er = v_[idx(i, col)], ei = vi_[idx(i, col)];
+                    tr -= er * cr[col] - ei * ci[col];
+                    ti -= er * ci[col] + ei * cr[col];
+                }
+            cr[i] = tr; ci[i] = ti;
+        }
+        sre.assign(n_ + 1, 0.0); sim.assign(n_ + 1, 0.0);
+        for (int i = n_; i > 0; --i) { sre[i2e_col_[i]] = cr[i]; sim[i2e_col_[i]] = ci[i]; }
+    }
+
     // Introspection for the structure tests.
     int ext_to_int(int ext) const { return e2i_row_[ext]; }
     int pivot_ext_row(int step) const { return i2e_row_[step]; }
@@ -117,7 +205,7 @@ public:
 
 private:
     int n_ = 0, current_size_ = 0;
-    std::vector<double> v_, tmp_;
+    std::vector<double> v_, vi_, tmp_;
     std::vector<char> ex_;
     std::vector<int> e2i_row_, e2i_col_, i2e_row_, i2e_col_;
     std::vector<long> mrow_, mcol_, mprod_;

@@ -61,12 +61,14 @@ std::unique_ptr<Circuit> build(const Template& t, const std::vector<DevDesc>& de
             case K_L: { auto* x = new Inductor; x->Value = d.p[0]; x->branchIdx = d.branch; dev.reset(x); break; }
             case K_V: {
                 auto* x = new VSource; fill_waveform(x->w, d); x->branchIdx = d.branch;
+                if (x->w.stype == SRC_DC && d.p.size() >= 3) { x->acMag = d.p[1]; x->acPhase = d.p[2]; }
                 // Value: DC -> value, SIN -> offset, PULSE -> v1, PWL -> values[0] (vsource.go:36-96)
                 x->Value = (x->w.stype == SRC_PULSE) ? x->w.v1 : (x->w.stype == SRC_PWL ? x->w.values[0] : x->w.dcValue);
                 dev.reset(x); break;
             }
             case K_I: {
                 auto* x = new ISource; fill_waveform(x->w, d);
+                if (x->w.stype == SRC_DC && d.p.size() >= 3) { x->acMag = d.p[1]; x->acPhase = d.p[2]; }
                 x->Value = (x->w.stype == SRC_PULSE) ? x->w.v1 : (x->w.stype == SRC_PWL ? x->w.values[0] : x->w.dcValue);
                 dev.reset(x); break;
             }
@@ -123,6 +125,9 @@ struct orc_job {
     double dc_start, dc_stop, dc_inc;
     int dc2_src_dev;         // >= 0: nested sweep (dc.go:205-270), this is the inner source
     double dc2_start, dc2_stop, dc2_inc;
+    int ac_sweep, ac_points; // analysis 2: 0 DEC, 1 OCT, 2 LIN; total number of points
+    double ac_fstart, ac_fstop;
+    int ac_refread;          // GetComplexSolution's literal index arithmetic over interleaved vectors (engine.hpp: ACAnalysis)
 };
 
 void* orc_circuit_new(int n_nodes, int n_branches) {
@@ -144,6 +149,7 @@ int orc_circuit_add(void* h, int kind, const char* name, const int* nodes, int n
 int orc_n_columns(void* h, int analysis) {
     Template* t = static_cast<Template*>(h);
     if (analysis == 0) return t->n_nodes + t->n_branches;
+    if (analysis == 2) { int nv = 0; for (auto& d : t->devs) if (d.kind == K_V) ++nv; return 1 + 2 * (t->n_nodes + nv); }
     int nr = 0; for (auto& d : t->devs) if (d.kind == K_R) ++nr;
     return (analysis == 4 ? 2 : 1) + t->n_nodes + t->n_branches + nr;        // 4: nested DC sweep (SWEEP1, SWEEP2)
 }
@@ -196,6 +202,15 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
                 op_path = op.path;
                 cnt.op_solves = c->Matrix->n_solves;
                 if (ok) rs.push(op.result.data() + 1);
+            } else if (job->analysis == 2) {
+                if (!c->nonlinearDevices.empty()) { bad = 3; break; }      // refused, like the product (engine.hpp: ACAnalysis)
+                ACAnalysis ac(job->ac_fstart, job->ac_fstop, job->ac_points, job->ac_sweep);
+                ac.ckt = c.get(); ac.interleaved_readout = job->ac_refread != 0;
+                st = ac.Setup();
+                const long op_solves = c->Matrix->n_solves;
+                if (st == RUN_OK) st = ac.Execute(rs);
+                cnt.op_solves = c->Matrix->n_solves - op_solves;           // the sweep's solves (the product runs no operating point)
+                fail_at = ac.fail_freq;
             } else if (job->analysis == 1) {
                 Transient tr(job->tstart, job->tstop, job->tstep, job->tmax, job->uic != 0);
                 st = tr.Setup(c.get());

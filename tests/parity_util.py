@@ -68,7 +68,7 @@ def run_gpu(ctx, text, n, overrides, out=T.OUT_WAVE, cap_rows=0, opts=None, anal
 
 
 def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, analysis=None, tran=None, want_wave=True, dc=None,
-               dc2=None):
+               dc2=None, **extra):
     oc = O.OracleCircuit(text)
     kw = {}
     if dc2 is not None:
@@ -77,7 +77,7 @@ def run_oracle(text, n, overrides, threads=0, cap_rows=None, want_stats=False, a
     elif dc is not None:
         kw = dict(dc=dict(source=dc[0], start=dc[1], stop=dc[2], inc=dc[3]))
     res = oc.run(n, overrides=overrides, threads=threads, cap_rows=cap_rows, want_stats=want_stats, analysis=analysis, tran=tran,
-                 want_wave=want_wave, **kw)
+                 want_wave=want_wave, **kw, **extra)
     return oc, res
 
 

@@ -26,7 +26,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 AN_OP, AN_TRAN, AN_AC, AN_DC, AN_DC2 = 0, 1, 2, 3, 4
-OUT_WAVE, OUT_STATS, OUT_GRID = 1, 2, 4
+OUT_WAVE, OUT_STATS, OUT_GRID, OUT_AC_REFREAD = 1, 2, 4, 8
 K_R, K_C, K_L, K_V, K_I, K_D, K_Q, K_M, K_K, K_LCORE = range(10)
 ST_OK, ST_OP_FAILED, ST_TRAN_FAILED, ST_DC_FAILED, ST_OVERFLOW, ST_AC_FAILED = range(6)
 

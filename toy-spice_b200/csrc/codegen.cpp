@@ -495,9 +495,7 @@ void emit_ac(Emitter& e, const Plan& pl) {
             case 0: e.line("Ar[" + k + "]" + sg + "D[" + S(d.d_off) + "];"); break;
             case 1: e.line("Ai[" + k + "]" + sg + "omega * (P[" + S(d.p_off) + "] * 1.0);"); break;
             case 2: e.line("Ai[" + k + "]" + sg + "omega * P[" + S(d.p_off) + "];"); break;
-            case 3: e.line("Ar[" + k + "]" + sg + "1.0;"); break;
-            case 4: e.line("Ai[" + k + "]" + sg + "(-1.0 / (omega * D[" + S(d.d_off) + "]));"); break;
-            default: e.line("Ai[" + k + "]" + sg + "omega * D[" + S(d.d_off + a.code - 5) + "];"); break;
+            default: e.line("Ar[" + k + "]" + sg + "1.0;"); break;
             }
         }
         // right-hand sides: AC magnitude / phase of the sources (vsource.go:160-176, isource.go:149-165)
@@ -552,11 +550,18 @@ void emit_ac(Emitter& e, const Plan& pl) {
     --e.ind;
     e.line("}");
     // result row of one frequency (ac.go:73-95, StoreACResult anlysis.go:87-111): magnitude = cmplx.Abs, phase in degrees
-    e.line("__device__ __forceinline__ void signals_ac(const double* xr, const double* xi, double* out) const {");
+    // refread: GetComplexSolution(i) = (solution[i], solution[i+Size]) taken literally over Sparse 1.3's interleaved vector
+    // (solution[2i] = re x_i, solution[2i+1] = im x_i, entries 0 and 1 unused), matrix/circuit.go:168-173 vs :41-44
+    e.line("__device__ __forceinline__ void signals_ac(const double* xr, const double* xi, bool refread, double* out) const {");
     ++e.ind;
     int c = 0;
+    auto flat = [&](int q) -> std::string {            // entry q of the interleaved vector
+        if (q < 2 || q > 2 * n + 1) return "0.0";
+        return std::string(q % 2 == 0 ? "xr[" : "xi[") + S(q / 2) + "]";
+    };
     auto emit_mp = [&](int idx) {
-        e.line("out[" + S(c) + "] = hypot(xr[" + S(idx) + "], xi[" + S(idx) + "]); out[" + S(c + 1) + "] = atan2(xi[" + S(idx) + "], xr[" + S(idx) + "]) * 180.0 / TSB_PI;");
+        e.line("{ const double re = refread ? " + flat(idx) + " : xr[" + S(idx) + "], im = refread ? " + flat(idx + n) + " : xi[" + S(idx) + "];");
+        e.line("  out[" + S(c) + "] = tsb_go_hypot(re, im); out[" + S(c + 1) + "] = atan2(im, re) * 180.0 / TSB_PI; }");
         c += 2;
     };
     for (int i = 1; i <= pl.n_nodes; ++i) emit_mp(i);

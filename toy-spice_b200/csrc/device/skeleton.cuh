@@ -84,6 +84,7 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #define TSB_OUT_WAVE 1
 #define TSB_OUT_STATS 2
 #define TSB_OUT_GRID 4
+#define TSB_OUT_AC_REFREAD 8
 
 #ifndef TSB_X_STATS_PRED
 #define TSB_X_STATS_PRED 1
@@ -634,14 +635,21 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             next_time = time + dt;
             if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
             c.eval_sources(time, 1.0);          // sources are evaluated at the START of the step
-            rdt = 1.0 / dt;                     // the one division by the time step of this attempt
+            rdt = tsb_rcp_dt(dt);               // the one division by the time step of this attempt
             iter = 0; mode = TSB_MODE_TRAN; gmin = 0.0; cont = C_TRAN; phase = PH_NR;
         }
 
         // ---------------- one Newton iteration (op.go:45-86, tran.go:172-213) -------------------
         if (Ckt::HAS_NL && (mode == TSB_MODE_OP || iter > 0)) c.update_nl(c.xo);
         const bool is_tran = mode == TSB_MODE_TRAN;
-        bool solved = c.template assemble_solve<-1>(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
+        bool solved;
+        if constexpr (Ckt::HAS_TF && !(LINEAR_LOOP || NL_LOOP)) {
+            // the transient runs in this state machine (lane refill, or the warp-synchronous loops switched off): its solves
+            // must be the SAME arithmetic as tsb_tran_nonlinear's — the condensed elimination — or the result of an
+            // instance would depend on the mapping that ran it
+            if (is_tran) solved = c.template assemble_solve_tf<true>(time, dt, rdt, typename Ckt::TsbNoMid());
+            else solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, rdt, gmin);
+        } else solved = c.template assemble_solve<-1>(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
         if (is_tran) ++n_sol_tran; else ++n_sol_op;
         ++n_exec;
         conv = false; fail = !solved;
@@ -876,7 +884,7 @@ __device__ __forceinline__ void tsb_run_ac_instance(const TsbArgs& a, long long 
             if (!c.solve_ac(omega, xr, xi)) { status = TSB_ST_AC_FAILED; fail_at = freq; break; }
             double row[Ckt::NCOL_AC];
             row[0] = freq;
-            c.signals_ac(xr, xi, row + 1);
+            c.signals_ac(xr, xi, (a.out_flags & TSB_OUT_AC_REFREAD) != 0, row + 1);
             sink.push(row);
         }
         if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;

@@ -122,8 +122,10 @@ void device_stamp_entries(const Plan& plan, int di, std::vector<StampEntry>& out
 //   code 2: (0, +-omega*L)      inductor.go:43-57 — an ADMITTANCE j*omega*L between the nodes; the branch row stays empty,
 //                               so every circuit with an inductor is singular in the reference's AC analysis
 //   code 3: (+-1, 0)            vsource.go:155-177 incidence
-//   code 4: (0, -+1/(omega*L0)) magnetic.go:276-300 (air-core value); branch row empty as well
-//   code 5 + q: (0, +-omega*M_q) mutual.go:122-185, pair q of the coupling
+// Mutual and MagneticInductor stamp NOTHING in this mode: circuit.Stamp calls dev.Stamp (circuit.go:165-176), and their Stamp
+// methods have no AC case (mutual.go:63-65 returns unless Mode == TransientAnalysis; magnetic.go:205-273 switches over OP and
+// transient only) — the StampAC methods they define (mutual.go:122, magnetic.go:276) are never reached.  A core inductor's
+// branch row is therefore empty as well.
 // Nonlinear devices stamp small-signal values taken from the state their operating point left behind — which the
 // reference computes on a COMPLEX matrix with a real-indexed right-hand side (matrix/circuit.go:99-105 vs :126-150):
 // not reproducible without the un-vendored module's vector layout, so AC analysis is offered for linear circuits only.
@@ -142,23 +144,35 @@ void device_ac_entries(const Plan& plan, int di, std::vector<AcEntry>& out) {
     case TSB_R: quad(n[0], n[1], 0); break;
     case TSB_C: quad_c(n[0], n[1], 1); break;
     case TSB_L: quad_c(n[0], n[1], 2); break;
-    case TSB_LCORE: quad(n[0], n[1], 4); break;
     case TSB_V:
         if (n[0] != 0) { out.push_back({d.branch, n[0], 3, +1}); out.push_back({n[0], d.branch, 3, +1}); }
         if (n[1] != 0) { out.push_back({d.branch, n[1], 3, -1}); out.push_back({n[1], d.branch, 3, -1}); }
         break;
-    case TSB_K: {
-        int m = (int)d.ip.size(), q = 0;
-        for (int i = 0; i < m; ++i)
-            for (int j = i + 1; j < m; ++j, ++q) {
-                const int* a = plan.devs[d.ip[i]].nodes; const int* b = plan.devs[d.ip[j]].nodes;
-                auto el = [&](int r, int c, double sg) { if (r > 0 && c > 0) out.push_back({r, c, 5 + q, sg}); };
-                el(a[0], b[0], +1); el(a[0], b[1], -1); el(a[1], b[0], -1); el(a[1], b[1], +1);
-                el(b[0], a[0], +1); el(b[0], a[1], -1); el(b[1], a[0], -1); el(b[1], a[1], +1);
-            }
-        break;
-    }
     default: break;
+    }
+}
+
+// generateFrequencyPoints (ac.go:100-126) with Go's math.Log10 / Log2 / Pow: log2(x) = Log(frac)*(1/Ln2) + exp over Frexp's
+// split, log10(x) = log2(x)*(Ln2/Ln10) (src/math/log10.go), Pow as restated in models.cuh.  A single point divides by zero
+// there (step = NaN or Inf, the one frequency NaN); kept.
+void ac_frequency_points(int sweep_type, int n_points, double fstart, double fstop, std::vector<double>& f) {
+    auto go_log2 = [](double x) {
+        int e;
+        const double frac = std::frexp(x, &e);
+        if (frac == 0.5) return (double)(e - 1);
+        return std::log(frac) * (1 / 0.693147180559945309417232121458176568) + (double)e;
+    };
+    auto go_log10 = [&](double x) { return go_log2(x) * (0.693147180559945309417232121458176568 / 2.30258509299404568401799145468436421); };
+    f.assign((size_t)n_points, 0.0);
+    if (sweep_type == 0) {
+        const double ls = go_log10(fstart), le = go_log10(fstop), step = (le - ls) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = tsb_go_pow(10.0, ls + (double)i * step);
+    } else if (sweep_type == 1) {
+        const double ls = go_log2(fstart), le = go_log2(fstop), step = (le - ls) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = tsb_go_pow(2.0, ls + (double)i * step);
+    } else {
+        const double step = (fstop - fstart) / (double)(n_points - 1);
+        for (int i = 0; i < n_points; ++i) f[i] = fstart + (double)i * step;
     }
 }
 

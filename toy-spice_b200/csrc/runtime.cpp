@@ -1178,18 +1178,8 @@ int tsb_run_ac(tsb_batch* b, int sweep_type, int n_points, double fstart, double
     if (sweep_type < 0 || sweep_type > 2 || n_points < 1 || n_points > (1 << 20)) return fail(ctx, TSB_E_INVALID, "invalid sweep type or number of points");
     if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_INVALID, "TSB_OUT_GRID applies to transient analysis only");
     if (!(out_flags & (TSB_OUT_WAVE | TSB_OUT_STATS))) return fail(ctx, TSB_E_INVALID, "no output selected");
-    std::vector<double> f((size_t)n_points);
-    // ac.go:100-126 (a single point divides by zero there: step = NaN, the one frequency is NaN; kept)
-    if (sweep_type == 0) {
-        const double ls = log10(fstart), le = log10(fstop), step = (le - ls) / (double)(n_points - 1);
-        for (int i = 0; i < n_points; ++i) f[i] = pow(10.0, ls + (double)i * step);
-    } else if (sweep_type == 1) {
-        const double ls = log2(fstart), le = log2(fstop), step = (le - ls) / (double)(n_points - 1);
-        for (int i = 0; i < n_points; ++i) f[i] = pow(2.0, ls + (double)i * step);
-    } else {
-        const double step = (fstop - fstart) / (double)(n_points - 1);
-        for (int i = 0; i < n_points; ++i) f[i] = fstart + (double)i * step;
-    }
+    std::vector<double> f;
+    ac_frequency_points(sweep_type, n_points, fstart, fstop, f);       // ac.go:100-126
     tsb_opts o = resolve(opts, p);
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;

@@ -113,6 +113,7 @@ void device_stamp_entries(const Plan& plan, int dev_index, std::vector<StampEntr
 // AddComplexElement calls of one device's StampAC in call order: (row, col, code); codes are listed at the definition.
 struct AcEntry { int row, col, code; double sign; };
 void device_ac_entries(const Plan& plan, int dev_index, std::vector<AcEntry>& out);
+void ac_frequency_points(int sweep_type, int n_points, double fstart, double fstop, std::vector<double>& f);
 int device_num_outputs(const Dev& d);
 // codegen.cpp
 struct CodegenConfig {
