@@ -73,6 +73,32 @@ def flops_per_solve(devs, n) -> dict:
     return dict(n=n, lu=f_lu_dense(n), stamp=stamp, conv=conv, total=f_lu_dense(n) + stamp + conv)
 
 
+def executed_flops(deck: str, strict: int = 0):
+    """FP64 flops per EXECUTED solve as ncu counted them (2*DFMA + DMUL + DADD, thread level; tests/gpu_flops.py ->
+    profiles/executed_flops.json), or None.  The generated kernels skip structural zeros, condense the invariant pivots and
+    hoist invariant stamps, so this is well below the dense-algorithm model above — `frac` is reported on THIS figure."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))["decks"].get(deck + (":strict" if strict else ""))
+        return float(e["flops_per_executed_solve"]) if e else None
+    except Exception:
+        return None
+
+
+def flop_fields(deck: str, strict: int, executed_solves: int, ms: float, model_flops: int, fp64_peak, n_gpus: int = 1) -> dict:
+    """tflops / frac of one launch.  Top level: ALGORITHMIC flops as SURVEY §8(d) defines them (dense n x n LU as the reference
+    factors it + stamps + convergence test, per executed solve) — the contract's roofline numerator; a value above 1 means
+    the kernel does less arithmetic than the algorithm's count (structural zeros skipped, invariant pivots condensed), like
+    DRAM traffic below the algorithmic bytes.  `executed`: the FP64 flops the kernel really issues (ncu opcode counts)."""
+    sec = ms * 1e-3
+    mt = executed_solves * model_flops / sec / 1e12
+    out = {"flops_per_solve": model_flops, "tflops": mt, "frac": mt / (fp64_peak * n_gpus) if fp64_peak else None}
+    fe = executed_flops(deck, strict)
+    et = executed_solves * fe / sec / 1e12 if fe else None
+    out["executed"] = {"flops_per_solve": fe, "tflops": et, "frac": et / (fp64_peak * n_gpus) if (fe and fp64_peak) else None,
+                       "source": "ncu opcode counts, 2*DFMA + DMUL + DADD (profiles/executed_flops.json)" if fe else "no capture for this deck"}
+    return out
+
+
 def ncu_json(key: str):
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
@@ -375,23 +401,32 @@ def main():
     dom = decks[-1]
     dom_tot = totals[dom["name"]]
     dom_solves = int(dom_tot[4])          # EXECUTED factor+solve passes (the redundant linear re-solve is not run, not counted)
-    dom_flops = dom_solves * dom["flops"]["total"]
     dom_ms = float(np.mean(ms_dom))
-    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    dom_ff = flop_fields(dom["name"], args.strict_fp, dom_solves, dom_ms, dom["flops"]["total"], fp64_peak)
+    ncu_dom = ncu_json(f"ncu:{dom['name']}:{n}:stats") or {}
+    # Issue-rate view of the same launch: the kernel's arithmetic is ~1/4 of its instructions (statistics, step control,
+    # state rotation, table look-ups are the rest), so the scheduler — 4 warp instructions per clock and SM — is the binding
+    # unit, not the FP64 pipe.  warp instructions per executed solve from the ncu capture x executed solves / time / peak.
+    wi = ncu_dom.get("warp_instructions_per_executed_solve")
+    issue_peak = 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+    issue = {"warp_instructions_per_executed_solve": wi, "achieved_per_s": dom_solves / 32 * wi / (dom_ms * 1e-3) if wi else None,
+             "peak_per_s": issue_peak, "frac": (dom_solves / 32 * wi / (dom_ms * 1e-3)) / issue_peak if wi else None,
+             "peak_source": "148 SMs x 4 schedulers x 1 warp instruction per clock x the SM clock sampled in this run"}
     roofline = {
-        "bound": "fp64", "kernel": "tsb_optran (rlc.cir)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_json(f"{dom['name']}:{n}:stats"),
+        "bound": "fp64", "kernel": "tsb_optran (rlc.cir)", "achieved": dom_ff["tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": dom_ff["frac"], "traffic": ncu_json(f"{dom['name']}:{n}:stats"),
         "peak_source": "DFMA-chain microbenchmark measured in this run (tsb_ctx_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-        "flops_per_solve": dom["flops"], "executed_solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
-        # `achieved` / `frac` count only the factor+solve passes this kernel EXECUTES (the conservative reading), at
-        # SURVEY §8(d)'s per-solve figure F_LU(n, dense as the reference factors it) + F_stamp + F_conv.  The work of the
-        # reference algorithm (two solves per step and the LTE-rejected solves, which this kernel proves redundant and
-        # does not run) is reported beside it, not instead of it.
-        "reference_algorithm": {
-            "flops_per_launch": int(dom_tot[2]) * dom["flops"]["total"], "solves_per_launch": int(dom_tot[2]),
-            "achieved": int(dom_tot[2]) * dom["flops"]["total"] / (dom_ms * 1e-3) / 1e12,
-            "frac": (int(dom_tot[2]) * dom["flops"]["total"] / (dom_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None},
-        "ncu": ncu_json(f"ncu:{dom['name']}:{n}:stats"),
+        # `achieved` / `frac`: ALGORITHMIC flops — SURVEY §8(d)'s per-solve figure F_LU(n, dense as the reference factors it) +
+        # F_stamp + F_conv x the factor+solve passes this kernel EXECUTES — over the measured FP64 peak (the same accounting
+        # as round 1's 0.404).  `executed`: the FP64 arithmetic the kernel really issues per solve (ncu opcode counts): the
+        # generated code skips structural zeros and, since round 2, eliminates the run-invariant pivots once per instance,
+        # so it issues ~1/3 of the algorithmic count.  Neither figure counts the reference's second solve per step or its
+        # LTE-rejected solves (proved redundant, not run): those are in `reference_algorithm`.
+        "flops_per_solve": dom["flops"], "executed": dom_ff["executed"],
+        "executed_solves_per_launch": dom_solves, "ms_per_launch": dom_ms,
+        "reference_algorithm": {"solves_per_launch": int(dom_tot[2]), "flops_per_launch": int(dom_tot[2]) * dom["flops"]["total"],
+                                "frac": (int(dom_tot[2]) * dom["flops"]["total"] / (dom_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None},
+        "issue": issue, "ncu": ncu_dom,
         "algorithmic_hbm_bytes_per_launch": n * (8 * 3 + 4 * dom["ncol"] * 8 + 8 + 4 + 6 * 8),
     }
 
@@ -494,10 +529,9 @@ def main():
         st = b.status()
         fl = flops_per_solve(ckt.devices(), ckt.n)
         steps = int(tot[0]) if an == T.AN_TRAN else int(cnt[7].sum())        # accepted steps / stored sweep points / 1 per OP
-        tf = int(tot[4]) * fl["total"] / (ms * 1e-3) / 1e12
         ent = {"deck": name, "analysis": {T.AN_OP: "op", T.AN_TRAN: "tran", T.AN_DC: "dc"}[an], "instances": hi - lo, "n": ckt.n,
                "ms_per_launch": ms, "steps": steps, "circuit_timesteps_per_sec": steps / (ms * 1e-3), "executed_solves": int(tot[4]),
-               "flops_per_solve": fl["total"], "tflops": tf, "frac": tf / fp64_peak if fp64_peak else None,
+               **flop_fields(name, args.strict_fp if strict is None else strict, int(tot[4]), ms, fl["total"], fp64_peak),
                "lane_util": lane_util(cnt[6]) if nl else 1.0,
                "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
                "nan_instances": int(np.isnan(b.stats_all()[3]).any(axis=0).sum()) if (an != T.AN_OP and hi - lo <= (1 << 22)) else None}
@@ -524,11 +558,10 @@ def main():
                             "decks": [{"deck": d["name"], "analysis": "tran", "instances": n, "n": d["ckt"].n,
                                        "ms_per_launch": float(np.mean([ms_steps[i] - ms_dom[i] for i in range(len(ms_dom))])) if d is decks[0] else dom_ms,
                                        "steps": int(totals[d["name"]][0]), "executed_solves": int(totals[d["name"]][4]),
-                                       "flops_per_solve": d["flops"]["total"], "lane_util": 1.0} for d in decks]})
+                                       "model_flops": d["flops"]["total"], "lane_util": 1.0} for d in decks]})
             for e in configs[-1]["decks"]:
                 e["circuit_timesteps_per_sec"] = e["steps"] / (e["ms_per_launch"] * 1e-3)
-                e["tflops"] = e["executed_solves"] * e["flops_per_solve"] / (e["ms_per_launch"] * 1e-3) / 1e12
-                e["frac"] = e["tflops"] / fp64_peak if fp64_peak else None
+                e.update(flop_fields(e["deck"], args.strict_fp, e["executed_solves"], e["ms_per_launch"], e.pop("model_flops"), fp64_peak))
             # [2] diode1-5: Monte Carlo over Is / n
             configs.append({"config": "configs[2] diode1-5.cir, Monte Carlo over Is / n (Newton with per-instance convergence masks)",
                             "decks": [measure_deck(nm, n20) for nm in ("diode2", "diode4", "diode1", "diode5", "diode3")]})
@@ -550,8 +583,7 @@ def main():
                     dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(w, op=dist.ReduceOp.SUM)
                     e["ms_per_launch"], e["steps"], e["executed_solves"], e["instances"] = float(t[0]), int(w[0]), int(w[1]), int(w[2])
                     e["circuit_timesteps_per_sec"] = e["steps"] / (e["ms_per_launch"] * 1e-3)
-                    e["tflops"] = e["executed_solves"] * e["flops_per_solve"] / (e["ms_per_launch"] * 1e-3) / 1e12
-                    e["frac"] = e["tflops"] / (fp64_peak * world) if fp64_peak else None
+                    e.update(flop_fields(e["deck"], args.strict_fp, e["executed_solves"], e["ms_per_launch"], e["flops_per_solve"], fp64_peak, world))
         t1 = [e for cfg in configs for e in cfg.get("decks", []) if e.get("deck") == "transformer1"]
         if t1:
             e = t1[0]

@@ -23,6 +23,7 @@ const (
 	anTran = int(C.TSB_AN_TRAN)
 	anDC   = int(C.TSB_AN_DC)
 	anDC2  = int(C.TSB_AN_DC2)
+	anAC   = int(C.TSB_AN_AC)
 )
 
 // base holds what the three analyses share.
@@ -76,6 +77,8 @@ func (a *base) firstFailure() error {
 		return fmt.Errorf("failed to converge at t=%g", a.batch.FailurePoint(0)) // tran.go:119
 	case C.TSB_ST_DC_FAILED:
 		return fmt.Errorf("convergence error at sweep value %g", a.batch.FailurePoint(0)) // dc.go:128
+	case C.TSB_ST_AC_FAILED:
+		return fmt.Errorf("matrix solve error at f=%g: matrix factorization failed", a.batch.FailurePoint(0)) // ac.go:68
 	}
 	return nil
 }
@@ -208,5 +211,45 @@ func (d *BatchDCSweep) GetResults() map[string][]float64 {
 		an = anDC2
 	}
 	r, _ := d.batch.Instance(0, an)
+	return r
+}
+
+// ---------------------------------------------------------------------------------------------- AC analysis
+// BatchAC keeps analysis.NewAC's parameter list (ac.go:21) after the netlist text.  Linear circuits only (tspice_b200.h:
+// tsb_run_ac); a circuit with an inductor fails at the first frequency exactly as the reference's does.
+type BatchAC struct {
+	base
+	fStart, fStop float64
+	nPoints       int
+	pType         string
+	RefRead       bool // TSB_OUT_AC_REFREAD: GetComplexSolution's literal index arithmetic over interleaved vectors
+}
+
+func NewBatchAC(netlistText string, fStart, fStop float64, nPoints int, pType string) *BatchAC {
+	return &BatchAC{base: base{Netlist: netlistText}, fStart: fStart, fStop: fStop, nPoints: nPoints, pType: pType}
+}
+
+func (a *BatchAC) Setup(ckt *circuit.Circuit) error { return a.setup(ckt) } // the operating point of ac.go:33-49 has no effect on a linear circuit's sweep
+
+func (a *BatchAC) Execute() error {
+	if a.batch == nil {
+		return fmt.Errorf("circuit not set") // ac.go:52-54
+	}
+	sweep := map[string]C.int{"DEC": 0, "OCT": 1, "LIN": 2}[a.pType]
+	out := C.int(a.Out)
+	if a.RefRead {
+		out |= C.TSB_OUT_AC_REFREAD
+	}
+	if rc := C.tsb_run_ac(a.batch.h, sweep, C.int(a.nPoints), C.double(a.fStart), C.double(a.fStop), out, nil); rc != C.TSB_OK {
+		return a.ctx.lastErr("tsb_run_ac")
+	}
+	if err := a.batch.Sync(); err != nil {
+		return err
+	}
+	return a.firstFailure()
+}
+
+func (a *BatchAC) GetResults() map[string][]float64 { // keys FREQ, V(n)_MAG, V(n)_PHASE, I(Vsrc)_MAG, I(Vsrc)_PHASE (anlysis.go:87-111)
+	r, _ := a.batch.Instance(0, anAC)
 	return r
 }

@@ -648,7 +648,7 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
             // must be the SAME arithmetic as tsb_tran_nonlinear's — the condensed elimination — or the result of an
             // instance would depend on the mapping that ran it
             if (is_tran) solved = c.template assemble_solve_tf<true>(time, dt, rdt, typename Ckt::TsbNoMid());
-            else solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, rdt, gmin);
+            else solved = c.template assemble_solve<-1>(mode, 0.0, 0.0, rdt, gmin);      // the very instantiation the other mappings' operating point runs
         } else solved = c.template assemble_solve<-1>(mode, is_tran ? time : 0.0, is_tran ? dt : 0.0, rdt, gmin);
         if (is_tran) ++n_sol_tran; else ++n_sol_op;
         ++n_exec;
