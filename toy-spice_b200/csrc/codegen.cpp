@@ -57,7 +57,7 @@ void emit_eval(Emitter& e, const Plan& pl, int di, const std::string& ov) {
     case TSB_C: e.line("tsb_cap_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
     case TSB_L: e.line("tsb_ind_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
     case TSB_LCORE: e.line("tsb_lcore_eval(D[" + std::to_string(d.d_off) + "], e, " + ov + ");"); break;
-    case TSB_D: e.line("tsb_dio_eval(" + P + ", " + S + ", e, " + ov + ");"); break;
+    case TSB_D: e.line("tsb_dio_eval(" + P + ", D + " + std::to_string(d.d_off) + ", " + S + ", e, " + ov + ");"); break;
     case TSB_Q: e.line("tsb_bjt_eval(" + P + ", " + S + ", " + std::to_string(d.ip.empty() ? 0 : d.ip[0]) + ", " + ov + ");"); break;
     case TSB_M:
         e.line("tsb_mos_eval(" + P + ", " + S + ", " + std::to_string(d.ip.size() > 0 ? d.ip[0] : 1) + ", " +
@@ -638,6 +638,7 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         if (d.kind == TSB_R) e.line("D[" + std::to_string(d.d_off) + "] = tsb_res_g(" + P + ");");
         else if (d.kind == TSB_L) e.line("tsb_ind_derive(" + P + ", D + " + std::to_string(d.d_off) + ");");
         else if (d.kind == TSB_LCORE) e.line("D[" + std::to_string(d.d_off) + "] = tsb_lcore_L0(" + P + ");");
+        else if (d.kind == TSB_D) e.line("tsb_dio_derive(" + P + ", D + " + std::to_string(d.d_off) + ");");
         else if (d.kind == TSB_M) e.line("tsb_mos_init_state(" + P + ", S + " + std::to_string(d.s_off) + ");");
         else if (d.kind == TSB_K) {
             int m = (int)d.ip.size(), q = 0;

@@ -89,6 +89,9 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #ifndef TSB_X_STATS_PRED
 #define TSB_X_STATS_PRED 1
 #endif
+#ifndef TSB_X_CONVSEL
+#define TSB_X_CONVSEL 1
+#endif
 #ifndef TSB_X_LTEFLAGS
 #define TSB_X_LTEFLAGS 1            // linear loop: truncation-error DECISIONS from predicates instead of selecting the maximum
 #endif
@@ -101,8 +104,11 @@ __device__ __forceinline__ bool tsb_converged(const double* x, const double* xo,
     bool ok = true;
 #pragma unroll
     for (int i = 1; i <= N; ++i) {
-        double diff = fabs(x[i] - xo[i]);
-        double tol = reltol * fmax(fabs(x[i]), fabs(xo[i])) + abstol;
+        const double diff = fabs(x[i] - xo[i]);
+        // math.Max(|new|, |old|) as a plain select: the two differ only when an operand is NaN — and then diff is NaN too, so
+        // `diff > tol` is false whatever tol is (the library fmax costs ~10 instructions per element for its NaN handling)
+        const double ax = fabs(x[i]), ao = fabs(xo[i]);
+        const double tol = reltol * (TSB_X_CONVSEL ? (ax > ao ? ax : ao) : fmax(ax, ao)) + abstol;
         if (diff > tol) ok = false;
     }
     return ok;

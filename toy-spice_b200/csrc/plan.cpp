@@ -236,6 +236,7 @@ struct Nominal {
             if (d.kind == TSB_R) D[d.d_off] = tsb_res_g(&P[d.p_off]);
             else if (d.kind == TSB_L) tsb_ind_derive(&P[d.p_off], &D[d.d_off]);
             else if (d.kind == TSB_LCORE) D[d.d_off] = tsb_lcore_L0(&P[d.p_off]);
+            else if (d.kind == TSB_D) tsb_dio_derive(&P[d.p_off], &D[d.d_off]);
             else if (d.kind == TSB_M) tsb_mos_init_state(&P[d.p_off], &S[d.s_off]);
             else if (d.kind == TSB_K) {
                 int m = (int)d.ip.size(), q = 0;
@@ -276,7 +277,7 @@ struct Nominal {
         case TSB_C: tsb_cap_eval(p, s, e, o); break;
         case TSB_L: tsb_ind_eval(p, s, e, o); break;
         case TSB_LCORE: tsb_lcore_eval(D[d.d_off], e, o); break;
-        case TSB_D: tsb_dio_eval(p, s, e, o); break;
+        case TSB_D: tsb_dio_eval(p, &D[d.d_off], s, e, o); break;
         case TSB_Q: tsb_bjt_eval(p, s, d.ip.empty() ? 0 : d.ip[0], o); break;
         case TSB_M: tsb_mos_eval(p, s, d.ip.size() > 0 ? d.ip[0] : 1, d.ip.size() > 1 ? d.ip[1] : 0, e, o); break;
         case TSB_K: {
@@ -506,7 +507,7 @@ int plan_finalize(Plan& pl) {
         d.n_state = state_size(d.kind); d.s_off = pl.n_state; pl.n_state += d.n_state;
         d.d_off = -1;
         if (d.kind == TSB_R || d.kind == TSB_LCORE) { d.d_off = pl.n_derived; pl.n_derived += 1; }
-        if (d.kind == TSB_L) { d.d_off = pl.n_derived; pl.n_derived += 3; }
+        if (d.kind == TSB_L || d.kind == TSB_D) { d.d_off = pl.n_derived; pl.n_derived += 3; }
         if (d.kind == TSB_K) { int m = (int)d.ip.size(); d.d_off = pl.n_derived; pl.n_derived += m * (m - 1) / 2; }
         if (d.nonlinear()) pl.has_nonlinear = true;
         if (d.time_dependent()) pl.has_time_dependent = true;
