@@ -122,7 +122,21 @@ typedef struct tsb_opts {
                            beside the main launch) publishes these per attempt, every other instance looks them up and
                            verifies (time, dt) bit for bit, computing them itself on a miss — results are bit-identical
                            with and without; 0: off; -1 (default): on for batches of >= 2^18 instances */
+    int coop_parts;     /* transient analysis of circuits without nonlinear devices, fast build: 2 or 4 = the cooperative mapping —
+                           the netlist is cut into that many sub-circuits joined by a small separator, and one instance is
+                           advanced by that many threads in different warps of a block (each eliminates its own sub-circuit;
+                           a few doubles per step attempt cross shared memory around one named barrier).  For circuits too
+                           large for one thread's registers (n >~ 14).  The elimination order is a nested-dissection order:
+                           results differ from the thread-per-circuit mapping by rounding (like the fast build's other
+                           re-associations).  TSB_E_UNSUPPORTED when the circuit has no such partition (see
+                           tsb_plan_coop_info), has nonlinear devices or mutual couplings, or with strict_fp / TSB_OUT_GRID.
+                           0 (default): off */
 } tsb_opts;
+
+/* The partition behind tsb_opts.coop_parts (parts = 2 or 4): owner[u] for every unknown u = 1..n (external numbering: nodes,
+   then branches; owner[0] unused) = the part that eliminates it, -1 = separator.  Returns TSB_E_UNSUPPORTED when the plan has
+   no partition into `parts` sub-circuits.  `owner` holds n + 1 ints; either pointer may be NULL. */
+int tsb_plan_coop_info(const tsb_plan* plan, int parts, int* owner, int* n_separator);
 
 /* Output selection for tsb_run_tran / tsb_run_dc. */
 enum {

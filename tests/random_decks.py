@@ -142,3 +142,35 @@ def rc_ladder(sections: int) -> str:
         lines.append(f"C{k} {k + 1} 0 100n")
     lines.append(".tran 0.01ms 3ms")
     return "\n".join(lines) + "\n"
+
+
+def rlc_ladder(sections: int) -> str:
+    """Vin - (R - L in series, C to ground) x sections: 2 nodes and one branch current per section."""
+    lines = [f"* RLC ladder, {sections} sections", "Vin 1 0 SIN(0 5 1k)"]
+    node = 1
+    for k in range(1, sections + 1):
+        lines.append(f"R{k} {node} {node + 1} 50")
+        lines.append(f"L{k} {node + 1} {node + 2} 1m")
+        lines.append(f"C{k} {node + 2} 0 100n")
+        node += 2
+    lines.append(".tran 0.01ms 1ms")
+    return "\n".join(lines) + "\n"
+
+
+def rc_mesh(rows: int, cols: int) -> str:
+    """rows x cols grid of nodes, a resistor between neighbours, a capacitor to ground at every node, driven at one corner
+    through a resistor: separators of a cut are whole rows / columns of the grid (several unknowns)."""
+    def nd(i, j):
+        return 2 + i * cols + j
+    lines = [f"* RC mesh {rows} x {cols}", "Vin 1 0 PULSE(0 5 0.1m 0.05m 0.05m 0.8m 2m)", f"Rin 1 {nd(0, 0)} 100"]
+    k = 0
+    for i in range(rows):
+        for j in range(cols):
+            lines.append(f"C{i}_{j} {nd(i, j)} 0 {50 + 10 * ((i * 7 + j * 3) % 9)}n")
+            if j + 1 < cols:
+                k += 1; lines.append(f"Rh{k} {nd(i, j)} {nd(i, j + 1)} {100 + 20 * ((i + 2 * j) % 5)}")
+            if i + 1 < rows:
+                k += 1; lines.append(f"Rv{k} {nd(i, j)} {nd(i + 1, j)} {150 + 30 * ((2 * i + j) % 4)}")
+    lines.append(f"Rload {nd(rows - 1, cols - 1)} 0 1k")
+    lines.append(".tran 0.01ms 2ms")
+    return "\n".join(lines) + "\n"

@@ -58,7 +58,7 @@ class TsbError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("abstol", C.c_double), ("reltol", C.c_double), ("gmin", C.c_double),
                 ("trtol", C.c_double), ("strict_fp", C.c_int), ("block_size", C.c_int), ("skip_linear_resolve", C.c_int), ("min_blocks", C.c_int), ("lane_refill", C.c_int), ("grid_dt", C.c_double),
-                ("share_time_grid", C.c_int)]
+                ("share_time_grid", C.c_int), ("coop_parts", C.c_int)]
 
 
 def lib_path() -> str:
@@ -104,6 +104,7 @@ def lib():
             "tsb_plan_structure": (i32, [vp, P(i32), P(i32), P(i32)]),
             "tsb_plan_pattern": (i32, [vp, i32, P(i32), P(i32), i32, P(i32)]),
             "tsb_plan_num_columns": (i32, [vp, i32]),
+            "tsb_plan_coop_info": (i32, [vp, i32, P(i32), P(i32)]),
             "tsb_plan_column_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
             "tsb_batch_create": (i32, [vp, i64, P(vp)]),
             "tsb_batch_destroy": (None, [vp]),
@@ -358,6 +359,14 @@ class Circuit:
         if i < 0:
             raise KeyError(name)
         return i
+
+    def coop_info(self, parts: int):
+        """tsb_plan_coop_info: owner[u] of every unknown u = 0..n for the cooperative mapping (tsb_opts.coop_parts): the part
+        that eliminates it, -1 = separator (owner[0] is unused); None when the netlist has no such partition."""
+        own = (C.c_int * (self.n + 1))()
+        nsep = C.c_int()
+        rc = lib().tsb_plan_coop_info(self.h, parts, own, C.byref(nsep))
+        return list(own) if rc == 0 else None
 
     def analysis_card(self) -> dict:
         an, uic, src = C.c_int(), C.c_int(), C.c_int()

@@ -12,6 +12,8 @@
 // with the per-device stamp arithmetic delegated to device/models.cuh and the analysis drivers
 // to device/skeleton.cuh (both embedded verbatim so the unit compiles under NVRTC and nvcc alike).
 #include <cstdio>
+#include <algorithm>
+#include <map>
 #include <set>
 #include <sstream>
 #include <vector>
@@ -24,6 +26,9 @@ static const char* k_models_src =
     ;
 static const char* k_skeleton_src =
 #include "skeleton_src.inc"
+    ;
+static const char* k_coop_src =
+#include "coop_src.inc"
     ;
 
 namespace {
@@ -570,7 +575,341 @@ void emit_ac(Emitter& e, const Plan& pl) {
     e.line("}");
 }
 
+
+// ---- cooperative mapping (CoopPlan, device/coop.cuh): one struct per part ----------------------------------------------------
+// The elimination program cp.lu is in nested-dissection order: steps 1..n_int eliminate the interiors (part 0's first),
+// the rest the separator.  Part p emits, for a solve,
+//   phase_a   the stamps of the devices it owns, the elimination steps of its interior, the forward substitution of its
+//             interior; what these add to separator entries / separator right-hand sides is its CONTRIBUTION, written to the
+//             exchange buffer (one slot per contributed value);
+//   phase_b   (after the barrier) the separator system summed over the contributions of all parts in part order — the same
+//             additions in the same order in every part, so every part holds the same bits — eliminated and solved by every
+//             part for itself, then the back substitution of the part's own interior.
+// Structural zeros are tracked symbolically per part (an entry no own device stamps and no own step fills does not exist
+// for that part), so a part touches only what its sub-circuit makes non-zero.
+struct CoopSym {
+    std::vector<int> devs;                 // own devices, stamp order
+    std::set<int> a_assigned, b_assigned;  // entries / rhs rows stamped by own devices
+    std::set<int> touched;                 // entries structurally non-zero in this part's view after its own elimination
+    std::vector<int> steps;                // own elimination steps, ascending
+    std::vector<int> xe, xc;               // contributed separator entries / separator steps with a rhs contribution
+    std::set<int> cnz;                     // steps (own and separator) whose c[] is structurally non-zero after the own forward pass
+    std::vector<int> cols;                 // own result columns, ascending (part 0: column 0 = TIME first)
+};
+
+static const int COOP_HDR = 2;             // exchange slots 0 (flags) and 1 (result-store key, part 0)
+
+void coop_analyse(const Plan& pl, const CoopPlan& cp, std::vector<CoopSym>& sym, int& nx) {
+    const LuProgram& lu = cp.lu;
+    const int n = lu.n;
+    sym.assign(cp.parts, CoopSym());
+    for (int di : pl.stamp_order) sym[cp.dev_owner[di]].devs.push_back(di);
+    for (int k = 1; k <= n; ++k) if (cp.step_owner[k] >= 0) sym[cp.step_owner[k]].steps.push_back(k);
+    for (size_t c = 0; c < cp.col_owner.size(); ++c) sym[cp.col_owner[c]].cols.push_back((int)c);
+    auto is_sep_entry = [&](int e) { return cp.owner[lu.pos[e].first] < 0 && cp.owner[lu.pos[e].second] < 0; };
+    nx = COOP_HDR;
+    for (int p = 0; p < cp.parts; ++p) {
+        CoopSym& y = sym[p];
+        for (int di : y.devs)
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (s.col == 0) y.b_assigned.insert(s.row);
+                else y.a_assigned.insert(lu.index.at({s.row, s.col}));
+            }
+        y.touched = y.a_assigned;
+        for (int k : y.steps) {
+            const LuProgram::Step& st = lu.steps[k];
+            for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+                if (!y.touched.count(st.urow[ui])) continue;
+                for (size_t li = 0; li < st.lcol.size(); ++li) if (y.touched.count(st.lcol[li])) y.touched.insert(st.target[ui][li]);
+            }
+        }
+        for (int e : y.touched) if (is_sep_entry(e)) y.xe.push_back(e);
+        for (int k = 1; k <= n; ++k) if (y.b_assigned.count(lu.prow[k]) && (cp.step_owner[k] == p || cp.step_owner[k] < 0)) y.cnz.insert(k);
+        for (int k : y.steps) {
+            if (!y.cnz.count(k)) continue;
+            const LuProgram::Step& st = lu.steps[k];
+            for (size_t li = 0; li < st.lcol.size(); ++li) if (y.touched.count(st.lcol[li])) y.cnz.insert(st.lrow_step[li]);
+        }
+        for (int k = cp.n_int + 1; k <= n; ++k) if (y.cnz.count(k)) y.xc.push_back(k);
+        nx = std::max(nx, COOP_HDR + (int)y.xe.size() + (int)y.xc.size());
+    }
+}
+
+void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConfig& cfg) {
+    const LuProgram& lu = cp.lu;
+    const int n = lu.n, NP = cp.parts;
+    auto S = [](int k) { return std::to_string(k); };
+    std::vector<CoopSym> sym;
+    int nx = 0;
+    coop_analyse(pl, cp, sym, nx);
+    int nown_max = 0;
+    for (const CoopSym& y : sym) nown_max = std::max(nown_max, (int)y.cols.size());
+    e.line("#define TSB_COOP_PARTS " + S(NP));
+    e.line("#define TSB_COOP_NX " + S(nx) + "          // exchange slots per part and attempt");
+    e.line("#define TSB_COOP_NOWN_MAX " + S(nown_max) + "   // result columns of the widest part");
+    e.line("#define TSB_COOP_NCOL " + S((int)cp.col_owner.size()));
+    // the separator system after the gather: which entries / right-hand sides exist, for every part alike
+    std::set<int> sep_touched, sep_cnz;
+    for (const CoopSym& y : sym) { sep_touched.insert(y.xe.begin(), y.xe.end()); sep_cnz.insert(y.xc.begin(), y.xc.end()); }
+    for (int p = 0; p < NP; ++p) {
+        const CoopSym& y = sym[p];
+        Plan sub = pl;                          // same numbering, own devices only: the stamp emitters work unchanged
+        sub.stamp_order = y.devs;
+        e.line("struct CoopPart" + S(p) + " {");
+        ++e.ind;
+        e.line("static constexpr int PART = " + S(p) + ", NOWN = " + S((int)y.cols.size()) + ", N = " + S(n) + ";");
+        e.line("double P[" + S(std::max(1, pl.n_params)) + "], S[" + S(std::max(1, pl.n_state)) + "], D[" + S(std::max(1, pl.n_derived)) + "], SV[" +
+               S(std::max(1, pl.n_src)) + "], x[" + S(n + 1) + "];     // global numbering; only this part's elements are ever touched");
+        e.line("double A[" + S((int)lu.pos.size()) + "], c[" + S(n + 1) + "];   // factors / substitution vector kept from phase_a to phase_b");
+        e.line("const double* U_;");
+        e.line("__device__ __forceinline__ int col(int j) const {");
+        {
+            std::string tab;
+            for (size_t j = 0; j < y.cols.size(); ++j) tab += (j ? ", " : "") + S(y.cols[j]);
+            e.line("    constexpr int C[" + S(std::max<size_t>(1, y.cols.size())) + "] = {" + (tab.empty() ? "0" : tab) + "};");
+            e.line("    return C[j];");
+        }
+        e.line("}");
+        // ---- load: own parameters, derived values, the state the operating point left (tsb_optran's hand-over) ----
+        e.line("__device__ __forceinline__ void load(const TsbArgs& a, long long inst) {");
+        ++e.ind;
+        e.line("U_ = a.U;");
+        for (int di : y.devs) {
+            const Dev& d = pl.devs[di];
+            if (!((d.kind == TSB_V || d.kind == TSB_I) && d.src_type() == TSB_SRC_PWL))
+                for (size_t j = 0; j < d.p.size(); ++j) {
+                    int k = d.p_off + (int)j;
+                    if (cfg.varying[k]) e.line("P[" + S(k) + "] = __ldcs(a.pv[" + S(cfg.var_slot[k]) + "] + inst);   // " + d.name + " p" + S((int)j));
+                    else e.line("P[" + S(k) + "] = a." + (k < 32 ? "Uc[" : "U[") + S(k) + "];");
+                }
+            std::string P = "P + " + S(d.p_off);
+            if (d.kind == TSB_R) e.line("D[" + S(d.d_off) + "] = tsb_res_g(" + P + ");");
+            else if (d.kind == TSB_L) e.line("tsb_ind_derive(" + P + ", D + " + S(d.d_off) + ");");
+            else if (d.kind == TSB_LCORE) e.line("D[" + S(d.d_off) + "] = tsb_lcore_L0(" + P + ");");
+            for (int q = 0; q < d.n_state; ++q) e.line("S[" + S(d.s_off + q) + "] = a.coop_state[(long long)" + S(d.s_off + q) + " * a.n_inst + inst];");
+            if (d.src_slot >= 0) e.line("SV[" + S(d.src_slot) + "] = 0.0;");
+        }
+        for (int u = 1; u <= n; ++u)
+            if (cp.owner[u] == p || cp.owner[u] < 0) e.line("x[" + S(u) + "] = a.coop_state[(long long)" + S(pl.n_state + u) + " * a.n_inst + inst];");
+        e.line("x[0] = 0.0;");
+        --e.ind;
+        e.line("}");
+        // ---- sources --------------------------------------------------------------------------------------------
+        for (int nb = 0; nb < 2; ++nb) {
+            e.line(nb ? "__device__ __forceinline__ bool eval_sources_nb(double t) {" : "__device__ __forceinline__ void eval_sources(double t, double fac) {");
+            ++e.ind;
+            if (nb) e.line("bool ok = true;");
+            for (int di : y.devs) {
+                const Dev& d = pl.devs[di];
+                if (d.src_slot < 0) continue;
+                std::string sv = "SV[" + S(d.src_slot) + "]", P = "P + " + S(d.p_off);
+                std::string fac = nb ? "1.0" : (d.kind == TSB_V ? "fac" : "1.0");
+                switch (d.src_type()) {
+                case TSB_SRC_DC: e.line(sv + " = P[" + S(d.p_off) + "] * " + fac + ";"); break;
+                case TSB_SRC_SIN: e.line(sv + (nb ? " = tsb_src_sin_nb(" + P + ", t, ok);" : " = tsb_src_sin(" + P + ", t, " + fac + ");")); break;
+                case TSB_SRC_PULSE: e.line(sv + " = tsb_src_pulse(" + P + ", t);"); break;
+                case TSB_SRC_PWL: e.line(sv + " = tsb_src_pwl(U_ + " + S(d.p_off) + ", " + S((int)d.p.size() / 2) + ", t);"); break;
+                }
+            }
+            e.line(nb ? "(void)t; return ok;" : "(void)t; (void)fac;");
+            --e.ind;
+            e.line("}");
+        }
+        // ---- truncation-error decisions of the own devices (Ckt::lte_flags restricted; OR / AND over parts is exact) ----
+        e.line("__device__ __forceinline__ void lte_flags(double dt, double rdt, double trtol, double thr, bool& gt, bool& small) {");
+        ++e.ind;
+        e.line("gt = false; small = 0.0 < thr;");
+        for (int di : y.devs) {
+            const Dev& d = pl.devs[di];
+            if (d.kind == TSB_C)
+                e.line("{ const double l = tsb_cap_lte(P + " + S(d.p_off) + ", S + " + S(d.s_off) + ", dt, rdt); gt = gt | (l > trtol); small = small & !(l >= thr); }");
+            else if (d.kind == TSB_L) {
+                e.line("{ double cu, vo; tsb_ind_lte2(S + " + S(d.s_off) + ", dt, rdt, cu, vo);");
+                e.line("  const bool nan = ((cu != cu) | (vo != vo)) & !((cu == TSB_INF) | (vo == TSB_INF));");
+                e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol))); small = small & !(!nan & ((cu >= thr) | (vo >= thr))); }");
+            }
+        }
+        e.line("(void)dt; (void)rdt; (void)trtol;");
+        --e.ind;
+        e.line("}");
+        // ---- phase_a ----------------------------------------------------------------------------------------------
+        e.line("// stamps, own elimination, own forward substitution; contributions -> xb[slot * 32] (this lane's column of the buffer)");
+        e.line("__device__ __forceinline__ bool phase_a(double time, double dt, double rdt, double* xb) {");
+        ++e.ind;
+        e.line("TsbEnv e; e.mode = TSB_MODE_TRAN; e.time = time; e.dt = dt; e.gmin = 0.0; e.rdt = rdt;");
+        e.line("double b[" + S(n + 1) + "];");
+        for (int k : y.touched) if (!y.a_assigned.count(k)) e.line("A[" + S(k) + "] = 0.0;   // fill (" + S(lu.pos[k].first) + "," + S(lu.pos[k].second) + ")");
+        emit_stamps(e, sub, lu, false, false, true, nullptr);
+        e.line("bool lu_ok = true;");
+        for (int k : y.steps) {
+            const LuProgram::Step& st = lu.steps[k];
+            const std::string piv = "A[" + S(st.piv) + "]";
+            e.line("// step " + S(k) + ": pivot (" + S(lu.prow[k]) + "," + S(lu.pcol[k]) + ")");
+            if (!y.touched.count(st.piv)) e.line(piv + " = 0.0;");
+            e.line("lu_ok = lu_ok & (" + piv + " != 0.0);");
+            e.line(piv + " = tsb_rcp(" + piv + ");");
+            for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+                if (!y.touched.count(st.urow[ui])) continue;
+                const std::string u = "A[" + S(st.urow[ui]) + "]";
+                e.line(u + " *= " + piv + ";");
+                for (size_t li = 0; li < st.lcol.size(); ++li)
+                    if (y.touched.count(st.lcol[li])) e.line("A[" + S(st.target[ui][li]) + "] -= " + u + " * A[" + S(st.lcol[li]) + "];");
+            }
+        }
+        {   // forward substitution over the own steps; separator rows collect this part's share
+            std::set<int> nz;                      // c[k] assigned so far
+            auto init_c = [&](int k) {
+                if (nz.count(k)) return;
+                nz.insert(k);
+                e.line("c[" + S(k) + "] = " + (y.b_assigned.count(lu.prow[k]) ? "b[" + S(lu.prow[k]) + "]" : std::string("0.0")) + ";");
+            };
+            for (int k = 1; k <= n; ++k) if (y.cnz.count(k) && y.b_assigned.count(lu.prow[k])) init_c(k);
+            for (int k : y.steps) {
+                if (!y.cnz.count(k)) continue;
+                init_c(k);
+                const LuProgram::Step& st = lu.steps[k];
+                e.line("c[" + S(k) + "] *= A[" + S(st.piv) + "];");
+                for (size_t li = 0; li < st.lcol.size(); ++li) {
+                    if (!y.touched.count(st.lcol[li])) continue;
+                    const int j = st.lrow_step[li];
+                    const std::string prod = "c[" + S(k) + "] * A[" + S(st.lcol[li]) + "]";
+                    if (!nz.count(j)) { nz.insert(j); e.line("c[" + S(j) + "] = -(" + prod + ");"); }
+                    else e.line("c[" + S(j) + "] -= " + prod + ";");
+                }
+            }
+        }
+        {
+            int slot = COOP_HDR;
+            for (int k : y.xe) e.line("xb[" + S(slot++) + " * 32] = A[" + S(k) + "];");
+            for (int k : y.xc) e.line("xb[" + S(slot++) + " * 32] = c[" + S(k) + "];");
+        }
+        e.line("(void)b; (void)e;");
+        e.line("return lu_ok;");
+        --e.ind;
+        e.line("}");
+        // ---- phase_b ----------------------------------------------------------------------------------------------
+        e.line("// xall: the attempt's exchange buffer, [part][slot][lane] with this lane's offset already applied");
+        e.line("__device__ __forceinline__ bool phase_b(const double* xall) {");
+        ++e.ind;
+        e.line("bool lu_ok = true;");
+        auto gather = [&](const std::string& tgt, bool entry, int k) {
+            std::string sum;
+            for (int q = 0; q < NP; ++q) {
+                const std::vector<int>& lst = entry ? sym[q].xe : sym[q].xc;
+                auto it = std::find(lst.begin(), lst.end(), k);
+                if (it == lst.end()) continue;
+                const int slot = COOP_HDR + (int)(it - lst.begin()) + (entry ? 0 : (int)sym[q].xe.size());
+                sum += (sum.empty() ? "" : " + ") + std::string("xall[") + S(q * nx + slot) + " * 32]";
+            }
+            e.line(tgt + " = " + (sum.empty() ? "0.0" : sum) + ";");
+        };
+        std::set<int> st_touched = sep_touched;
+        for (int k : sep_touched) gather("A[" + S(k) + "]", true, k);
+        std::vector<char> cz(n + 1, 1);
+        for (int k = cp.n_int + 1; k <= n; ++k) if (sep_cnz.count(k)) { gather("c[" + S(k) + "]", false, k); cz[k] = 0; }
+        for (int k : y.steps) cz[k] = y.cnz.count(k) ? 0 : 1;
+        for (int k = cp.n_int + 1; k <= n; ++k) {         // the separator's elimination steps, by every part alike
+            const LuProgram::Step& st = lu.steps[k];
+            const std::string piv = "A[" + S(st.piv) + "]";
+            e.line("// separator step " + S(k) + ": pivot (" + S(lu.prow[k]) + "," + S(lu.pcol[k]) + ")");
+            if (!st_touched.count(st.piv)) { e.line(piv + " = 0.0;"); st_touched.insert(st.piv); }
+            e.line("lu_ok = lu_ok & (" + piv + " != 0.0);");
+            e.line(piv + " = tsb_rcp(" + piv + ");");
+            for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+                if (!st_touched.count(st.urow[ui])) continue;
+                const std::string u = "A[" + S(st.urow[ui]) + "]";
+                e.line(u + " *= " + piv + ";");
+                for (size_t li = 0; li < st.lcol.size(); ++li) {
+                    if (!st_touched.count(st.lcol[li])) continue;
+                    const int t = st.target[ui][li];
+                    const std::string prod = u + " * A[" + S(st.lcol[li]) + "]";
+                    if (!st_touched.count(t)) { st_touched.insert(t); e.line("A[" + S(t) + "] = -(" + prod + ");"); }
+                    else e.line("A[" + S(t) + "] -= " + prod + ";");
+                }
+            }
+        }
+        for (int k = cp.n_int + 1; k <= n; ++k) {         // forward
+            if (cz[k]) continue;
+            const LuProgram::Step& st = lu.steps[k];
+            e.line("c[" + S(k) + "] *= A[" + S(st.piv) + "];");
+            for (size_t li = 0; li < st.lcol.size(); ++li) {
+                if (!st_touched.count(st.lcol[li])) continue;
+                const int j = st.lrow_step[li];
+                const std::string prod = "c[" + S(k) + "] * A[" + S(st.lcol[li]) + "]";
+                if (cz[j]) { cz[j] = 0; e.line("c[" + S(j) + "] = -(" + prod + ");"); }
+                else e.line("c[" + S(j) + "] -= " + prod + ";");
+            }
+        }
+        auto back = [&](int k, const std::set<int>& tch) {
+            const LuProgram::Step& st = lu.steps[k];
+            for (size_t ui = 0; ui < st.urow.size(); ++ui) {
+                if (!tch.count(st.urow[ui])) continue;
+                const int j = st.ucol_step[ui];
+                if (cz[j]) continue;
+                const std::string prod = "A[" + S(st.urow[ui]) + "] * c[" + S(j) + "]";
+                if (cz[k]) { cz[k] = 0; e.line("c[" + S(k) + "] = -(" + prod + ");"); }
+                else e.line("c[" + S(k) + "] -= " + prod + ";");
+            }
+        };
+        for (int k = n; k > cp.n_int; --k) back(k, st_touched);
+        for (auto it = y.steps.rbegin(); it != y.steps.rend(); ++it) back(*it, y.touched);
+        for (int k = cp.n_int + 1; k <= n; ++k) e.line("x[" + S(lu.pcol[k]) + "] = " + (cz[k] ? std::string("0.0") : "c[" + S(k) + "]") + ";");
+        for (int k : y.steps) e.line("x[" + S(lu.pcol[k]) + "] = " + (cz[k] ? std::string("0.0") : "c[" + S(k) + "]") + ";");
+        e.line("return lu_ok;");
+        --e.ind;
+        e.line("}");
+        // ---- state of the own time-dependent devices, own result columns --------------------------------------------
+        auto vd_expr = [&](const Dev& d) { return "(x[" + S(d.nodes[0]) + "] - x[" + S(d.nodes[1]) + "])"; };
+        e.line("__device__ __forceinline__ void load_state(double dt) {");
+        ++e.ind;
+        for (int di : y.devs) {
+            const Dev& d = pl.devs[di];
+            if (d.kind == TSB_L) e.line("tsb_ind_load(P + " + S(d.p_off) + ", D + " + S(d.d_off) + ", S + " + S(d.s_off) + ", " + vd_expr(d) + ", dt);");
+        }
+        e.line("(void)dt;");
+        --e.ind;
+        e.line("}");
+        e.line("__device__ __forceinline__ void update_state() {");
+        ++e.ind;
+        for (int di : y.devs) {
+            const Dev& d = pl.devs[di];
+            if (d.kind == TSB_C) e.line("tsb_cap_update(P + " + S(d.p_off) + ", S + " + S(d.s_off) + ", " + vd_expr(d) + ");");
+            if (d.kind == TSB_L) e.line("tsb_ind_update(D + " + S(d.d_off) + ", S + " + S(d.s_off) + ", " + vd_expr(d) + ");");
+        }
+        --e.ind;
+        e.line("}");
+        e.line("__device__ __forceinline__ void signals(double time, double* out) const {   // own columns of [TIME, GetSolution()...]");
+        ++e.ind;
+        {
+            std::map<int, int> rcol;                // result column -> resistor device
+            int c = n + 1;
+            for (size_t di = 0; di < pl.devs.size(); ++di) if (pl.devs[di].kind == TSB_R) rcol[c++] = (int)di;
+            for (size_t j = 0; j < y.cols.size(); ++j) {
+                const int col = y.cols[j];
+                std::string v;
+                if (col == 0) v = "time";
+                else if (col <= pl.n_nodes) v = "x[" + S(col) + "]";
+                else if (col <= n) v = "-x[" + S(col) + "]";
+                else { const Dev& d = pl.devs[rcol.at(col)]; v = "tsb_div_by(x[" + S(d.nodes[0]) + "] - x[" + S(d.nodes[1]) + "], P[" + S(d.p_off) + "], D[" + S(d.d_off) + "])"; }
+                e.line("out[" + S((int)j) + "] = " + v + ";");
+            }
+        }
+        e.line("(void)time; (void)out;");
+        --e.ind;
+        e.line("}");
+        --e.ind;
+        e.line("};");
+    }
+}
+
 }  // namespace
+
+void coop_dimensions(const Plan& pl, const CoopPlan& cp, int& nx, int& nown_max) {
+    std::vector<CoopSym> sym;
+    coop_analyse(pl, cp, sym, nx);
+    nown_max = 0;
+    for (const CoopSym& y : sym) nown_max = std::max(nown_max, (int)y.cols.size());
+}
 
 std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     Emitter e;
@@ -587,6 +926,9 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("#define TSB_GRID " + std::to_string(cfg.grid ? 1 : 0));
     e.line("#define TSB_ORDER " + std::to_string(cfg.order ? 1 : 0));
     e.line("#define TSB_TGRID " + std::to_string(cfg.tgrid && !pl.has_nonlinear && cfg.skip_linear ? 1 : 0));
+    const CoopPlan* coop = nullptr;          // cooperative transient kernels ride along (device/coop.cuh)
+    if (cfg.coop_parts > 0 && cfg.fast_div) { auto it = pl.coop.find(cfg.coop_parts); if (it != pl.coop.end()) coop = &it->second; }
+    if (coop) e.line("#define TSB_COOP 1");
     if (!cfg.extra_defines.empty()) e.os << cfg.extra_defines << "\n";     // development knob ($TSB_EXTRA_DEFINES)
     e.os << k_models_src << "\n" << k_skeleton_src << "\n";
 
@@ -907,6 +1249,13 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     --e.ind;
     e.line("}");
 
+    if (coop) {
+        e.line("// hand-over to the cooperative transient kernel: device state and solution, instance-fastest");
+        e.line("__device__ __forceinline__ void dump_state(double* o, long long n_inst, long long inst) const {");
+        for (int i = 0; i < pl.n_state; ++i) e.line("    o[(long long)" + std::to_string(i) + " * n_inst + inst] = S[" + std::to_string(i) + "];");
+        for (int i = 0; i <= n; ++i) e.line("    o[(long long)" + std::to_string(pl.n_state + i) + " * n_inst + inst] = x[" + std::to_string(i) + "];");
+        e.line("}");
+    }
     // ---- signals -----------------------------------------------------------------------------------
     e.line("__device__ __forceinline__ void signals(double* out) const {   // circuit.GetSolution (circuit.go:242-273)");
     ++e.ind;
@@ -923,6 +1272,35 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     --e.ind;
     e.line("};");
     e.line("");
+    if (coop) {
+        const int groups = cfg.coop_groups > 0 ? cfg.coop_groups : 1;
+        const int cblock = 32 * coop->parts * groups;
+        e.line("#define TSB_COOP_BLOCK " + std::to_string(cblock));
+        e.line("#ifndef TSB_COOP_MIN_BLOCKS");
+        e.line("#define TSB_COOP_MIN_BLOCKS " + std::to_string(std::max(1, 384 / cblock)));
+        e.line("#endif");
+        emit_coop(e, pl, *coop, cfg);
+        e.os << k_coop_src << "\n";
+        e.line("// One group of TSB_COOP_PARTS warps per 32 instances: warp w runs part w % PARTS of the instances of group w / PARTS.");
+        e.line("// Every part is a loop nest of its own behind an early return (a switch inside one shared loop made ptxas spill");
+        e.line("// ten times as much: 1432 instead of 140 bytes at 168 registers).");
+        e.line("template <class Part> __device__ __forceinline__ void tsb_coop_loop(const TsbArgs& a, double* xg, int group, int lane) {");
+        e.line("    constexpr int G = TSB_COOP_BLOCK / (32 * TSB_COOP_PARTS);");
+        e.line("    for (long long base = (long long)blockIdx.x * (G * 32); base < a.n_run; base += (long long)gridDim.x * (G * 32)) {");
+        e.line("        const long long slot = base + group * 32 + lane;");
+        e.line("        const bool valid = slot < a.n_run;");
+        e.line("        tsb_coop_tran_part<Part>(a, tsb_slot_instance(a, slot, valid), valid, xg, 1 + group);");
+        e.line("    }");
+        e.line("}");
+        e.line("extern \"C\" __global__ void __launch_bounds__(TSB_COOP_BLOCK, TSB_COOP_MIN_BLOCKS) tsb_coop_tran(TsbArgs a) {");
+        e.line("    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;");
+        e.line("    const int part = warp % TSB_COOP_PARTS, group = warp / TSB_COOP_PARTS;");
+        e.line("    double* xg = tsb_smem + 4 * TSB_COOP_NOWN_MAX * TSB_COOP_BLOCK + group * (2 * TSB_COOP_PARTS * TSB_COOP_NX * 32);");
+        for (int p2 = 0; p2 + 1 < coop->parts; ++p2)
+            e.line("    if (part == " + std::to_string(p2) + ") { tsb_coop_loop<CoopPart" + std::to_string(p2) + ">(a, xg, group, lane); return; }");
+        e.line("    tsb_coop_loop<CoopPart" + std::to_string(coop->parts - 1) + ">(a, xg, group, lane);");
+        e.line("}");
+    }
     e.line("extern \"C\" __global__ void __launch_bounds__(TSB_BLOCK, TSB_MIN_BLOCKS) tsb_optran(TsbArgs a) {");
     e.line("    if (Ckt::HAS_NL && TSB_LANE_REFILL) {   // persistent lanes: finished lanes refill themselves from a.work_counter");
     e.line("        long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;");

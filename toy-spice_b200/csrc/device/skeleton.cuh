@@ -65,6 +65,10 @@ struct TsbArgs {
     // that is the same for every instance can be an instruction operand (or be re-read) instead of occupying a register
     // pair of every thread for the whole run.  U (global memory) keeps the full table (PWL points, parameters beyond).
     double Uc[TSB_UC_MAX];
+    // Cooperative mapping (device/coop.cuh, kernels generated with TSB_COOP): the operating point runs thread-per-circuit in
+    // tsb_optran, which then hands the device state and the solution over — [n_state + N + 1][n_inst] doubles — instead of
+    // running the transient itself; tsb_coop_tran picks them up.  NULL: tsb_optran runs the whole analysis.
+    double* coop_state;
 };
 
 // Slot -> instance.  With an order, lanes of a warp can be given instances that behave alike (similar Newton
@@ -86,6 +90,9 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #define TSB_OUT_GRID 4
 #define TSB_OUT_AC_REFREAD 8
 
+#ifndef TSB_COOP
+#define TSB_COOP 0
+#endif
 #ifndef TSB_X_STATS_PRED
 #define TSB_X_STATS_PRED 1
 #endif
@@ -780,6 +787,13 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         }
     }
     if (LINEAR_LOOP) {
+#if TSB_COOP
+        if (a.coop_state) {           // hand-over to the cooperative transient kernel (status != OK: it has nothing to run)
+            if (linear_tran) c.dump_state(a.coop_state, a.n_inst, inst);
+            finish_instance();
+            return;
+        }
+#endif
         // the operating point(s) ran in the loop above; the transient of a linear circuit has its own loop, kept
         // outside so that its register allocation is not entangled with the Newton state machine
         if (linear_tran) tsb_tran_linear(a, c, sink, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);

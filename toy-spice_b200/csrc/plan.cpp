@@ -465,6 +465,180 @@ static void build_tranfast(Plan& pl, Nominal& nom) {
     pl.has_tranfast = true;
 }
 
+
+// ---- cooperative mapping: partition + nested-dissection order (CoopPlan, tsb_internal.hpp) ---------------------------------
+// Graph: one vertex per unknown, a clique per device over the unknowns it stamps or reads.  Recursive bisection by
+// breadth-first level sets (every root, every level tried; the cheapest separator that leaves two non-empty sides wins,
+// ties to the better balance), then a pass that returns separator vertices with neighbours on one side only to that side.
+// The graphs are tiny (n <= 64), so exhaustive search over roots and levels costs nothing.
+namespace coop_detail {
+
+struct Cut { std::vector<int> A, B, S; bool ok = false; };
+
+Cut bisect(const std::vector<int>& V, const std::vector<std::vector<char>>& adj, int n) {
+    Cut best; long best_score = -1;
+    std::vector<char> in(n + 1, 0);
+    for (int v : V) in[v] = 1;
+    for (int root : V) {
+        std::vector<int> level(n + 1, -1), q{root};
+        level[root] = 0;
+        int k = 0;
+        for (size_t h = 0; h < q.size(); ++h) {
+            int v = q[h];
+            for (int w = 1; w <= n; ++w) if (in[w] && adj[v][w] && level[w] < 0) { level[w] = level[v] + 1; k = std::max(k, level[w]); q.push_back(w); }
+        }
+        for (int i = 0; i <= k; ++i) {          // i = 0: only meaningful when the subgraph is disconnected (empty separator)
+            std::vector<int> side(n + 1, 0);     // 1 A, 2 B, 3 S
+            int nA = 0, nB = 0;
+            for (int v : V) {
+                if (level[v] < 0) continue;
+                if (i == 0) { side[v] = 1; ++nA; }
+                else if (level[v] < i) { side[v] = 1; ++nA; }
+                else if (level[v] == i) side[v] = 3;
+                else { side[v] = 2; ++nB; }
+            }
+            for (int v : V) if (level[v] < 0) { if (nA <= nB) { side[v] = 1; ++nA; } else { side[v] = 2; ++nB; } }   // other components
+            for (int v : V) {                     // a separator vertex that touches one side only belongs to that side
+                if (side[v] != 3) continue;
+                bool tA = false, tB = false;
+                for (int w : V) if (adj[v][w]) { if (side[w] == 1) tA = true; if (side[w] == 2) tB = true; }
+                if (tA && tB) continue;
+                if (tA || (!tB && nA <= nB)) { side[v] = 1; ++nA; } else { side[v] = 2; ++nB; }
+            }
+            if (nA == 0 || nB == 0) continue;
+            int nS = 0;
+            for (int v : V) if (side[v] == 3) ++nS;
+            bool clean = true;                    // (the moves above cannot connect A and B, checked anyway)
+            for (int v : V) for (int w : V) if (adj[v][w] && side[v] == 1 && side[w] == 2) clean = false;
+            if (!clean) continue;
+            long score = 2L * nS + std::labs((long)nA - nB);
+            if (best_score < 0 || score < best_score) {
+                best_score = score; best = Cut(); best.ok = true;
+                for (int v : V) (side[v] == 1 ? best.A : side[v] == 2 ? best.B : best.S).push_back(v);
+            }
+        }
+    }
+    return best;
+}
+
+}  // namespace coop_detail
+
+static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
+    const int n = pl.n();
+    if (pl.has_nonlinear || pl.has_mutual || n < 2 * parts || n > 64 || (parts != 2 && parts != 4)) return false;
+    // ---- graph ------------------------------------------------------------------------------------------------------------
+    std::vector<std::vector<char>> adj(n + 1, std::vector<char>(n + 1, 0));
+    std::vector<std::vector<int>> dev_unk(pl.devs.size());
+    for (size_t di = 0; di < pl.devs.size(); ++di) {
+        const Dev& d = pl.devs[di];
+        std::set<int> u;
+        for (const StampEntry& s : pl.stamps[di]) { if (s.row) u.insert(s.row); if (s.col) u.insert(s.col); }
+        for (int i = 0; i < d.n_nodes; ++i) if (d.nodes[i]) u.insert(d.nodes[i]);
+        if (d.branch > pl.n_nodes) u.insert(d.branch);
+        dev_unk[di].assign(u.begin(), u.end());
+        for (int a : u) for (int b : u) if (a != b) adj[a][b] = 1;
+    }
+    // ---- partition ---------------------------------------------------------------------------------------------------------
+    cp = CoopPlan();
+    cp.parts = parts;
+    cp.owner.assign(n + 1, -1);
+    std::vector<int> all;
+    for (int v = 1; v <= n; ++v) all.push_back(v);
+    coop_detail::Cut top = coop_detail::bisect(all, adj, n);
+    if (!top.ok) return false;
+    std::vector<std::vector<int>> interior;
+    if (parts == 2) { interior = {top.A, top.B}; }
+    else {
+        coop_detail::Cut ca = coop_detail::bisect(top.A, adj, n), cb = coop_detail::bisect(top.B, adj, n);
+        if (!ca.ok || !cb.ok) return false;
+        interior = {ca.A, ca.B, cb.A, cb.B};
+    }
+    for (int p = 0; p < parts; ++p) {
+        if (interior[p].empty()) return false;
+        std::sort(interior[p].begin(), interior[p].end());
+        for (int v : interior[p]) cp.owner[v] = p;
+    }
+    // ---- devices and result columns ---------------------------------------------------------------------------------------
+    cp.dev_owner.assign(pl.devs.size(), -1);
+    std::vector<int> load(parts, 0);
+    for (size_t di = 0; di < pl.devs.size(); ++di) {
+        int own = -1;
+        for (int u : dev_unk[di]) if (cp.owner[u] >= 0) { if (own >= 0 && own != cp.owner[u]) return false; own = cp.owner[u]; }
+        cp.dev_owner[di] = own;
+        if (own >= 0) ++load[own];
+    }
+    for (size_t di = 0; di < pl.devs.size(); ++di)           // devices between separator unknowns only: to the least loaded part
+        if (cp.dev_owner[di] < 0) { int p = (int)(std::min_element(load.begin(), load.end()) - load.begin()); cp.dev_owner[di] = p; ++load[p]; }
+    const int ncol = pl.num_columns(TSB_AN_TRAN);
+    cp.col_owner.assign(ncol, 0);
+    std::vector<int> ncols(parts, 0);
+    ncols[0] = 1;                                              // TIME
+    for (int u = 1; u <= n; ++u) if (cp.owner[u] >= 0) { cp.col_owner[u] = cp.owner[u]; ++ncols[cp.owner[u]]; }
+    {
+        int c = n + 1;
+        for (size_t di = 0; di < pl.devs.size(); ++di) if (pl.devs[di].kind == TSB_R) { if (c >= ncol) return false; cp.col_owner[c] = cp.dev_owner[di]; ++ncols[cp.dev_owner[di]]; ++c; }
+        if (c != ncol) return false;
+    }
+    for (int u = 1; u <= n; ++u) if (cp.owner[u] < 0) { int p = (int)(std::min_element(ncols.begin(), ncols.end()) - ncols.begin()); cp.col_owner[u] = p; ++ncols[p]; }
+    // ---- nested-dissection order on the nominal transient matrix -----------------------------------------------------------
+    const double dt_rep = 1e-6;
+    std::vector<std::vector<char>> on(n + 1, std::vector<char>(n + 1, 0));
+    std::vector<std::vector<double>> val(n + 1, std::vector<double>(n + 1, 0.0));
+    {
+        TsbEnv env{TSB_MODE_TRAN, 0.0, dt_rep, 0.0, 1.0 / dt_rep};
+        double o[64];
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (device_num_outputs(d) > 64) return false;
+            nom.eval(di, env, o);
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (s.col == 0) continue;
+                on[s.row][s.col] = 1;
+                val[s.row][s.col] += s.sign * (s.out == OUT_CONST ? s.cval : o[s.out]);
+            }
+        }
+    }
+    PivotOrder ord; ord.n = n; ord.ext2int.assign(n + 1, 0); ord.prow.assign(n + 1, 0); ord.pcol.assign(n + 1, 0);
+    cp.step_owner.assign(n + 1, -1);
+    std::vector<char> rdone(n + 1, 0), cdone(n + 1, 0);
+    int k = 0;
+    auto order_block = [&](const std::vector<int>& rows, const std::vector<int>& cols, int owner) -> bool {
+        const int m = (int)rows.size();
+        if (m == 0) return true;
+        MarkowitzLU blk(m);
+        for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) if (on[rows[i]][cols[j]]) blk.add(i + 1, j + 1, val[rows[i]][cols[j]]);
+        if (blk.assigned() != m || !blk.order_and_factor()) return false;
+        for (int q = 1; q <= m; ++q) {
+            const int br = rows[blk.pivot_row(q) - 1], bc = cols[blk.pivot_col(q) - 1];
+            ++k; ord.prow[k] = br; ord.pcol[k] = bc; cp.step_owner[k] = owner; rdone[br] = 1; cdone[bc] = 1;
+            if (val[br][bc] == 0.0) return false;
+            for (int i = 1; i <= n; ++i) {             // numeric elimination on the full matrix: the separator block becomes the Schur complement
+                if (rdone[i] || !on[i][bc]) continue;
+                for (int j = 1; j <= n; ++j) {
+                    if (cdone[j] || !on[br][j]) continue;
+                    on[i][j] = 1;
+                    val[i][j] -= val[i][bc] * val[br][j] / val[br][bc];
+                }
+            }
+        }
+        return true;
+    };
+    for (int p = 0; p < parts; ++p) if (!order_block(interior[p], interior[p], p)) return false;
+    cp.n_int = k;
+    std::vector<int> sep;
+    for (int v = 1; v <= n; ++v) if (cp.owner[v] < 0) sep.push_back(v);
+    if (!order_block(sep, sep, -1)) return false;
+    if (k != n) return false;
+    std::vector<std::pair<int, int>> pat = pl.pattern_op;
+    pat.insert(pat.end(), pl.pattern_tran_extra.begin(), pl.pattern_tran_extra.end());
+    build_lu_program(n, pat, ord, false, cp.lu);
+    for (const auto& rc : cp.lu.pos) {                       // no entry may couple two interiors (fill included)
+        const int a = cp.owner[rc.first], b = cp.owner[rc.second];
+        if (a >= 0 && b >= 0 && a != b) return false;
+    }
+    return true;
+}
+
 }  // namespace
 
 int plan_finalize(Plan& pl) {
@@ -620,6 +794,13 @@ int plan_finalize(Plan& pl) {
         Nominal nom2(pl);            // fresh device state: the order must not depend on where the replay above left it
         nom2.derive();
         build_tranfast(pl, nom2);
+    }
+    pl.coop.clear();
+    for (int parts : {2, 4}) {
+        Nominal nom3(pl);
+        nom3.derive();
+        CoopPlan cp;
+        if (build_coop(pl, nom3, parts, cp)) pl.coop[parts] = cp;
     }
     pl.finalized = true;
     return TSB_OK;

@@ -66,11 +66,12 @@ struct TsbArgsHost {
     int tgrid_cap;
     int tgrid_role;
     double Uc[32];
+    double* coop_state;
 };
 
 struct KernelModule {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t optran = nullptr, dc = nullptr, stamp = nullptr, stamp_staged = nullptr, ac = nullptr;
+    cudaKernel_t optran = nullptr, dc = nullptr, stamp = nullptr, stamp_staged = nullptr, ac = nullptr, coop = nullptr;
     int info_regs = -1, info_spill = -1, min_blocks = 0;
 };
 
@@ -142,6 +143,7 @@ struct tsb_batch {
     std::string memo_sig, memo_autokey;
     KernelModule* memo_module = nullptr;
     long long* d_order = nullptr;                      // tsb_batch_set_order: processing order (device copy)
+    double* d_coop_state = nullptr;                    // cooperative mapping: hand-over of the operating point, [n_state + n + 1][n_inst]
     size_t wave_bytes = 0, stats_bytes = 0;
 };
 
@@ -267,6 +269,8 @@ CodegenConfig make_config(const tsb_batch* b, const tsb_opts& o, int dc_param) {
     cfg.skip_linear = o.skip_linear_resolve != 0;
     cfg.lane_refill = o.lane_refill != 0;
     cfg.tgrid = o.share_time_grid != 0;
+    cfg.coop_parts = o.coop_parts > 0 ? o.coop_parts : 0;
+    if (cfg.coop_parts) cfg.tgrid = false;
     if (const char* tf = getenv("TSB_TRANFAST")) cfg.tranfast = *tf != '0';       // development knob: A/B of the condensed elimination
     cfg.grid = b->grid_kernel;
     cfg.dc_nested = b->dc_nested; cfg.dc_param2 = b->dc_param2;
@@ -342,8 +346,8 @@ int get_module(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** out, std::
     sig.reserve(b->varying.size() + 96);
     sig.append(b->varying.begin(), b->varying.end());
     const char* xd = getenv("TSB_EXTRA_DEFINES");
-    char tail[160];
-    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.share_time_grid != 0, o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
+    char tail[200];
+    snprintf(tail, sizeof tail, "|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%d|%lld|%p|", o.coop_parts, o.share_time_grid != 0, o.strict_fp, o.block_size, o.skip_linear_resolve, o.min_blocks, o.lane_refill,
              (int)b->grid_kernel, (int)(b->d_order != nullptr), dc_param, (int)b->dc_nested, b->dc_param2, ctx->choice_epoch, (void*)ctx);
     sig += tail;
     if (xd) sig += xd;
@@ -414,6 +418,7 @@ int get_module_uncached(tsb_batch* b, tsb_opts o, int dc_param, KernelModule** o
     CU(ctx, cudaLibraryGetKernel(&m.stamp, m.lib, "tsb_stamp"));
     CU(ctx, cudaLibraryGetKernel(&m.stamp_staged, m.lib, "tsb_stamp_staged"));
     CU(ctx, cudaLibraryGetKernel(&m.ac, m.lib, "tsb_ac"));
+    if (src.find("tsb_coop_tran(TsbArgs a)") != std::string::npos) CU(ctx, cudaLibraryGetKernel(&m.coop, m.lib, "tsb_coop_tran"));
     m.info_regs = info.regs; m.info_spill = info.spill_st; m.min_blocks = o.min_blocks;
     ctx->modules[key] = m;
     *out = &ctx->modules[key];
@@ -703,6 +708,7 @@ void tsb_default_opts(tsb_opts* o) {
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
     o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0; o->grid_dt = 0.0;
     o->share_time_grid = -1;
+    o->coop_parts = 0;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -846,6 +852,15 @@ int tsb_plan_finalize(tsb_plan* plan) {
 void tsb_plan_destroy(tsb_plan* plan) { plan_release(plan); }
 const char* tsb_plan_error(tsb_plan* plan) { return plan ? plan->p.error.c_str() : ""; }
 
+int tsb_plan_coop_info(const tsb_plan* plan, int parts, int* owner, int* n_separator) {
+    if (!plan || !plan->p.finalized) return TSB_E_INVALID;
+    auto it = plan->p.coop.find(parts);
+    if (it == plan->p.coop.end()) return TSB_E_UNSUPPORTED;
+    const CoopPlan& cp = it->second;
+    if (owner) for (int u = 0; u <= plan->p.n(); ++u) owner[u] = u == 0 ? -1 : cp.owner[u];
+    if (n_separator) *n_separator = plan->p.n() - cp.n_int;
+    return TSB_OK;
+}
 int tsb_plan_size(const tsb_plan* plan, int* n_nodes, int* n_branches) {
     if (!plan) return TSB_E_INVALID;
     if (n_nodes) *n_nodes = plan->p.n_nodes;
@@ -947,6 +962,7 @@ void tsb_batch_destroy(tsb_batch* b) {
         }
         cudaFree(b->d_uniform);
         cudaFree(b->d_order);
+        cudaFree(b->d_coop_state);
         cudaFree(b->d_tgrid); cudaFree(b->d_tgrid_pub); cudaFree(b->d_partial);
         if (b->ev_fetch) { cudaEventSynchronize(b->ev_fetch); cudaEventDestroy(b->ev_fetch); }
         if (b->ev_run) cudaEventDestroy(b->ev_run);
@@ -1032,6 +1048,7 @@ int tsb_run_op(tsb_batch* b, const tsb_opts* opts) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     tsb_ctx* ctx = b->ctx;
     tsb_opts o = resolve(opts, b->plan->p);
+    o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
@@ -1068,6 +1085,17 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         wave_cap_rows = n_grid;
     }
     CU(ctx, cudaSetDevice(ctx->device));
+    if (o.coop_parts != 0) {
+        // cooperative mapping (device/coop.cuh): refuse what it does not cover instead of silently running something else
+        const Plan& cpl = b->plan->p;
+        if (o.coop_parts != 2 && o.coop_parts != 4) return fail(ctx, TSB_E_INVALID, "coop_parts must be 0, 2 or 4");
+        if (cpl.has_nonlinear || cpl.has_mutual) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: circuits with nonlinear devices or mutual couplings run thread-per-circuit");
+        if (!cpl.coop.count(o.coop_parts)) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the netlist has no partition into that many sub-circuits (tsb_plan_coop_info)");
+        if (o.strict_fp) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the nested-dissection order is a re-association, not available in the strict build");
+        if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: TSB_OUT_GRID is not available on the cooperative mapping");
+        if (!o.skip_linear_resolve || o.lane_refill) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts needs skip_linear_resolve = 1 and lane_refill = 0");
+        if (o.min_blocks <= 0) o.min_blocks = 2;          // tsb_optran only runs the operating point here: no launch-bounds search
+    }
     KernelModule* m = nullptr;
     b->grid_kernel = (out_flags & TSB_OUT_GRID) != 0;
     std::string autokey;
@@ -1083,7 +1111,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     const char* tune_env = getenv("TSB_AUTOTUNE");
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-    if (o.min_blocks <= 0 && !autokey.empty() && b->n_inst >= TSB_TUNE_MIN_INSTANCES && !ctx->tuned.count(autokey) &&
+    if (o.coop_parts == 0 && o.min_blocks <= 0 && !autokey.empty() && b->n_inst >= TSB_TUNE_MIN_INSTANCES && !ctx->tuned.count(autokey) &&
         !(tune_env && *tune_env == '0') && cap == cudaStreamCaptureStatusNone) {
         rc = autotune_min_blocks(b, o, autokey, m->min_blocks, a, persistent);
         if (rc == TSB_OK) rc = get_module(b, o, -1, &m);
@@ -1092,6 +1120,29 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     b->grid_kernel = false;
     b->tgrid_used = 0;
     const Plan& pl = b->plan->p;
+    if (o.coop_parts > 0) {
+        if (!m->coop) return fail(ctx, TSB_E_COMPILE, "cooperative kernel missing from the module");
+        const CoopPlan& cp = pl.coop.at(o.coop_parts);
+        if (!b->d_coop_state) CU(ctx, cudaMalloc(&b->d_coop_state, (size_t)(pl.n_state + pl.n() + 1) * b->n_inst * sizeof(double)));
+        a.coop_state = b->d_coop_state;
+        // 1. operating point(s) thread-per-circuit, state handed over; 2. the transient on the cooperative mapping
+        TsbArgsHost a1 = a;
+        a1.out_flags = 0;
+        if ((rc = launch(b, o, m->optran, a1, false, m->min_blocks)) != TSB_OK) return rc;
+        int nx = 0, nown = 0;
+        coop_dimensions(pl, cp, nx, nown);
+        const int groups = 1, block = 32 * cp.parts * groups;
+        const size_t smem = ((size_t)4 * nown * block + (size_t)groups * 2 * cp.parts * nx * 32) * sizeof(double);
+        if (smem > 227 * 1024) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the statistics of one block do not fit in shared memory");
+        if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)m->coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long blocks = (a.n_run + 32 * groups - 1) / (32 * groups);
+        if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+        if (blocks < 1) blocks = 1;
+        void* kargs[] = {&a};
+        CU(ctx, cudaLaunchKernel((const void*)m->coop, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
+        ++ctx->launches;
+        return TSB_OK;
+    }
     const bool tg_possible = !pl.has_nonlinear && o.skip_linear_resolve != 0 && o.share_time_grid != 0 && !persistent;
     if (tg_possible && (o.share_time_grid > 0 || b->n_inst >= TSB_TGRID_MIN_INSTANCES)) {
         if ((rc = launch_pilot(b, o, m->optran, a)) != TSB_OK) return rc;
@@ -1130,6 +1181,7 @@ static int run_dc_impl(tsb_batch* b, int src_dev, double start, double stop, dou
         for (double v1 : s1) for (double v2 : s2) { sweep.push_back(v1); sweep2.push_back(v2); }
     }
     tsb_opts o = resolve(opts, b->plan->p);
+    o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
     CU(ctx, cudaSetDevice(ctx->device));
     auto dc_param_of = [&](int d) {
         const Dev& sd = p.devs[d];
@@ -1181,6 +1233,7 @@ int tsb_run_ac(tsb_batch* b, int sweep_type, int n_points, double fstart, double
     std::vector<double> f;
     ac_frequency_points(sweep_type, n_points, fstart, fstop, f);       // ac.go:100-126
     tsb_opts o = resolve(opts, p);
+    o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
@@ -1204,6 +1257,7 @@ int tsb_batch_stamp_dev(tsb_batch* b, int mode, double time, double dt, double g
     tsb_ctx* ctx = b->ctx;
     if (!A_dev || !b_dev || (mode != 0 && mode != 1)) return fail(ctx, TSB_E_INVALID, "tsb_batch_stamp_dev: mode must be 0 (OP) or 1 (transient), outputs non-null");
     tsb_opts o = resolve(opts, b->plan->p);
+    o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;

@@ -62,6 +62,21 @@ struct LuProgram {
     bool dense = false;
 };
 
+// Cooperative mapping (device/coop.cuh): one circuit is solved by P threads in P different warps of a block.  The unknowns
+// are split into P interiors that do not touch each other and a separator; part p stamps the devices it owns, eliminates
+// its interior (a nested-dissection order: interiors first, separator last) and hands its contribution to the separator
+// system to the others through shared memory; every part then solves the (small) separator system and back-substitutes
+// its interior.  Built by plan.cpp: build_coop for circuits without nonlinear devices and without mutual couplings.
+struct CoopPlan {
+    int parts = 0;
+    std::vector<int> owner;          // [n+1] unknown (external index) -> part, -1: separator
+    std::vector<int> dev_owner;      // [devs] device -> part
+    std::vector<int> step_owner;     // [n+1] elimination step of `lu` -> part, -1: separator step
+    std::vector<int> col_owner;      // [transient columns] result column -> part (column 0, TIME: part 0)
+    int n_int = 0;                   // steps 1..n_int eliminate interiors (part 0's first, then part 1's, ...), the rest the separator
+    LuProgram lu;                    // elimination program of the nested-dissection order over the stamped pattern
+};
+
 struct Plan {
     tsb_ctx* ctx = nullptr;
     int n_nodes = 0, n_branches = 0;
@@ -96,6 +111,7 @@ struct Plan {
     LuProgram lu_tf;
     std::vector<char> tf_variant;
     bool has_tranfast = false;
+    std::map<int, CoopPlan> coop;                   // parts (2, 4) -> cooperative plan, where one exists
     bool init_struct_singular = false;
     bool has_nonlinear = false, has_time_dependent = false, has_bjt = false, has_mutual = false;
     std::string error;
@@ -133,7 +149,11 @@ struct CodegenConfig {
     bool lane_refill = false;       // nonlinear circuits: resident grid, finished lanes fetch the next instance
     bool tgrid = false;             // linear circuits: kernels that can read / publish the shared time grid (skeleton.cuh)
     bool tranfast = true;           // fast build: transient solves use the condensed elimination (lu_tf) where the plan has one
+    int coop_groups = 1;            // cooperative kernels: groups of `coop_parts` warps per block
+    int coop_parts = 0;             // > 0: the unit also carries the cooperative transient kernels for plan.coop[coop_parts]
 };
 std::string generate_source(const Plan& plan, const CodegenConfig& cfg);
+// cooperative kernels: exchange slots per part and attempt, result columns of the widest part (what sizes their shared memory)
+void coop_dimensions(const Plan& plan, const CoopPlan& cp, int& nx, int& nown_max);
 
 }  // namespace tsb
