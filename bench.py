@@ -591,6 +591,38 @@ def main():
                                   "contiguous shards of one global draw, seed 4567)", "n_gpus": world, "ms": e["ms_per_launch"],
                       "circuit_timesteps_per_sec": e["circuit_timesteps_per_sec"], "scaling": "strong"}
 
+    # ---- larger n: a 24-section RC ladder (26 unknowns, 51 result columns), one thread per circuit against the
+    # cooperative mapping (one instance per 2 threads in different warps, tsb_opts.coop_parts; the default picks it) ----------
+    larger_n = None
+    if not args.no_configs:
+        try:
+            nl = max(1024, int((1 << 18) * args.config_scale))
+            ltext = W.rc_ladder(24)
+            lckt = T.Circuit.from_netlist(ltext, ctx)
+            lcard = lckt.analysis_card()
+            lov = W.sweep_draws(lckt.devices(), nl, 5 + 7919 * rank)
+            ldev = {k: torch.from_numpy(v).to(dev_name) for k, v in lov.items()}
+            larger_n = {"workload": f"RC ladder, 24 sections (n = 26 unknowns, 51 result columns), {nl} instances per GPU, transient, statistics output",
+                        "mappings": []}
+            for parts, label in ((0, "one thread per circuit"), (2, "cooperative, 2 threads per circuit"), (4, "cooperative, 4 threads per circuit")):
+                lb = lckt.batch(nl)
+                for (d, p), v in ldev.items():
+                    lb.set_param(d, p, v)
+                lo = T.default_opts(strict_fp=0, coop_parts=parts)
+                ms = min(timed_launches(lambda: lb.run_tran(lcard["tstart"], lcard["tstop"], lcard["tstep"], lcard["tmax"], lcard["uic"],
+                                                            out=T.OUT_STATS, opts=lo), reps=2))
+                tot = lb.totals()
+                larger_n["mappings"].append({"mapping": label, "coop_parts": parts, "ms_per_launch": ms, "steps": int(tot[0]),
+                                             "circuit_timesteps_per_sec": int(tot[0]) / (ms * 1e-3), "failed": int((lb.status() != 0).sum())})
+                del lb
+            base = larger_n["mappings"][0]["ms_per_launch"]
+            for e in larger_n["mappings"]:
+                e["speedup_vs_thread_mapping"] = base / e["ms_per_launch"]
+            larger_n["default"] = "coop_parts = -1 picks 2 parts for circuits of >= 16 unknowns without nonlinear devices (fast build)"
+            del ldev
+        except Exception as ex:
+            larger_n = {"error": repr(ex)[:300]}
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -612,7 +644,7 @@ def main():
                     "pipelined": "read-back of step i overlaps step i+1 (two batches per deck, tsb_result_fetch_async)", "results_check": bool(e2e_ok)},
             "gpu_launches": int(launches), "failed_instances": bad_status,
             "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp,
-            "configs": configs, "strong": strong, "cpu_baseline": cpu,
+            "configs": configs, "strong": strong, "larger_n": larger_n, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

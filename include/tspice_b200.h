@@ -126,11 +126,13 @@ typedef struct tsb_opts {
                            the netlist is cut into that many sub-circuits joined by a small separator, and one instance is
                            advanced by that many threads in different warps of a block (each eliminates its own sub-circuit;
                            a few doubles per step attempt cross shared memory around one named barrier).  For circuits too
-                           large for one thread's registers (n >~ 14).  The elimination order is a nested-dissection order:
-                           results differ from the thread-per-circuit mapping by rounding (like the fast build's other
-                           re-associations).  TSB_E_UNSUPPORTED when the circuit has no such partition (see
-                           tsb_plan_coop_info), has nonlinear devices or mutual couplings, or with strict_fp / TSB_OUT_GRID.
-                           0 (default): off */
+                           large for one thread's registers.  The elimination order is a nested-dissection order: results
+                           differ from the thread-per-circuit mapping by rounding (like the fast build's other
+                           re-associations).  An explicit 2 / 4 fails with TSB_E_UNSUPPORTED when the circuit has no such
+                           partition (tsb_plan_coop_info), has nonlinear devices or mutual couplings, or with strict_fp /
+                           TSB_OUT_GRID.  0: off.  -1 (default): two parts for circuits of >= 16 unknowns where all of the
+                           above holds (measured on B200, RC ladders: n = 18 1.6x, n = 26 2.1x the thread-per-circuit rate),
+                           else off */
 } tsb_opts;
 
 /* The partition behind tsb_opts.coop_parts (parts = 2 or 4): owner[u] for every unknown u = 1..n (external numbering: nodes,

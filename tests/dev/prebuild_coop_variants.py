@@ -16,7 +16,7 @@ mbs = sys.argv[2].split(",") if len(sys.argv) > 2 else [""]
 jobs = []
 for s in secs:
     ckt = T.Circuit.from_netlist(rc_ladder(s))
-    for parts in (0, 2, 4):
+    for parts in (0, 2, 4, 8):
         if parts and ckt.coop_info(parts) is None:
             continue
         for mb in (mbs if parts else [""]):

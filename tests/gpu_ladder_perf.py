@@ -27,7 +27,7 @@ def main():
         dev = {k: torch.from_numpy(v).cuda() for k, v in ov.items()}
         card = ckt.analysis_card()
         ref = None
-        for parts in (0, 2, 4):
+        for parts in (0, 2, 4, 8):
             if parts and ckt.coop_info(parts) is None:
                 continue
             for mb in (mbs if parts else [""]):
@@ -40,13 +40,18 @@ def main():
                     b.set_param(d, p, v)
                 o = T.default_opts(coop_parts=parts)
                 ms = []
-                for it in range(3):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(stream)
-                    b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=o)
-                    e1.record(stream)
-                    stream.synchronize()
-                    ms.append(e0.elapsed_time(e1))
+                try:
+                    for it in range(3):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream)
+                        b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=o)
+                        e1.record(stream)
+                        stream.synchronize()
+                        ms.append(e0.elapsed_time(e1))
+                except T.TsbError as ex:
+                    print(f"ladder sections={sections:2d} n={ckt.n:2d} instances={n} coop_parts={parts}: does not launch ({str(ex)[:120]})", flush=True)
+                    del b
+                    continue
                 tot = b.totals()
                 s = b.stats_all()
                 if ref is None:

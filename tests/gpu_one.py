@@ -17,9 +17,13 @@ def main():
         kw[k] = int(v)
     out = {"stats": T.OUT_STATS, "wave": T.OUT_WAVE, "grid": T.OUT_GRID}[sys.argv[4] if len(sys.argv) > 4 else "stats"]
     ctx = T.Context(0)
-    text = T.BUNDLED[deck]
+    if deck.startswith("ladder"):
+        from random_decks import rc_ladder
+        text = rc_ladder(int(deck[6:]))
+    else:
+        text = T.BUNDLED[deck]
     ckt = T.Circuit.from_netlist(text, ctx)
-    ov = PU.draws(deck, ckt, n)
+    ov = PU.draws(deck, ckt, n, seed=5 if deck.startswith("ladder") else None)
     dev = {k: torch.from_numpy(v).cuda() for k, v in ov.items()}
     torch.cuda.synchronize()
     card = ckt.analysis_card()

@@ -162,7 +162,7 @@ DECKS["mesh4x5"] = rc_mesh(4, 5)
 DECKS["random0"] = random_deck(0)[0]
 
 
-@pytest.mark.parametrize("parts", [2, 4])
+@pytest.mark.parametrize("parts", [2, 4, 8])
 @pytest.mark.parametrize("name", sorted(DECKS))
 def test_cooperative_solve_equals_reference_order(built, name, parts):
     with tempfile.TemporaryDirectory() as tmp:
@@ -181,7 +181,7 @@ def test_partition_is_a_partition(built):
     pattern: an entry between two different interiors would make the plan refuse the partition)."""
     for name, text in DECKS.items():
         ckt = T.Circuit.from_netlist(text)
-        for parts in (2, 4):
+        for parts in (2, 4, 8):
             owner = ckt.coop_info(parts)
             if owner is None:
                 continue

@@ -20,7 +20,7 @@ DECKS = {
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("parts", [2, 4])
+@pytest.mark.parametrize("parts", [2, 4, 8])
 @pytest.mark.parametrize("name", sorted(DECKS))
 def test_cooperative_transient_matches_oracle(ctx, name, parts):
     text, cap = DECKS[name]
@@ -36,7 +36,7 @@ def test_cooperative_transient_matches_oracle(ctx, name, parts):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("parts", [2, 4])
+@pytest.mark.parametrize("parts", [2, 4, 8])
 @pytest.mark.parametrize("name", ["ladder24", "mesh4x5", "rlc"])
 def test_cooperative_statistics_equal_thread_mapping(ctx, name, parts):
     """Several blocks, a ragged tail, statistics output: same rows / counters / status as the thread-per-circuit mapping, values

@@ -84,16 +84,17 @@ def test_random_active_deck_matches_oracle(ctx, seed, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("coop", [0, -1])
 @pytest.mark.parametrize("sections", [12, 24])
-def test_rc_ladder_beyond_the_bundled_sizes(ctx, sections):
+def test_rc_ladder_beyond_the_bundled_sizes(ctx, sections, coop):
     """n = 14 and 26 unknowns: past the point where a circuit fits in one thread's registers (the generated kernel
-    spills to local memory) the thread-per-circuit path must still be CORRECT — it is the fallback until analysis
-    drivers exist on top of the warp-per-circuit LU."""
+    spills to local memory) the thread-per-circuit path (coop_parts = 0) must still be CORRECT; the default (-1) runs the
+    n = 26 ladder on the cooperative mapping (tests/test_gpu_coop.py has its own parity decks)."""
     from random_decks import rc_ladder
     text = rc_ladder(sections)
     n = 6
     ov = PU.draws("ladder", T.Circuit.from_netlist(text), n, seed=77)
-    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=1024)
+    ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=1024, opts=T.default_opts(coop_parts=coop))
     _, ores = PU.run_oracle(text, n, ov, cap_rows=1024)
     rep = PU.compare_waves(batch, ores, n)
     assert PU.report_ok(rep), rep

@@ -1276,9 +1276,19 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         const int groups = cfg.coop_groups > 0 ? cfg.coop_groups : 1;
         const int cblock = 32 * coop->parts * groups;
         e.line("#define TSB_COOP_BLOCK " + std::to_string(cblock));
-        e.line("#ifndef TSB_COOP_MIN_BLOCKS");
-        e.line("#define TSB_COOP_MIN_BLOCKS " + std::to_string(std::max(1, 384 / cblock)));
-        e.line("#endif");
+        {
+            // Launch bounds: the per-thread statistics (32 bytes per own result column) decide how many blocks an SM holds;
+            // asking for more only lowers the register cap for nothing (measured: ladder n = 26, 4 parts: 14.5 ms at the
+            // shared-memory limit of 3 blocks, 16.0 ms at 4, 20.2 ms at 2).
+            int nx = 0, nown = 0;
+            coop_dimensions(pl, *coop, nx, nown);
+            const size_t smem = ((size_t)4 * nown * cblock + (size_t)groups * 2 * coop->parts * nx * 32) * sizeof(double) + 1024;
+            int mb = (int)((227 * 1024) / smem);
+            mb = std::max(1, std::min(mb, std::max(1, 512 / cblock)));        // at most what 128 registers per thread allow
+            e.line("#ifndef TSB_COOP_MIN_BLOCKS");
+            e.line("#define TSB_COOP_MIN_BLOCKS " + std::to_string(mb));
+            e.line("#endif");
+        }
         emit_coop(e, pl, *coop, cfg);
         e.os << k_coop_src << "\n";
         e.line("// One group of TSB_COOP_PARTS warps per 32 instances: warp w runs part w % PARTS of the instances of group w / PARTS.");

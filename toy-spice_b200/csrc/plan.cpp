@@ -525,7 +525,7 @@ Cut bisect(const std::vector<int>& V, const std::vector<std::vector<char>>& adj,
 
 static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
     const int n = pl.n();
-    if (pl.has_nonlinear || pl.has_mutual || n < 2 * parts || n > 64 || (parts != 2 && parts != 4)) return false;
+    if (pl.has_nonlinear || pl.has_mutual || n < 2 * parts || n > 96 || (parts != 2 && parts != 4 && parts != 8)) return false;
     // ---- graph ------------------------------------------------------------------------------------------------------------
     std::vector<std::vector<char>> adj(n + 1, std::vector<char>(n + 1, 0));
     std::vector<std::vector<int>> dev_unk(pl.devs.size());
@@ -544,14 +544,20 @@ static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
     cp.owner.assign(n + 1, -1);
     std::vector<int> all;
     for (int v = 1; v <= n; ++v) all.push_back(v);
-    coop_detail::Cut top = coop_detail::bisect(all, adj, n);
-    if (!top.ok) return false;
     std::vector<std::vector<int>> interior;
-    if (parts == 2) { interior = {top.A, top.B}; }
-    else {
-        coop_detail::Cut ca = coop_detail::bisect(top.A, adj, n), cb = coop_detail::bisect(top.B, adj, n);
-        if (!ca.ok || !cb.ok) return false;
-        interior = {ca.A, ca.B, cb.A, cb.B};
+    {
+        int levels = 0;
+        while ((1 << levels) < parts) ++levels;
+        // recursive bisection: the separators of all levels together are THE separator, the leaves the interiors
+        struct Rec {
+            const std::vector<std::vector<char>>& adj; int n; std::vector<std::vector<int>>& out;
+            bool run(const std::vector<int>& V, int lv) {
+                if (lv == 0) { out.push_back(V); return !V.empty(); }
+                coop_detail::Cut c = coop_detail::bisect(V, adj, n);
+                return c.ok && run(c.A, lv - 1) && run(c.B, lv - 1);
+            }
+        } rec{adj, n, interior};
+        if (!rec.run(all, levels) || (int)interior.size() != parts) return false;
     }
     for (int p = 0; p < parts; ++p) {
         if (interior[p].empty()) return false;
@@ -796,7 +802,7 @@ int plan_finalize(Plan& pl) {
         build_tranfast(pl, nom2);
     }
     pl.coop.clear();
-    for (int parts : {2, 4}) {
+    for (int parts : {2, 4, 8}) {
         Nominal nom3(pl);
         nom3.derive();
         CoopPlan cp;

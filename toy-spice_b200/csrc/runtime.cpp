@@ -637,6 +637,8 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
 // only when the main launch lasts many times longer than the pilot (one instance alone is latency-bound: ~10-20 ms
 // for the 2.4e4 attempts of an inductor deck), hence the instance threshold of the automatic mode.
 const int64_t TSB_TGRID_MIN_INSTANCES = 1 << 18;
+const int TSB_COOP_AUTO_MIN_N = 16;        // tsb_opts.coop_parts = -1: two parts from this many unknowns up
+const int TSB_COOP4_AUTO_MIN_N = 1 << 20;   //                             four parts from this many (no measured win yet)
 const int TSB_TGRID_CAP = 1 << 16;
 
 // The table is a pure function of the analysis arguments, the tolerances that steer the step control, the uniform
@@ -708,7 +710,7 @@ void tsb_default_opts(tsb_opts* o) {
     o->max_iter = 100; o->abstol = 1e-12; o->reltol = 1e-6; o->gmin = 1e-12; o->trtol = 7.0;
     o->strict_fp = -1; o->block_size = 128; o->skip_linear_resolve = 1; o->min_blocks = 0; o->lane_refill = 0; o->grid_dt = 0.0;
     o->share_time_grid = -1;
-    o->coop_parts = 0;
+    o->coop_parts = -1;
 }
 const char* tsb_version(void) { return "tspice_b200 0.1 (sm_100a)"; }
 
@@ -1085,10 +1087,27 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         wave_cap_rows = n_grid;
     }
     CU(ctx, cudaSetDevice(ctx->device));
-    if (o.coop_parts != 0) {
-        // cooperative mapping (device/coop.cuh): refuse what it does not cover instead of silently running something else
+    if (const char* ce = getenv("TSB_COOP")) { if (*ce) o.coop_parts = atoi(ce); }      // development / A-B knob
+    if (o.coop_parts < 0) {
+        // auto: the cooperative mapping where it measured faster than one thread per circuit (RC ladders on B200: n = 14
+        // 0.86x, n = 18 1.6x, n = 26 2.1x with two parts) and everything it needs holds; otherwise thread-per-circuit
         const Plan& cpl = b->plan->p;
-        if (o.coop_parts != 2 && o.coop_parts != 4) return fail(ctx, TSB_E_INVALID, "coop_parts must be 0, 2 or 4");
+        o.coop_parts = 0;
+        if (!cpl.has_nonlinear && !cpl.has_mutual && !o.strict_fp && !(out_flags & TSB_OUT_GRID) && o.skip_linear_resolve && !o.lane_refill) {
+            int pick = 0;
+            if (cpl.n() >= TSB_COOP_AUTO_MIN_N && cpl.coop.count(2)) pick = 2;
+            if (cpl.n() >= TSB_COOP4_AUTO_MIN_N && cpl.coop.count(4)) pick = 4;
+            if (pick) {
+                int nx = 0, nown = 0;
+                coop_dimensions(cpl, cpl.coop.at(pick), nx, nown);
+                if (((size_t)4 * nown * 32 * pick + (size_t)2 * pick * nx * 32) * sizeof(double) <= 100 * 1024) o.coop_parts = pick;
+            }
+        }
+    }
+    if (o.coop_parts != 0) {
+        // cooperative mapping (device/coop.cuh): an explicit request is refused where it does not apply, never silently replaced
+        const Plan& cpl = b->plan->p;
+        if (o.coop_parts != 2 && o.coop_parts != 4 && o.coop_parts != 8) return fail(ctx, TSB_E_INVALID, "coop_parts must be -1, 0, 2, 4 or 8");
         if (cpl.has_nonlinear || cpl.has_mutual) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: circuits with nonlinear devices or mutual couplings run thread-per-circuit");
         if (!cpl.coop.count(o.coop_parts)) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the netlist has no partition into that many sub-circuits (tsb_plan_coop_info)");
         if (o.strict_fp) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the nested-dissection order is a re-association, not available in the strict build");

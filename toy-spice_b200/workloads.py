@@ -72,3 +72,14 @@ def sweep_draws(devices, n: int, seed: int):
                 v = rng.normal(a, b, n)
             out[(d["name"], pi)] = v
     return out
+
+
+def rc_ladder(sections: int) -> str:
+    """Synthetic larger-n deck (not a reference circuit): Vin - (R - C to ground) x sections, i.e.
+    sections + 2 unknowns and 2 * sections + 3 result columns — past n ~ 14 more than one thread's registers hold."""
+    lines = [f"* RC ladder, {sections} sections", "Vin 1 0 SIN(0 5 1k)"]
+    for k in range(1, sections + 1):
+        lines.append(f"R{k} {k} {k + 1} 100")
+        lines.append(f"C{k} {k + 1} 0 100n")
+    lines.append(".tran 0.01ms 3ms")
+    return "\n".join(lines) + "\n"
