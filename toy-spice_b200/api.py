@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "tsb_plan_from_netlist", "tsb_plan_add_device", "tsb_plan_finalize", "tsb_plan_destroy", "tsb_plan_error",
     "tsb_plan_size", "tsb_plan_num_devices", "tsb_plan_device_info", "tsb_plan_device_params",
     "tsb_plan_find_device", "tsb_plan_node_name", "tsb_plan_analysis", "tsb_plan_structure", "tsb_plan_pattern",
-    "tsb_plan_num_columns", "tsb_plan_column_name", "tsb_batch_create", "tsb_batch_destroy", "tsb_batch_set_param",
+    "tsb_plan_num_columns", "tsb_plan_column_name", "tsb_plan_coop_info", "tsb_batch_create", "tsb_batch_destroy", "tsb_batch_set_param",
     "tsb_batch_set_param_dev", "tsb_batch_set_param_uniform", "tsb_run_op", "tsb_run_tran", "tsb_run_dc",
     "tsb_batch_sync", "tsb_result_dims", "tsb_result_dev_ptrs", "tsb_result_rows", "tsb_result_status",
     "tsb_result_counters", "tsb_result_waveform", "tsb_result_wave_all", "tsb_result_stats_all",

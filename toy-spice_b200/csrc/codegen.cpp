@@ -719,6 +719,7 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
         e.line("__device__ __forceinline__ void lte_flags(double dt, double rdt, double trtol, double thr, bool& gt, bool& small) {");
         ++e.ind;
         e.line("gt = false; small = 0.0 < thr;");
+        e.line("double trtol2 = trtol, thr2 = thr; TSB_OPAQUE(trtol2); TSB_OPAQUE(thr2);");
         for (int di : y.devs) {
             const Dev& d = pl.devs[di];
             if (d.kind == TSB_C)
@@ -726,10 +727,10 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
             else if (d.kind == TSB_L) {
                 e.line("{ double cu, vo; tsb_ind_lte2(S + " + S(d.s_off) + ", dt, rdt, cu, vo);");
                 e.line("  const bool nan = ((cu != cu) | (vo != vo)) & !((cu == TSB_INF) | (vo == TSB_INF));");
-                e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol))); small = small & !(!nan & ((cu >= thr) | (vo >= thr))); }");
+                e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol2))); small = small & !(!nan & ((cu >= thr) | (vo >= thr2))); }");
             }
         }
-        e.line("(void)dt; (void)rdt; (void)trtol;");
+        e.line("(void)dt; (void)rdt; (void)trtol; (void)trtol2; (void)thr2;");
         --e.ind;
         e.line("}");
         // ---- phase_a ----------------------------------------------------------------------------------------------
@@ -1235,6 +1236,11 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
     e.line("__device__ __forceinline__ void lte_flags(double dt, double rdt, double trtol, double thr, bool& gt, bool& small) {");
     ++e.ind;
     e.line("gt = false; small = 0.0 < thr;");
+    e.line("#if TSB_X_LTE_OPAQUE");
+    e.line("double trtol2 = trtol, thr2 = thr; TSB_OPAQUE(trtol2); TSB_OPAQUE(thr2);     // see TSB_OPAQUE");
+    e.line("#else");
+    e.line("const double trtol2 = trtol, thr2 = thr;");
+    e.line("#endif");
     for (int di : pl.stamp_order) {
         const Dev& d = pl.devs[di];
         if (d.kind == TSB_C) {
@@ -1242,10 +1248,10 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         } else if (d.kind == TSB_L) {
             e.line("{ double cu, vo; tsb_ind_lte2(S + " + std::to_string(d.s_off) + ", dt, rdt, cu, vo);");
             e.line("  const bool nan = ((cu != cu) | (vo != vo)) & !((cu == TSB_INF) | (vo == TSB_INF));");
-            e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol))); small = small & !(!nan & ((cu >= thr) | (vo >= thr))); }");
+            e.line("  gt = gt | (!nan & ((cu > trtol) | (vo > trtol2))); small = small & !(!nan & ((cu >= thr) | (vo >= thr2))); }");
         }
     }
-    e.line("(void)dt; (void)rdt; (void)trtol;");
+    e.line("(void)dt; (void)rdt; (void)trtol; (void)trtol2; (void)thr2;");
     --e.ind;
     e.line("}");
 

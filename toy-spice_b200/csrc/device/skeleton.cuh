@@ -99,6 +99,15 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #ifndef TSB_X_CONVSEL
 #define TSB_X_CONVSEL 1
 #endif
+#ifndef TSB_X_LTE_OPAQUE
+#define TSB_X_LTE_OPAQUE 1          // truncation-error predicates: keep the two compares of an inductor's terms apart (TSB_OPAQUE, models.cuh)
+#endif
+#ifndef TSB_X_UNROLL2
+#define TSB_X_UNROLL2 0             // linear transient loop unrolled twice (loop-carried state without register moves): see r02_notes.md
+#endif
+#ifndef TSB_X_TGLOOK
+#define TSB_X_TGLOOK 1              // shared time grid: one compare on the hot path of the look-up bookkeeping (tsb_tran_linear)
+#endif
 #ifndef TSB_X_LTEFLAGS
 #define TSB_X_LTEFLAGS 1            // linear loop: truncation-error DECISIONS from predicates instead of selecting the maximum
 #endif
@@ -372,16 +381,34 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
     int n_acc = 0, n_rej = 0, n_bad = 0;   // accepted, rejected, failed solves; attempt number = n_acc + n_rej
     constexpr int ND = TsbTgLayout<Ckt::NSRC>::ND;
     const bool tg_pub = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 1;
-    // entries [0, tg_limit) are known to be published; -1: this thread does not (or no longer) read the table
-    int tg_limit = (TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0) ? 0 : -1;
+    // entries [0, tg_limit) are known to be published.  TSB_X_TGLOOK: tg_limit is 0 when this thread does not (or no longer)
+    // read the table, and tg_next is the attempt at which the published count is looked at again — the first multiple of
+    // TSB_TG_LOOK_EVERY at or above tg_limit, INT_MAX when off — so the hot path is two integer compares (k == tg_next,
+    // k < tg_limit); the older form (tg_limit = -1 for "off", three tests and two reconvergence points) cost 12 instructions
+    // per attempt.  Same look-ups at the same attempts either way.
+    const bool tg_reader = TSB_TGRID && a.tgrid != nullptr && a.tgrid_role == 0;
+    int tg_limit = TSB_X_TGLOOK ? 0 : (tg_reader ? 0 : -1);
+    int tg_next = tg_reader ? 0 : 0x7fffffff;
+#if TSB_X_UNROLL2
+#pragma unroll 2
+#endif
     while (time < a.tstop) {
         const int k = n_acc + n_rej;                       // attempt number: the table index
         const double t_tag = time, dt_tag = dt;
         bool look = false;
-        if (TSB_TGRID && tg_limit >= 0) {
-            if (k >= tg_limit && (k & (TSB_TG_LOOK_EVERY - 1)) == 0) {
+        if (TSB_TGRID && TSB_X_TGLOOK) {
+            if (k == tg_next) {
                 // caught up with what this thread knows to be published: look again every few attempts (a reader that
                 // runs ahead of the pilot will not find anything new for a while)
+                const unsigned long long pub = tsb_ld_relaxed(a.tgrid_pub);
+                const int lim = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
+                if (lim > k) { tsb_fence_acquire(); tg_limit = lim; tg_next = (lim + TSB_TG_LOOK_EVERY - 1) & ~(TSB_TG_LOOK_EVERY - 1); }
+                else tg_next = k + TSB_TG_LOOK_EVERY;
+                if (k >= a.tgrid_cap) { tg_limit = 0; tg_next = 0x7fffffff; }
+            }
+            look = k < tg_limit;
+        } else if (TSB_TGRID && tg_limit >= 0) {
+            if (k >= tg_limit && (k & (TSB_TG_LOOK_EVERY - 1)) == 0) {
                 const unsigned long long pub = tsb_ld_relaxed(a.tgrid_pub);
                 const int lim = pub < (unsigned long long)a.tgrid_cap ? (int)pub : a.tgrid_cap;
                 if (lim > k) { tsb_fence_acquire(); tg_limit = lim; }
@@ -390,7 +417,11 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
             look = k < tg_limit;
             if (TSB_TG_PREFETCH && look) tsb_prefetch_l1(a.tgrid + (long long)k * ND);      // consumed after the factorisation
         }
+#if TSB_X_TGLOOK
+        double2 e0, e1;            // only read under `look` (no zero-initialisation: four instructions per attempt)
+#else
         double2 e0 = make_double2(0.0, 0.0), e1 = make_double2(0.0, 0.0);
+#endif
         if (TSB_TGRID && TSB_X_TG_EARLY && look) {          // in flight during the LTE test and the factorisation
             const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)k * ND);
             e0 = TSB_TG_LD(e); e1 = TSB_TG_LD(e + 1);
@@ -424,7 +455,7 @@ __device__ __forceinline__ void tsb_tran_linear(const TsbArgs& a, Ckt& c, Sink& 
                 const double2* e = reinterpret_cast<const double2*>(a.tgrid + (long long)k * ND);
                 if (!TSB_X_TG_EARLY) { e0 = TSB_TG_LD(e); e1 = TSB_TG_LD(e + 1); }
                 hit = ((__double_as_longlong(e0.x) ^ __double_as_longlong(t_tag)) | (__double_as_longlong(e0.y) ^ __double_as_longlong(dt_tag))) == 0;
-                if (!hit) tg_limit = -1;                    // this instance has left the pilot's grid: stop looking
+                if (!hit) { tg_limit = TSB_X_TGLOOK ? 0 : -1; tg_next = 0x7fffffff; }      // this instance has left the pilot's grid: stop looking
                 hit = hit && e1.x != TSB_TG_NO_KEY;
                 if (hit) {
                     key = e1.x;

@@ -602,16 +602,19 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
                         const TsbArgsHost& a_full, bool persistent) {
     tsb_ctx* ctx = b->ctx;
     const int block = o_auto.block_size > 0 ? o_auto.block_size : 128;
-    long long n_sub = (long long)ctx->sms * TSB_MAX_MIN_BLOCKS * block * 2;
-    if (n_sub > b->n_inst) n_sub = b->n_inst;
     cudaEvent_t e0, e1;
     CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
-    int best = rule_choice; float best_ms = 0.f;
+    int best = rule_choice; double best_per = 0.0;
     for (int mb = rule_choice; mb <= TSB_MAX_MIN_BLOCKS && mb <= rule_choice + 2; ++mb) {
         tsb_opts o = o_auto; o.min_blocks = mb;
         KernelModule* m = nullptr;
         int rc = get_module(b, o, -1, &m);
         if (rc != TSB_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        // three FULL waves of this candidate's own residency, compared per instance: one sub-batch size for all candidates
+        // (round 1: two waves of the largest) is a whole number of waves for that one only and charges the others a
+        // nearly empty tail wave — measured on rlc.cir: 6 blocks/SM won the sub-batch and lost the real run, 191 vs 184 ms
+        long long n_sub = (long long)ctx->sms * mb * block * 3;
+        if (n_sub > b->n_inst) n_sub = b->n_inst;
         float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {              // rep 0 loads the module and warms the clocks
             TsbArgsHost a = a_full; a.n_run = n_sub;
@@ -621,7 +624,8 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
             CU(ctx, cudaEventSynchronize(e1));
             CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
         }
-        if (mb == rule_choice || ms < best_ms * 0.98f) { best = mb; best_ms = ms; }     // a later candidate must win by 2 %
+        const double per = (double)ms / (double)n_sub;
+        if (mb == rule_choice || per < best_per * 0.97) { best = mb; best_per = per; }     // a later candidate must win by 3 %
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->auto_choice[autokey] = best;
