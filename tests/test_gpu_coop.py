@@ -74,3 +74,42 @@ def test_cooperative_mapping_refuses_what_it_does_not_cover(ctx):
         PU.run_gpu(ctx, dtext, 4, dov, out=T.OUT_STATS, opts=T.default_opts(coop_parts=2))
     with pytest.raises(T.TsbError):       # rc.cir: three unknowns, nothing to cut
         PU.run_gpu(ctx, T.BUNDLED["rc"], 4, PU.draws("rc", T.Circuit.from_netlist(T.BUNDLED["rc"]), 4), out=T.OUT_STATS, opts=T.default_opts(coop_parts=2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [2, 4])
+def test_cooperative_uic_and_start_time(ctx, parts):
+    """`uic` (no operating point: the hand-over carries zero state) and a start time > 0 (rows before it suppressed, the
+    result-store key of those steps never computed) on the cooperative mapping, against the oracle."""
+    text = rc_ladder(12)
+    n = 12
+    ov = PU.draws("ladder", T.Circuit.from_netlist(text), n, seed=9)
+    card = T.Circuit.from_netlist(text).analysis_card()
+    for tran in ({"uic": True}, {"tstart": 0.4 * card["tstop"]}, {"uic": True, "tstart": 0.25 * card["tstop"]}):
+        ckt, batch, an = PU.run_gpu(ctx, text, n, ov, cap_rows=1024, tran=tran, opts=T.default_opts(coop_parts=parts))
+        _, ores = PU.run_oracle(text, n, ov, cap_rows=1024, tran=tran)
+        rep = PU.compare_waves(batch, ores, n)
+        assert PU.report_ok(rep), (tran, PU.report_str(rep))
+        assert rep["compared_points"] > 0 and rep["counter_mismatch"] == 0, (tran, PU.report_str(rep))
+
+
+@pytest.mark.gpu
+def test_cooperative_processing_order_changes_no_bit(ctx):
+    """tsb_batch_set_order on the cooperative mapping: which instance a group of lanes works on is free; parameters and results
+    stay in the caller's order, bit for bit."""
+    text = rc_ladder(16)
+    n = 1000
+    ckt = T.Circuit.from_netlist(text, ctx)
+    ov = PU.draws("ladder", ckt, n, seed=4)
+    card = ckt.analysis_card()
+    res = []
+    for perm in (None, np.random.default_rng(1).permutation(n)):
+        b = ckt.batch(n)
+        for (d, p), v in ov.items():
+            b.set_param(d, p, v)
+        if perm is not None:
+            b.set_order(perm)
+        b.run_tran(card["tstart"], card["tstop"], card["tstep"], card["tmax"], card["uic"], out=T.OUT_STATS, opts=T.default_opts(coop_parts=2))
+        res.append((b.stats_all().copy(), b.rows().copy(), b.counters().copy(), b.status().copy()))
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y, equal_nan=True)
