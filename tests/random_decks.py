@@ -174,3 +174,46 @@ def rc_mesh(rows: int, cols: int) -> str:
     lines.append(f"Rload {nd(rows - 1, cols - 1)} 0 1k")
     lines.append(".tran 0.01ms 2ms")
     return "\n".join(lines) + "\n"
+
+
+def random_linear_network(seed: int, nodes: int = 16):
+    """A larger random LINEAR deck (for the cooperative mapping's partitioner): `nodes` nodes on a random spanning tree of
+    resistors plus a few chords (loops make separators of several unknowns), a capacitor to ground at most nodes, a couple of
+    inductors in series branches (branch unknowns), one or two sources of different waveforms.  Every node has a resistive
+    path to ground through the tree and a load resistor."""
+    rng = np.random.default_rng(50_000 + seed)
+    lines = [f"* random linear network {seed}, {nodes} nodes"]
+    src = ["SIN(0 5 1k)", "PULSE(0 5 0.1m 0.05m 0.05m 0.6m 1.5m)", "PWL(0 0 0.2m 0 0.5m 3.3 1m 3.3 1.2m -1 2m 0)"][seed % 3]
+    lines.append(f"Vin 1 0 {src}")
+    nr = nc = nl = 0
+    nxt = nodes + 1                      # extra nodes for the series inductors
+    n_ind = int(rng.integers(0, 3))
+    ind_edges = set(rng.choice(np.arange(2, nodes + 1), size=n_ind, replace=False).tolist()) if n_ind else set()
+    for k in range(2, nodes + 1):
+        lo = max(1, k - 4)               # a "wide chain": parents are recent nodes, so the graph has small cuts
+        other = int(rng.integers(lo, k))
+        rv = float(np.exp(rng.uniform(np.log(50), np.log(5e3))))
+        nr += 1
+        if k in ind_edges:               # R in series with L through an extra node
+            nl += 1
+            lines.append(f"R{nr} {other} {nxt} {rv:.5g}")
+            lines.append(f"L{nl} {nxt} {k} {float(np.exp(rng.uniform(np.log(2e-4), np.log(5e-3)))):.5g}")
+            nxt += 1
+        else:
+            lines.append(f"R{nr} {other} {k} {rv:.5g}")
+    for _ in range(max(1, nodes // 5)):  # chords
+        a = int(rng.integers(2, nodes + 1))
+        b = int(rng.integers(max(2, a - 5), min(nodes, a + 5) + 1))
+        if a != b:
+            nr += 1
+            lines.append(f"R{nr} {a} {b} {float(np.exp(rng.uniform(np.log(200), np.log(2e4)))):.5g}")
+    for k in range(2, nodes + 1):
+        if rng.random() < 0.8:
+            nc += 1
+            lines.append(f"C{nc} {k} 0 {float(np.exp(rng.uniform(np.log(2e-8), np.log(5e-7)))):.5g}")
+    nr += 1
+    lines.append(f"R{nr} {nodes} 0 {float(np.exp(rng.uniform(np.log(500), np.log(5e3)))):.5g}")
+    if seed % 2:
+        lines.append(f"Iload {max(2, nodes // 2)} 0 SIN(0 1m 2k)")
+    lines.append(".tran 0.01ms 2ms" if nl == 0 else ".tran 4e-6 4e-4")
+    return "\n".join(lines) + "\n", dict(nodes=nodes, inductors=nl)

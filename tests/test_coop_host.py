@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import parity_util as PU
-from random_decks import random_deck, rc_ladder, rc_mesh, rlc_ladder
+from random_decks import random_deck, random_linear_network, rc_ladder, rc_mesh, rlc_ladder
 
 T = PU.T
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -160,6 +160,8 @@ for _k in (2, 4, 7):
 DECKS["mesh3x4"] = rc_mesh(3, 4)
 DECKS["mesh4x5"] = rc_mesh(4, 5)
 DECKS["random0"] = random_deck(0)[0]
+for _s in range(8):
+    DECKS[f"net{_s}"] = random_linear_network(_s, 12 if _s % 2 else 20)[0]
 
 
 @pytest.mark.parametrize("parts", [2, 4, 8])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import parity_util as PU
-from random_decks import rc_ladder, rc_mesh, rlc_ladder
+from random_decks import random_linear_network, rc_ladder, rc_mesh, rlc_ladder
 
 T = PU.T
 
@@ -17,6 +17,9 @@ DECKS = {
     "rlc": (T.BUNDLED["rlc"], 24000),
     "rl": (T.BUNDLED["rl"], 24000),
 }
+for _s in (0, 2, 5, 6):          # random linear networks: irregular graphs, loops, inductor branches, three source waveforms
+    _t, _i = random_linear_network(_s, 20)
+    DECKS[f"net{_s}"] = (_t, 1024 if _i["inductors"] == 0 else 24000)
 
 
 @pytest.mark.gpu
@@ -113,3 +116,20 @@ def test_cooperative_processing_order_changes_no_bit(ctx):
         res.append((b.stats_all().copy(), b.rows().copy(), b.counters().copy(), b.status().copy()))
     for x, y in zip(res[0], res[1]):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_wide_circuit_on_the_thread_mapping(ctx):
+    """A 32-section ladder has 67 result columns: the statistics of a 128-thread block (274 KB) exceed an SM's shared memory.
+    Thread-per-circuit (coop_parts = 0) must still run — the library shrinks the block to 96 threads — and agree with the
+    cooperative mapping, which is what the default picks."""
+    text = rc_ladder(32)
+    n = 200
+    ov = PU.draws("ladder", T.Circuit.from_netlist(text), n, seed=8)
+    _, b0, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS, opts=T.default_opts(coop_parts=0, min_blocks=1))
+    s0, r0, c0 = b0.stats_all().copy(), b0.rows().copy(), b0.counters().copy()
+    _, b1, _ = PU.run_gpu(ctx, text, n, ov, out=T.OUT_STATS)
+    s1, r1, c1 = b1.stats_all(), b1.rows(), b1.counters()
+    assert np.array_equal(r0, r1) and np.array_equal(c0[:6], c1[:6]) and (b0.status() == 0).all() and (b1.status() == 0).all()
+    tol = 1e-9 * np.abs(s0) + 1e-12
+    assert np.all(np.abs(s1[[0, 1, 3]] - s0[[0, 1, 3]]) <= tol[[0, 1, 3]] * 10)

@@ -108,6 +108,12 @@ __device__ __forceinline__ long long tsb_slot_instance(const TsbArgs& a, long lo
 #ifndef TSB_X_TGLOOK
 #define TSB_X_TGLOOK 1              // shared time grid: one compare on the hot path of the look-up bookkeeping (tsb_tran_linear)
 #endif
+#ifndef TSB_X_CONV2TOL
+#define TSB_X_CONV2TOL 1            // convergence test against two tolerances instead of the tolerance of a selected maximum
+#endif
+#ifndef TSB_X_NRSTATE
+#define TSB_X_NRSTATE 1             // nonlinear transient: one integer state per lane in the Newton loop instead of three bools
+#endif
 #ifndef TSB_X_LTEFLAGS
 #define TSB_X_LTEFLAGS 1            // linear loop: truncation-error DECISIONS from predicates instead of selecting the maximum
 #endif
@@ -121,11 +127,20 @@ __device__ __forceinline__ bool tsb_converged(const double* x, const double* xo,
 #pragma unroll
     for (int i = 1; i <= N; ++i) {
         const double diff = fabs(x[i] - xo[i]);
+        const double ax = fabs(x[i]), ao = fabs(xo[i]);
+#if TSB_X_CONV2TOL
+        // diff > reltol * max(|new|, |old|) + abstol  <=>  diff exceeds BOTH reltol * |new| + abstol and reltol * |old| + abstol:
+        // a rounded product by reltol > 0 and a rounded sum are monotone in the operand, so the larger of the two tolerances IS
+        // the tolerance of the larger magnitude, bit for bit — two multiply-adds with |.| operand modifiers and two compares
+        // instead of materialising the magnitudes and selecting their maximum (8 -> 5 instructions per unknown and trip).
+        // NaN: diff is NaN whenever an operand is, both compares are false, the test passes as in the reference.
+        if ((diff > reltol * ax + abstol) & (diff > reltol * ao + abstol)) ok = false;
+#else
         // math.Max(|new|, |old|) as a plain select: the two differ only when an operand is NaN — and then diff is NaN too, so
         // `diff > tol` is false whatever tol is (the library fmax costs ~10 instructions per element for its NaN handling)
-        const double ax = fabs(x[i]), ao = fabs(xo[i]);
         const double tol = reltol * (TSB_X_CONVSEL ? (ax > ao ? ax : ao) : fmax(ax, ao)) + abstol;
         if (diff > tol) ok = false;
+#endif
     }
     return ok;
 }
@@ -535,6 +550,31 @@ __device__ __forceinline__ void tsb_tran_nonlinear(const TsbArgs& a, Ckt& c, Sin
         }
         // ---- doNRiter (tran.go:157-216) ---------------------------------------------------------------------
         int iter = 0;
+#if TSB_X_NRSTATE
+        // one integer per lane (0 iterating, 1 converged, 2 failed / not live): three bools carried across the loop were kept
+        // byte-packed by the compiler — 9 PRMT and a dozen flag instructions per trip (r02_notes section 9)
+        int nr = live ? 0 : 2;
+        while (__any_sync(0xffffffffu, nr == 0)) {
+            if (nr == 0) {
+                if (iter > 0) c.update_nl(c.xo);
+                bool solved;
+                if constexpr (Ckt::HAS_TF) solved = c.template assemble_solve_tf<true>(time, dt, rdt, typename Ckt::TsbNoMid());   // condensed elimination
+                else solved = c.template assemble_solve<TSB_MODE_TRAN>(TSB_MODE_TRAN, time, dt, rdt, 0.0);
+                ++n_sol;
+                if (!solved) nr = 2;
+                else {
+                    const bool cv = iter > 0 && tsb_converged<N>(c.x, c.xo, a.reltol, a.abstol);
+                    if (cv) nr = 1;
+                    else {
+#pragma unroll
+                        for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
+                        if (++iter >= a.max_iter) nr = 2;
+                    }
+                }
+            }
+        }
+        const bool fail = nr == 2;
+#else
         bool conv = false, fail = false, iterating = live;
         while (__any_sync(0xffffffffu, iterating)) {
             if (iterating) {
@@ -555,6 +595,7 @@ __device__ __forceinline__ void tsb_tran_nonlinear(const TsbArgs& a, Ckt& c, Sin
                 iterating = !(conv || fail);
             }
         }
+#endif
         // ---- tran.go:113-151 ------------------------------------------------------------------------------------
         if (live) {
             if (fail) {
@@ -868,24 +909,25 @@ __device__ __forceinline__ void tsb_run_dc_instance(const TsbArgs& a, long long 
             ++n_pts;
         }
         int iter = 0;
-        bool conv = false, fail = false, iterating = live;
-        while (__any_sync(0xffffffffu, iterating)) {
-            if (iterating) {
+        int nr = live ? 0 : 2;                       // 0 iterating, 1 converged, 2 failed / not live (see tsb_tran_nonlinear)
+        while (__any_sync(0xffffffffu, nr == 0)) {
+            if (nr == 0) {
                 if (Ckt::HAS_NL && iter > 0) c.update_nl(c.xo);
                 const bool solved = c.template assemble_solve<TSB_MODE_OP>(TSB_MODE_OP, 0.0, 0.0, 0.0, 0.0);
                 ++n_sol;
-                if (!solved) fail = true;
+                if (!solved) nr = 2;
                 else {
-                    if (iter > 0) conv = tsb_converged_dc<N>(c.x, c.xo, a.reltol, a.abstol);
-                    if (!conv) {
+                    const bool cv = iter > 0 && tsb_converged_dc<N>(c.x, c.xo, a.reltol, a.abstol);
+                    if (cv) nr = 1;
+                    else {
 #pragma unroll
                         for (int i = 1; i <= N; ++i) c.xo[i] = c.x[i];
-                        if (++iter >= a.max_iter) fail = true;
+                        if (++iter >= a.max_iter) nr = 2;
                     }
                 }
-                iterating = !(conv || fail);
             }
         }
+        const bool fail = nr == 2;
         if (live) {
             if (fail) { status = TSB_ST_DC_FAILED; fail_at = a.sweep[k]; live = false; }
             else {

@@ -564,6 +564,41 @@ static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
         std::sort(interior[p].begin(), interior[p].end());
         for (int v : interior[p]) cp.owner[v] = p;
     }
+    // ---- the nominal transient matrix (pattern and values) ------------------------------------------------------------------
+    const double dt_rep = 1e-6;
+    std::vector<std::vector<char>> on(n + 1, std::vector<char>(n + 1, 0));
+    std::vector<std::vector<double>> val(n + 1, std::vector<double>(n + 1, 0.0));
+    {
+        TsbEnv env{TSB_MODE_TRAN, 0.0, dt_rep, 0.0, 1.0 / dt_rep};
+        double o[64];
+        for (int di : pl.stamp_order) {
+            const Dev& d = pl.devs[di];
+            if (device_num_outputs(d) > 64) return false;
+            nom.eval(di, env, o);
+            for (const StampEntry& s : pl.stamps[di]) {
+                if (s.col == 0) continue;
+                on[s.row][s.col] = 1;
+                val[s.row][s.col] += s.sign * (s.out == OUT_CONST ? s.cval : o[s.out]);
+            }
+        }
+    }
+    // an interior unknown whose row or column has no entry inside its own interior (a voltage source's branch whose node went
+    // to the separator: its row holds the +-1 at that node only) cannot be pivoted there: it joins the separator
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int u = 1; u <= n; ++u) {
+            const int p = cp.owner[u];
+            if (p < 0) continue;
+            bool row = false, col = false;
+            for (int v = 1; v <= n; ++v) if (cp.owner[v] == p) { row = row || on[u][v]; col = col || on[v][u]; }
+            if (!row || !col) { cp.owner[u] = -1; changed = true; }
+        }
+    }
+    for (int p = 0; p < parts; ++p) {
+        interior[p].clear();
+        for (int u = 1; u <= n; ++u) if (cp.owner[u] == p) interior[p].push_back(u);
+        if (interior[p].empty()) return false;
+    }
     // ---- devices and result columns ---------------------------------------------------------------------------------------
     cp.dev_owner.assign(pl.devs.size(), -1);
     std::vector<int> load(parts, 0);
@@ -586,24 +621,7 @@ static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
         if (c != ncol) return false;
     }
     for (int u = 1; u <= n; ++u) if (cp.owner[u] < 0) { int p = (int)(std::min_element(ncols.begin(), ncols.end()) - ncols.begin()); cp.col_owner[u] = p; ++ncols[p]; }
-    // ---- nested-dissection order on the nominal transient matrix -----------------------------------------------------------
-    const double dt_rep = 1e-6;
-    std::vector<std::vector<char>> on(n + 1, std::vector<char>(n + 1, 0));
-    std::vector<std::vector<double>> val(n + 1, std::vector<double>(n + 1, 0.0));
-    {
-        TsbEnv env{TSB_MODE_TRAN, 0.0, dt_rep, 0.0, 1.0 / dt_rep};
-        double o[64];
-        for (int di : pl.stamp_order) {
-            const Dev& d = pl.devs[di];
-            if (device_num_outputs(d) > 64) return false;
-            nom.eval(di, env, o);
-            for (const StampEntry& s : pl.stamps[di]) {
-                if (s.col == 0) continue;
-                on[s.row][s.col] = 1;
-                val[s.row][s.col] += s.sign * (s.out == OUT_CONST ? s.cval : o[s.out]);
-            }
-        }
-    }
+    // ---- nested-dissection order ------------------------------------------------------------------------------------------
     PivotOrder ord; ord.n = n; ord.ext2int.assign(n + 1, 0); ord.prow.assign(n + 1, 0); ord.pcol.assign(n + 1, 0);
     cp.step_owner.assign(n + 1, -1);
     std::vector<char> rdone(n + 1, 0), cdone(n + 1, 0);

@@ -589,6 +589,14 @@ tsb_opts resolve(const tsb_opts* o, const Plan& plan) {
     return r;
 }
 
+// Per-thread statistics live in shared memory (32 bytes per result column): a circuit with many result columns does not fit
+// 128 threads' worth into an SM's 227 KB.  The block shrinks (whole warps) until it does; the block size is part of the
+// kernel's specialisation, so this happens before the module is requested.
+void fit_block_to_shared_memory(tsb_opts& o, int ncol, int out_flags) {
+    if (!(out_flags & (TSB_OUT_STATS | TSB_OUT_GRID))) return;
+    while (o.block_size > 32 && (size_t)4 * ncol * o.block_size * sizeof(double) > (size_t)226 * 1024) o.block_size -= 32;
+}
+
 // Launch-bounds autotuning.  The spill rule above is a static prior; what it trades (resident warps against spilled
 // bytes) moves with every change of the generated code, and the measured optimum was 1-2 blocks/SM above the rule
 // for the nonlinear decks (profiles/r01_notes.md).  So the first transient run of a large batch times the
@@ -1118,7 +1126,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: TSB_OUT_GRID is not available on the cooperative mapping");
         if (!o.skip_linear_resolve || o.lane_refill) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts needs skip_linear_resolve = 1 and lane_refill = 0");
         if (o.min_blocks <= 0) o.min_blocks = 2;          // tsb_optran only runs the operating point here: no launch-bounds search
-    }
+    } else fit_block_to_shared_memory(o, b->plan->p.num_columns(TSB_AN_TRAN), out_flags);
     KernelModule* m = nullptr;
     b->grid_kernel = (out_flags & TSB_OUT_GRID) != 0;
     std::string autokey;
@@ -1205,6 +1213,7 @@ static int run_dc_impl(tsb_batch* b, int src_dev, double start, double stop, dou
     }
     tsb_opts o = resolve(opts, b->plan->p);
     o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
+    fit_block_to_shared_memory(o, p.num_columns(nested ? (int)TSB_AN_DC2 : (int)TSB_AN_DC), out_flags);
     CU(ctx, cudaSetDevice(ctx->device));
     auto dc_param_of = [&](int d) {
         const Dev& sd = p.devs[d];
@@ -1257,6 +1266,7 @@ int tsb_run_ac(tsb_batch* b, int sweep_type, int n_points, double fstart, double
     ac_frequency_points(sweep_type, n_points, fstart, fstop, f);       // ac.go:100-126
     tsb_opts o = resolve(opts, p);
     o.coop_parts = 0;          // the cooperative mapping is a transient-only specialisation
+    fit_block_to_shared_memory(o, b->plan->p.num_columns(TSB_AN_AC), out_flags);
     CU(ctx, cudaSetDevice(ctx->device));
     KernelModule* m = nullptr;
     if ((rc = get_module(b, o, -1, &m)) != TSB_OK) return rc;
