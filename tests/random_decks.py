@@ -217,3 +217,37 @@ def random_linear_network(seed: int, nodes: int = 16):
         lines.append(f"Iload {max(2, nodes // 2)} 0 SIN(0 1m 2k)")
     lines.append(".tran 0.01ms 2ms" if nl == 0 else ".tran 4e-6 4e-4")
     return "\n".join(lines) + "\n", dict(nodes=nodes, inductors=nl)
+
+
+def diode_rc_ladder(sections: int) -> str:
+    """Nonlinear larger-n deck: the RC ladder with a diode clamp to ground at every third node (and a reverse one at every
+    fourth): Newton loops on a circuit of sections + 2 unknowns."""
+    lines = [f"* diode-clamped RC ladder, {sections} sections", "Vin 1 0 SIN(0 5 1k)"]
+    nd = 0
+    for k in range(1, sections + 1):
+        lines.append(f"R{k} {k} {k + 1} 100")
+        lines.append(f"C{k} {k + 1} 0 100n")
+        if k % 3 == 0:
+            nd += 1
+            lines.append(f"D{nd} {k + 1} 0 D")
+        elif k % 4 == 0:
+            nd += 1
+            lines.append(f"D{nd} 0 {k + 1} D")
+    lines.append(".tran 0.01ms 3ms")
+    return "\n".join(lines) + "\n"
+
+
+def mos_follower_chain(stages: int) -> str:
+    """Nonlinear larger-n deck with a hub: `stages` NMOS source followers (Level 1) in a chain, all drains on the supply node
+    — the supply node and its branch end up in the separator."""
+    lines = [f"* NMOS source-follower chain, {stages} stages", "VDD 1 0 DC 5", "VG 2 0 PULSE(0 5 1u 100n 100n 5u 10u)"]
+    prev = 2
+    for k in range(1, stages + 1):
+        out = 2 + k
+        lines.append(f"M{k} 1 {prev} {out} 0 NMOS_T L=2u W=20u")
+        lines.append(f"RS{k} {out} 0 10k")
+        lines.append(f"CS{k} {out} 0 1p")
+        prev = out
+    lines.append(".model NMOS_T NMOS(Level=1 VTO=0.7 KP=20u LAMBDA=0.01)")
+    lines.append(".tran 0.1u 10u")
+    return "\n".join(lines) + "\n"

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import parity_util as PU
-from random_decks import random_deck, random_linear_network, rc_ladder, rc_mesh, rlc_ladder
+from random_decks import diode_rc_ladder, mos_follower_chain, random_deck, random_linear_network, rc_ladder, rc_mesh, rlc_ladder
 
 T = PU.T
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -70,7 +70,7 @@ int main() {
         a.coop_state = state;
         Ckt c1;
         c1.load(a, 0); c1.init();
-        for (int k = 0; k < NSTATE; ++k) { double v = (uni() - 0.5) * 6.0; c1.S[k] = v; state[k] = v; }
+        for (int k = 0; k < NSTATE; ++k) { double v = (uni() - 0.5) * (NONLINEAR ? 1.2 : 6.0); c1.S[k] = v; state[k] = v; }
         for (int u = 0; u <= Ckt::N; ++u) { double v = u ? (uni() - 0.5) * 4.0 : 0.0; c1.x[u] = v; state[NSTATE + u] = v; }
         const double time = uni() * 2e-3, dt = std::exp(std::log(1e-9) + uni() * std::log(1e5));
         bool gt1, sm1;
@@ -137,7 +137,7 @@ def coop_host_check(text, parts, tmp):
             .replace("OWNER", ", ".join(map(str, owner)))
             .replace("NPAR", str(len(nominal))).replace("NOMINAL", ", ".join(repr(float(v)) for v in nominal) or "0")
             .replace("NVAR", str(len(slots))).replace("VARIDX", "((const int[]){" + ", ".join(map(str, slots or [0])) + "})")
-            .replace("NSTATE", str(nstate))
+            .replace("NSTATE", str(nstate)).replace("NONLINEAR", "1" if "HAS_NL = true" in struct else "0")
             .replace("PARTS_DECL", " ".join(f"CoopPart{p} q{p};" for p in range(parts)))
             .replace("PARTS_A", " ".join(f"run_a(q{p}, a, time, dt, xb, flags);" for p in range(parts)))
             .replace("PARTS_B", " ".join(f"run_b(q{p}, xb, dt, time, flags, x2, s2, row2, owner);" for p in range(parts))))
@@ -162,6 +162,12 @@ DECKS["mesh4x5"] = rc_mesh(4, 5)
 DECKS["random0"] = random_deck(0)[0]
 for _s in range(8):
     DECKS[f"net{_s}"] = random_linear_network(_s, 12 if _s % 2 else 20)[0]
+# circuits with nonlinear devices (the Newton-loop form of the cooperative mapping)
+DECKS["diodeladder12"] = diode_rc_ladder(12)
+DECKS["diodeladder24"] = diode_rc_ladder(24)
+DECKS["moschain6"] = mos_follower_chain(6)
+DECKS["moschain12"] = mos_follower_chain(12)
+DECKS["mosfet1"] = T.BUNDLED["mosfet1"]
 
 
 @pytest.mark.parametrize("parts", [2, 4, 8])

@@ -195,7 +195,11 @@ void emit_lu(Emitter& e, const LuProgram& lu, bool load_gmin, const std::string&
         // the dense (BJT) build returns at once, as the reference does.
         if (lu.dense) e.line("if (" + piv + " == 0.0) return false;");
         else e.line("lu_ok = lu_ok & (" + piv + " != 0.0);");
-        e.line(piv + " = " + std::string(lu.dense ? "1.0 / " + piv : "tsb_rcp(" + piv + ")") + ";");
+        // dense (BJT) builds: Inf / NaN pivots must give what IEEE gives the reference (1/Inf = 0, NaN stays NaN) — tsb_qdiv keeps
+        // the special values (the hardware seed wherever the correction did not converge) without the compiler's division
+        // sequence, whose slow path is a CALL for every non-finite operand: 11.8 calls per accepted step on bjt2.cir, where
+        // 99.8 % of the instances overflow to NaN as in the reference (r02_notes section 10)
+        e.line(piv + " = " + std::string(lu.dense ? "tsb_qdiv(1.0, " + piv + ")" : "tsb_rcp(" + piv + ")") + ";");
         for (size_t ui = 0; ui < st.urow.size(); ++ui) {
             std::string u = "A[" + std::to_string(st.urow[ui]) + "]";
             e.line(u + " *= " + piv + ";");
@@ -597,7 +601,7 @@ struct CoopSym {
     std::vector<int> cols;                 // own result columns, ascending (part 0: column 0 = TIME first)
 };
 
-static const int COOP_HDR = 2;             // exchange slots 0 (flags) and 1 (result-store key, part 0)
+static const int COOP_HDR = 3;             // exchange slots 0 (flags of phase_a), 1 (result-store key, part 0), 2 (flags of phase_b: Newton loops)
 
 void coop_analyse(const Plan& pl, const CoopPlan& cp, std::vector<CoopSym>& sym, int& nx) {
     const LuProgram& lu = cp.lu;
@@ -648,6 +652,7 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
     e.line("#define TSB_COOP_NX " + S(nx) + "          // exchange slots per part and attempt");
     e.line("#define TSB_COOP_NOWN_MAX " + S(nown_max) + "   // result columns of the widest part");
     e.line("#define TSB_COOP_NCOL " + S((int)cp.col_owner.size()));
+    e.line("#define TSB_COOP_NL " + std::string(pl.has_nonlinear ? "1" : "0") + "            // Newton loop (two barriers per iteration) / one solve per step");
     // the separator system after the gather: which entries / right-hand sides exist, for every part alike
     std::set<int> sep_touched, sep_cnz;
     for (const CoopSym& y : sym) { sep_touched.insert(y.xe.begin(), y.xe.end()); sep_cnz.insert(y.xc.begin(), y.xc.end()); }
@@ -658,6 +663,7 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
         e.line("struct CoopPart" + S(p) + " {");
         ++e.ind;
         e.line("static constexpr int PART = " + S(p) + ", NOWN = " + S((int)y.cols.size()) + ", N = " + S(n) + ";");
+        e.line("double xo[" + S(n + 1) + "];   // oldSolution of the Newton loop (circuits with nonlinear devices)");
         e.line("double P[" + S(std::max(1, pl.n_params)) + "], S[" + S(std::max(1, pl.n_state)) + "], D[" + S(std::max(1, pl.n_derived)) + "], SV[" +
                S(std::max(1, pl.n_src)) + "], x[" + S(n + 1) + "];     // global numbering; only this part's elements are ever touched");
         e.line("double A[" + S((int)lu.pos.size()) + "], c[" + S(n + 1) + "];   // factors / substitution vector kept from phase_a to phase_b");
@@ -686,12 +692,13 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
             if (d.kind == TSB_R) e.line("D[" + S(d.d_off) + "] = tsb_res_g(" + P + ");");
             else if (d.kind == TSB_L) e.line("tsb_ind_derive(" + P + ", D + " + S(d.d_off) + ");");
             else if (d.kind == TSB_LCORE) e.line("D[" + S(d.d_off) + "] = tsb_lcore_L0(" + P + ");");
+            else if (d.kind == TSB_D) e.line("tsb_dio_derive(" + P + ", D + " + S(d.d_off) + ");");
             for (int q = 0; q < d.n_state; ++q) e.line("S[" + S(d.s_off + q) + "] = a.coop_state[(long long)" + S(d.s_off + q) + " * a.n_inst + inst];");
             if (d.src_slot >= 0) e.line("SV[" + S(d.src_slot) + "] = 0.0;");
         }
         for (int u = 1; u <= n; ++u)
-            if (cp.owner[u] == p || cp.owner[u] < 0) e.line("x[" + S(u) + "] = a.coop_state[(long long)" + S(pl.n_state + u) + " * a.n_inst + inst];");
-        e.line("x[0] = 0.0;");
+            if (cp.owner[u] == p || cp.owner[u] < 0) e.line("x[" + S(u) + "] = a.coop_state[(long long)" + S(pl.n_state + u) + " * a.n_inst + inst]; xo[" + S(u) + "] = x[" + S(u) + "];");
+        e.line("x[0] = 0.0; xo[0] = 0.0;");
         --e.ind;
         e.line("}");
         // ---- sources --------------------------------------------------------------------------------------------
@@ -860,6 +867,37 @@ void emit_coop(Emitter& e, const Plan& pl, const CoopPlan& cp, const CodegenConf
         --e.ind;
         e.line("}");
         // ---- state of the own time-dependent devices, own result columns --------------------------------------------
+        // ---- Newton loop helpers (circuits with nonlinear devices): own devices, own unknowns ------------------------------
+        e.line("__device__ __forceinline__ void update_nl(const double* v) {   // circuit.UpdateNonlinearVoltages, own devices");
+        ++e.ind;
+        for (int di : y.devs) {
+            const Dev& d = pl.devs[di];
+            if (!d.nonlinear()) continue;
+            std::string Sx = "S + " + S(d.s_off);
+            auto v = [&](int k) { return "v[" + S(d.nodes[k]) + "]"; };
+            if (d.kind == TSB_D) e.line("S[" + S(d.s_off) + "] = " + v(0) + " - " + v(1) + ";");
+            else if (d.kind == TSB_M) e.line("tsb_mos_update(" + Sx + ", " + S(d.ip.size() > 1 ? d.ip[1] : 0) + ", " + v(0) + ", " + v(1) + ", " + v(2) + ", " + v(3) + ");");
+        }
+        e.line("(void)v;");
+        --e.ind;
+        e.line("}");
+        {
+            // convergence of the own unknowns (tran.go:192-207; the two-tolerance form of tsb_converged); the separator's
+            // unknowns are the same bits in every part: part 0 tests them
+            e.line("__device__ __forceinline__ bool converged_own(double reltol, double abstol) const {");
+            ++e.ind;
+            e.line("bool ok = true;");
+            for (int u = 1; u <= n; ++u)
+                if (cp.owner[u] == p || (cp.owner[u] < 0 && p == 0))
+                    e.line("{ const double diff = fabs(x[" + S(u) + "] - xo[" + S(u) + "]); if ((diff > reltol * fabs(x[" + S(u) + "]) + abstol) & (diff > reltol * fabs(xo[" + S(u) +
+                           "]) + abstol)) ok = false; }");
+            e.line("return ok;");
+            --e.ind;
+            e.line("}");
+            e.line("__device__ __forceinline__ void keep_old() {   // oldSolution = solution, own and separator unknowns");
+            for (int u = 1; u <= n; ++u) if (cp.owner[u] == p || cp.owner[u] < 0) e.line("    xo[" + S(u) + "] = x[" + S(u) + "];");
+            e.line("}");
+        }
         auto vd_expr = [&](const Dev& d) { return "(x[" + S(d.nodes[0]) + "] - x[" + S(d.nodes[1]) + "])"; };
         e.line("__device__ __forceinline__ void load_state(double dt) {");
         ++e.ind;
@@ -1305,7 +1343,8 @@ std::string generate_source(const Plan& pl, const CodegenConfig& cfg) {
         e.line("    for (long long base = (long long)blockIdx.x * (G * 32); base < a.n_run; base += (long long)gridDim.x * (G * 32)) {");
         e.line("        const long long slot = base + group * 32 + lane;");
         e.line("        const bool valid = slot < a.n_run;");
-        e.line("        tsb_coop_tran_part<Part>(a, tsb_slot_instance(a, slot, valid), valid, xg, 1 + group);");
+        e.line("        if (TSB_COOP_NL) tsb_coop_tran_nl_part<Part>(a, tsb_slot_instance(a, slot, valid), valid, xg, 1 + group);");
+        e.line("        else tsb_coop_tran_part<Part>(a, tsb_slot_instance(a, slot, valid), valid, xg, 1 + group);");
         e.line("    }");
         e.line("}");
         e.line("extern \"C\" __global__ void __launch_bounds__(TSB_COOP_BLOCK, TSB_COOP_MIN_BLOCKS) tsb_coop_tran(TsbArgs a) {");

@@ -197,4 +197,128 @@ __device__ __forceinline__ void tsb_coop_tran_part(const TsbArgs& a, long long i
     }
 }
 
+// The same for circuits WITH nonlinear devices (diodes, MOSFETs; BJT circuits do not partition): the Newton loop of
+// tran.go:157-216 around phase_a / phase_b.  Per iteration two barriers: contributions -> [barrier] -> separator solve,
+// back substitution and the part's own convergence test -> [barrier] -> every part combines the convergence flags and takes
+// the same decision.  Trip counts are uniform over the warp (votes, as in tsb_tran_nonlinear) and therefore over the group:
+// every part of an instance holds the same Newton state.  The truncation-error predicates read only the state of the last
+// accepted steps (not the solution being computed), so they travel with the first iteration's exchange, and so does the
+// result-store key of the step's end.
+template <class Part>
+__device__ __forceinline__ void tsb_coop_tran_nl_part(const TsbArgs& a, long long inst, bool valid, double* xg, int bar_id) {
+    constexpr int NP = TSB_COOP_PARTS, NX = TSB_COOP_NX;
+    const int lane = threadIdx.x & 31;
+    Part c;
+    TsbCoopSink<Part> sink(a, inst);
+    bool live = false;
+    if (valid) {
+        sink.begin();
+        live = a.status[inst] == TSB_ST_OK;
+        if (live) c.load(a, inst);
+    }
+    double time = 0.0, dt = a.minstep;
+    double last_key = -1.0;
+    TsbTimeKeyer keyer; keyer.reset();
+    int n_acc = 0, n_rej = 0, n_sol = 0;
+    int status = TSB_ST_OK;
+    double fail_at = 0.0;
+    live = live && time < a.tstop;
+    const bool ran = live;
+    int buf = 0;
+    while (__any_sync(0xffffffffu, live)) {
+        double next_time = time + dt;
+        double rdt = 0.0, key = -2.0;
+        bool lte_gt = false, lte_small = false;
+        if (live) {
+            if (next_time > a.tstop) { next_time = a.tstop; dt = next_time - time; }
+            rdt = tsb_rcp_dt(dt);
+            if (!c.eval_sources_nb(time)) c.eval_sources(time, 1.0);
+        }
+        int iter = 0;
+        int nr = live ? 0 : 2;                        // 0 iterating, 1 converged, 2 failed / not live
+        while (__any_sync(0xffffffffu, nr == 0)) {
+            double* xb = xg + (long long)buf * (NP * NX * 32) + lane;
+            double* mine = xb + Part::PART * NX * 32;
+            if (nr == 0) {
+                if (iter > 0) c.update_nl(c.xo);
+                const bool ok = c.phase_a(time, dt, rdt, mine);
+                int f = ok ? 4 : 0;
+                if (iter == 0) {
+                    bool g, sm;
+                    c.lte_flags(dt, rdt, a.trtol, a.trtol / 100, g, sm);
+                    f |= (g ? 1 : 0) | (sm ? 2 : 0);
+                    if (Part::PART == 0) mine[32] = next_time >= a.tstart ? keyer.key_any(next_time) : -2.0;
+                }
+                mine[0] = __longlong_as_double((long long)f);
+            }
+            tsb_coop_barrier(bar_id);
+            bool solved = false;
+            if (nr == 0) {
+                int f_or = 0, f_and = 7;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { const int f = (int)__double_as_longlong(xb[q * NX * 32]); f_or |= f; f_and &= f; }
+                if (iter == 0) { lte_gt = (f_or & 1) != 0; lte_small = (f_and & 2) != 0; key = xb[32]; }
+                solved = c.phase_b(xb) & ((f_and & 4) != 0);          // the same in every part: separator pivots and the AND of the own ones
+                ++n_sol;
+                const bool cv = solved && iter > 0 && c.converged_own(a.reltol, a.abstol);
+                mine[64] = __longlong_as_double((long long)(cv ? 1 : 0));
+            }
+            tsb_coop_barrier(bar_id);
+            if (nr == 0) {
+                if (!solved) nr = 2;
+                else {
+                    int cv_and = 1;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) cv_and &= (int)__double_as_longlong(xb[(q * NX + 2) * 32]);
+                    if (iter > 0 && cv_and) nr = 1;
+                    else {
+                        c.keep_old();
+                        if (++iter >= a.max_iter) nr = 2;
+                    }
+                }
+            }
+            buf ^= 1;
+        }
+        if (live) {
+            if (nr == 2) {                           // tran.go:113-120
+                if (dt > a.minstep) { dt /= 2; ++n_rej; }
+                else { status = TSB_ST_TRAN_FAILED; fail_at = time; live = false; }
+            } else if (lte_gt && dt > a.minstep) { dt /= 2; ++n_rej; }
+            else {
+                c.load_state(dt);
+                c.update_state();
+                time = next_time;
+                if (time >= a.tstart && key != last_key) {
+                    double row[Part::NOWN > 0 ? Part::NOWN : 1];
+                    c.signals(time, row);
+                    sink.push(c, row);
+                    last_key = key;
+                }
+                if (time < a.tstop && dt < a.maxstep) {
+                    const double grown = lte_small ? dt * 2 : dt * 1.1;
+                    dt = grown < a.maxstep ? grown : a.maxstep;
+                }
+                ++n_acc;
+                live = time < a.tstop;
+            }
+        }
+    }
+    tsb_coop_barrier(bar_id);
+    if (!valid) return;
+    sink.finish(c);
+    if (Part::PART == 0) {
+        if (sink.overflow && status == TSB_ST_OK) status = TSB_ST_OVERFLOW;
+        a.rows[inst] = sink.n_rows;
+        if (status != TSB_ST_OK) a.status[inst] = status;
+        if (ran) {
+            a.counters[0 * a.n_inst + inst] = n_acc;
+            a.counters[1 * a.n_inst + inst] = n_rej;
+            a.counters[2 * a.n_inst + inst] = n_sol;
+            a.counters[5 * a.n_inst + inst] = __double_as_longlong(fail_at);
+            a.counters[6 * a.n_inst + inst] += n_sol;
+            a.counters[7 * a.n_inst + inst] = sink.n_rows;
+        }
+    }
+}
+
 #endif  // TSB_COOP_CUH

@@ -872,6 +872,15 @@ __device__ __forceinline__ void tsb_run_optran_instance(const TsbArgs& a, long l
         finish_instance();
     }
     if (NL_LOOP) {
+#if TSB_COOP
+        if (a.coop_state) {           // hand-over to the cooperative transient kernel, as for linear circuits above
+            if (valid) {
+                if (linear_tran) c.dump_state(a.coop_state, a.n_inst, inst);
+                finish_instance();
+            }
+            return;
+        }
+#endif
         // every lane of the warp arrives here together (the loop above ends on a full-warp vote)
         tsb_tran_nonlinear(a, c, sink, valid && linear_tran, n_acc, n_rej, n_sol_tran, n_exec, status, fail_at);
         if (valid) finish_instance();

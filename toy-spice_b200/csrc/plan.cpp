@@ -525,7 +525,7 @@ Cut bisect(const std::vector<int>& V, const std::vector<std::vector<char>>& adj,
 
 static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
     const int n = pl.n();
-    if (pl.has_nonlinear || pl.has_mutual || n < 2 * parts || n > 96 || (parts != 2 && parts != 4 && parts != 8)) return false;
+    if (pl.has_bjt || pl.has_mutual || n < 2 * parts || n > 96 || (parts != 2 && parts != 4 && parts != 8)) return false;     // BJT circuits are generated dense (NaN bookkeeping): no partition
     // ---- graph ------------------------------------------------------------------------------------------------------------
     std::vector<std::vector<char>> adj(n + 1, std::vector<char>(n + 1, 0));
     std::vector<std::vector<int>> dev_unk(pl.devs.size());
@@ -557,7 +557,15 @@ static bool build_coop(const Plan& pl, Nominal& nom, int parts, CoopPlan& cp) {
                 return c.ok && run(c.A, lv - 1) && run(c.B, lv - 1);
             }
         } rec{adj, n, interior};
-        if (!rec.run(all, levels) || (int)interior.size() != parts) return false;
+        // hubs (a supply rail every stage hangs on) make every breadth-first level set huge: they go to the separator first
+        std::vector<int> rest;
+        for (int v : all) {
+            int deg = 0;
+            for (int w = 1; w <= n; ++w) deg += adj[v][w];
+            if (deg >= std::max(6, n / 2)) continue;
+            rest.push_back(v);
+        }
+        if (!rec.run(rest, levels) || (int)interior.size() != parts) return false;
     }
     for (int p = 0; p < parts; ++p) {
         if (interior[p].empty()) return false;

@@ -1120,7 +1120,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         // cooperative mapping (device/coop.cuh): an explicit request is refused where it does not apply, never silently replaced
         const Plan& cpl = b->plan->p;
         if (o.coop_parts != 2 && o.coop_parts != 4 && o.coop_parts != 8) return fail(ctx, TSB_E_INVALID, "coop_parts must be -1, 0, 2, 4 or 8");
-        if (cpl.has_nonlinear || cpl.has_mutual) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: circuits with nonlinear devices or mutual couplings run thread-per-circuit");
+        if (cpl.has_bjt || cpl.has_mutual) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: circuits with BJTs or mutual couplings run thread-per-circuit");
         if (!cpl.coop.count(o.coop_parts)) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the netlist has no partition into that many sub-circuits (tsb_plan_coop_info)");
         if (o.strict_fp) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the nested-dissection order is a re-association, not available in the strict build");
         if (out_flags & TSB_OUT_GRID) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: TSB_OUT_GRID is not available on the cooperative mapping");
