@@ -95,10 +95,10 @@ HARNESS = r'''
 #define __ldcs(p) (*(p))
 struct double2 { double x, y; };
 #include "MODELS"
-struct TsbArgs { long long n_inst; const double* pv[64]; const double* U; double Uc[32]; };
+struct TsbArgs { long long n_inst; const double* pv[128]; const double* U; double Uc[32]; };
 STRUCT
 int main(int argc, char** argv) {
-    double U[NPAR + 1], V[64][1];
+    double U[NPAR + 1], V[128][1];
     TsbArgs a; a.n_inst = 1; a.U = U;
     const double nominal[] = {NOMINAL};
     for (int k = 0; k < NPAR; ++k) { U[k] = nominal[k]; if (k < 32) a.Uc[k] = U[k]; }

@@ -29,7 +29,7 @@ HARNESS = r'''
 #define __ldcs(p) (*(p))
 struct double2 { double x, y; };
 #include "MODELS"
-struct TsbArgs { long long n_inst; const double* pv[64]; const double* U; double Uc[32]; };
+struct TsbArgs { long long n_inst; const double* pv[128]; const double* U; double Uc[32]; };
 STRUCT
 int main(int argc, char** argv) {
     const int trials = 200;
@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
     double worst = 0;
     int fails = 0, both_fail = 0;
     for (int t = 0; t < trials; ++t) {
-        double U[NPAR + 1], V[64][1];
+        double U[NPAR + 1], V[128][1];
         TsbArgs a; a.n_inst = 1; a.U = U;
         const double nominal[] = {NOMINAL};
         for (int k = 0; k < NPAR; ++k) { U[k] = nominal[k]; if (k < 32) a.Uc[k] = U[k]; }

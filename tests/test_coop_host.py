@@ -29,7 +29,7 @@ HARNESS = r'''
 #define __ldcs(p) (*(p))
 struct double2 { double x, y; };
 #include "MODELS"
-struct TsbArgs { long long n_inst; const double* pv[64]; const double* U; double Uc[32]; double* coop_state; };
+struct TsbArgs { long long n_inst; const double* pv[128]; const double* U; double Uc[32]; double* coop_state; };
 STRUCTS
 template <class Part> static void run_a(Part& c, const TsbArgs& a, double time, double dt, double* xb, int* flags) {
     c.load(a, 0);
@@ -60,7 +60,7 @@ int main() {
     double worst = 0, worst_state = 0, worst_row = 0;
     int fails = 0, sep_mismatch = 0, flag_mismatch = 0;
     for (int t = 0; t < trials; ++t) {
-        double U[NPAR + 1], V[64][1];
+        double U[NPAR + 1], V[128][1];
         TsbArgs a; a.n_inst = 1; a.U = U;
         const double nominal[] = {NOMINAL};
         for (int k = 0; k < NPAR; ++k) { U[k] = nominal[k]; if (k < 32) a.Uc[k] = U[k]; }

@@ -24,7 +24,7 @@
 #ifndef TSB_SKELETON_CUH
 #define TSB_SKELETON_CUH
 
-#define TSB_MAX_VARYING 64
+#define TSB_MAX_VARYING 128
 #define TSB_UC_MAX 32
 
 struct TsbArgs {

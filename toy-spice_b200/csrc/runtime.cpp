@@ -33,7 +33,7 @@ cudaError_t launch_lu_warp(const double* A, const double* b, double* x, int* sta
 using namespace tsb;
 
 // Mirror of the device-side TsbArgs (device/skeleton.cuh) — keep in sync.
-#define TSB_MAX_VARYING 64
+#define TSB_MAX_VARYING 128
 struct TsbArgsHost {
     long long n_inst;
     const double* pv[TSB_MAX_VARYING];
@@ -555,7 +555,7 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     a.n_inst = b->n_inst;
     a.n_run = b->n_inst;
     a.order = b->d_order;
-    if (b->slot_ptr.size() > TSB_MAX_VARYING) return fail(ctx, TSB_E_UNSUPPORTED, "too many per-instance parameters (max 64)");
+    if (b->slot_ptr.size() > TSB_MAX_VARYING) return fail(ctx, TSB_E_UNSUPPORTED, "too many per-instance parameters (max 128)");
     for (size_t s = 0; s < b->slot_ptr.size(); ++s) a.pv[s] = b->slot_ptr[s];
     size_t ub = b->uniform.size() * sizeof(double);
     if (!b->d_uniform) CU(ctx, cudaMalloc(&b->d_uniform, ub ? ub : 8));
