@@ -597,29 +597,30 @@ def main():
     if not args.no_configs:
         try:
             nl = max(1024, int((1 << 18) * args.config_scale))
-            ltext = W.rc_ladder(24)
-            lckt = T.Circuit.from_netlist(ltext, ctx)
-            lcard = lckt.analysis_card()
-            lov = W.sweep_draws(lckt.devices(), nl, 5 + 7919 * rank)
-            ldev = {k: torch.from_numpy(v).to(dev_name) for k, v in lov.items()}
-            larger_n = {"workload": f"RC ladder, 24 sections (n = 26 unknowns, 51 result columns), {nl} instances per GPU, transient, statistics output",
-                        "mappings": []}
-            for parts, label in ((0, "one thread per circuit"), (2, "cooperative, 2 threads per circuit"), (4, "cooperative, 4 threads per circuit")):
-                lb = lckt.batch(nl)
-                for (d, p), v in ldev.items():
-                    lb.set_param(d, p, v)
-                lo = T.default_opts(strict_fp=0, coop_parts=parts)
-                ms = min(timed_launches(lambda: lb.run_tran(lcard["tstart"], lcard["tstop"], lcard["tstep"], lcard["tmax"], lcard["uic"],
-                                                            out=T.OUT_STATS, opts=lo), reps=2))
-                tot = lb.totals()
-                larger_n["mappings"].append({"mapping": label, "coop_parts": parts, "ms_per_launch": ms, "steps": int(tot[0]),
-                                             "circuit_timesteps_per_sec": int(tot[0]) / (ms * 1e-3), "failed": int((lb.status() != 0).sum())})
-                del lb
-            base = larger_n["mappings"][0]["ms_per_launch"]
-            for e in larger_n["mappings"]:
-                e["speedup_vs_thread_mapping"] = base / e["ms_per_launch"]
-            larger_n["default"] = "coop_parts = -1 picks 2 parts for circuits of >= 16 unknowns without nonlinear devices (fast build)"
-            del ldev
+            larger_n = {"default": "coop_parts = -1 picks 2 parts for circuits of >= 16 unknowns without BJTs / mutual couplings (fast build)", "workloads": []}
+            for title, ltext in (("RC ladder, 24 sections (n = 26 unknowns, 51 result columns)", W.rc_ladder(24)),
+                                 ("diode-clamped RC ladder, 24 sections (n = 26, 14 diodes: Newton loops)", W.diode_rc_ladder(24))):
+                lckt = T.Circuit.from_netlist(ltext, ctx)
+                lcard = lckt.analysis_card()
+                lov = W.sweep_draws(lckt.devices(), nl, 5 + 7919 * rank)
+                ldev = {k: torch.from_numpy(v).to(dev_name) for k, v in lov.items()}
+                ent = {"workload": f"{title}, {nl} instances per GPU, transient, statistics output", "mappings": []}
+                for parts, label in ((0, "one thread per circuit"), (2, "cooperative, 2 threads per circuit"), (4, "cooperative, 4 threads per circuit")):
+                    lb = lckt.batch(nl)
+                    for (d, p), v in ldev.items():
+                        lb.set_param(d, p, v)
+                    lo = T.default_opts(strict_fp=0, coop_parts=parts)
+                    ms = min(timed_launches(lambda: lb.run_tran(lcard["tstart"], lcard["tstop"], lcard["tstep"], lcard["tmax"], lcard["uic"],
+                                                                out=T.OUT_STATS, opts=lo), reps=2))
+                    tot = lb.totals()
+                    ent["mappings"].append({"mapping": label, "coop_parts": parts, "ms_per_launch": ms, "steps": int(tot[0]),
+                                            "circuit_timesteps_per_sec": int(tot[0]) / (ms * 1e-3), "failed": int((lb.status() != 0).sum())})
+                    del lb
+                base = ent["mappings"][0]["ms_per_launch"]
+                for e in ent["mappings"]:
+                    e["speedup_vs_thread_mapping"] = base / e["ms_per_launch"]
+                larger_n["workloads"].append(ent)
+                del ldev
         except Exception as ex:
             larger_n = {"error": repr(ex)[:300]}
 

@@ -122,17 +122,17 @@ typedef struct tsb_opts {
                            beside the main launch) publishes these per attempt, every other instance looks them up and
                            verifies (time, dt) bit for bit, computing them itself on a miss — results are bit-identical
                            with and without; 0: off; -1 (default): on for batches of >= 2^18 instances */
-    int coop_parts;     /* transient analysis of circuits without nonlinear devices, fast build: 2 or 4 = the cooperative mapping —
-                           the netlist is cut into that many sub-circuits joined by a small separator, and one instance is
-                           advanced by that many threads in different warps of a block (each eliminates its own sub-circuit;
-                           a few doubles per step attempt cross shared memory around one named barrier).  For circuits too
-                           large for one thread's registers.  The elimination order is a nested-dissection order: results
-                           differ from the thread-per-circuit mapping by rounding (like the fast build's other
-                           re-associations).  An explicit 2 / 4 fails with TSB_E_UNSUPPORTED when the circuit has no such
-                           partition (tsb_plan_coop_info), has nonlinear devices or mutual couplings, or with strict_fp /
-                           TSB_OUT_GRID.  0: off.  -1 (default): two parts for circuits of >= 16 unknowns where all of the
-                           above holds (measured on B200, RC ladders: n = 18 1.6x, n = 26 2.1x the thread-per-circuit rate),
-                           else off */
+    int coop_parts;     /* transient analysis, fast build: 2, 4 or 8 = the cooperative mapping — the netlist is cut into that many
+                           sub-circuits joined by a small separator, and one instance is advanced by that many threads in
+                           different warps of a block (each eliminates its own sub-circuit; a few doubles per step attempt —
+                           per Newton iteration for circuits with diodes / MOSFETs — cross shared memory around named
+                           barriers).  For circuits too large for one thread's registers.  The elimination order is a
+                           nested-dissection order: results differ from the thread-per-circuit mapping by rounding (like the
+                           fast build's other re-associations).  An explicit value fails with TSB_E_UNSUPPORTED when the
+                           circuit has no such partition (tsb_plan_coop_info), has BJTs (generated dense) or mutual couplings,
+                           or with strict_fp / TSB_OUT_GRID.  0: off.  -1 (default): two parts for circuits of >= 16 unknowns
+                           where all of the above holds (measured on B200: RC ladders n = 18 1.6x, n = 26 2.1x, diode-clamped
+                           ladder n = 26 1.8x the thread-per-circuit rate), else off */
 } tsb_opts;
 
 /* The partition behind tsb_opts.coop_parts (parts = 2 or 4): owner[u] for every unknown u = 1..n (external numbering: nodes,

@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as G  # noqa: E402
 import parity_util as PU  # noqa: E402
-from random_decks import rc_ladder  # noqa: E402
+import random_decks as _RD
+rc_ladder = getattr(_RD, os.environ.get("LADDER_KIND", "rc_ladder"))       # e.g. LADDER_KIND=diode_rc_ladder  # noqa: E402
 
 T = PU.T
 secs = [int(x) for x in sys.argv[1].split(",")]

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 import parity_util as PU
-from random_decks import rc_ladder
+import random_decks as _RD
+rc_ladder = getattr(_RD, os.environ.get("LADDER_KIND", "rc_ladder"))       # e.g. LADDER_KIND=diode_rc_ladder
 
 T = PU.T
 

@@ -68,3 +68,8 @@ def test_live_bench_line(built):
         for e in c["decks"]:
             assert e["ms_per_launch"] > 0 and e["circuit_timesteps_per_sec"] > 0 and 0 < e["frac"] < 1.2 and 0 < e["lane_util"] <= 1.0, e
     assert d["strong"]["scaling"] == "strong" and d["e2e"]["results_check"] is True and "excluded" in d["config"]
+    # the larger-n entry: both ladders on the thread mapping and on the cooperative mapping, nothing failed
+    ln = d["larger_n"]
+    assert "error" not in ln and len(ln["workloads"]) == 2, ln
+    for w in ln["workloads"]:
+        assert [m["coop_parts"] for m in w["mappings"]] == [0, 2, 4] and all(m["failed"] == 0 and m["steps"] > 0 for m in w["mappings"]), w

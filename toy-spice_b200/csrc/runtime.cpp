@@ -1102,10 +1102,11 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
     if (const char* ce = getenv("TSB_COOP")) { if (*ce) o.coop_parts = atoi(ce); }      // development / A-B knob
     if (o.coop_parts < 0) {
         // auto: the cooperative mapping where it measured faster than one thread per circuit (RC ladders on B200: n = 14
-        // 0.86x, n = 18 1.6x, n = 26 2.1x with two parts) and everything it needs holds; otherwise thread-per-circuit
+        // 0.86x, n = 18 1.6x, n = 26 2.1x with two parts; diode-clamped ladders: n = 14 1.1x, n = 26 1.8x) and everything it
+        // needs holds; otherwise thread-per-circuit
         const Plan& cpl = b->plan->p;
         o.coop_parts = 0;
-        if (!cpl.has_nonlinear && !cpl.has_mutual && !o.strict_fp && !(out_flags & TSB_OUT_GRID) && o.skip_linear_resolve && !o.lane_refill) {
+        if (!cpl.has_bjt && !cpl.has_mutual && !o.strict_fp && !(out_flags & TSB_OUT_GRID) && o.skip_linear_resolve && !o.lane_refill) {
             int pick = 0;
             if (cpl.n() >= TSB_COOP_AUTO_MIN_N && cpl.coop.count(2)) pick = 2;
             if (cpl.n() >= TSB_COOP4_AUTO_MIN_N && cpl.coop.count(4)) pick = 4;

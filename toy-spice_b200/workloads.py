@@ -83,3 +83,21 @@ def rc_ladder(sections: int) -> str:
         lines.append(f"C{k} {k + 1} 0 100n")
     lines.append(".tran 0.01ms 3ms")
     return "\n".join(lines) + "\n"
+
+
+def diode_rc_ladder(sections: int) -> str:
+    """The same ladder with a diode clamp to ground at every third node and a reverse one at every fourth (not multiples of
+    three): a larger-n deck with Newton loops."""
+    lines = [f"* diode-clamped RC ladder, {sections} sections", "Vin 1 0 SIN(0 5 1k)"]
+    nd = 0
+    for k in range(1, sections + 1):
+        lines.append(f"R{k} {k} {k + 1} 100")
+        lines.append(f"C{k} {k + 1} 0 100n")
+        if k % 3 == 0:
+            nd += 1
+            lines.append(f"D{nd} {k + 1} 0 D")
+        elif k % 4 == 0:
+            nd += 1
+            lines.append(f"D{nd} 0 {k + 1} D")
+    lines.append(".tran 0.01ms 3ms")
+    return "\n".join(lines) + "\n"
