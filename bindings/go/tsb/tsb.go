@@ -113,6 +113,26 @@ func (p *Plan) Columns(analysis int) []string {
 	return out
 }
 
+// CoopInfo returns the partition behind tsb_opts.coop_parts (the cooperative mapping: one instance advanced by `parts`
+// GPU threads, each eliminating its own sub-circuit): owner[u] for every unknown u = 1..n is the part that eliminates it,
+// -1 = separator (owner[0] is unused); ok = false when the netlist has no partition into that many sub-circuits.  Nothing has
+// to be called for the mapping to be used: the default options pick it for circuits of >= 16 unknowns.
+func (p *Plan) CoopInfo(parts int) (owner []int, nSeparator int, ok bool) {
+	var nn, nb C.int
+	C.tsb_plan_size(p.h, &nn, &nb)
+	n := int(nn) + int(nb)
+	buf := make([]C.int, n+1)
+	var ns C.int
+	if rc := C.tsb_plan_coop_info(p.h, C.int(parts), &buf[0], &ns); rc != C.TSB_OK {
+		return nil, 0, false
+	}
+	owner = make([]int, n+1)
+	for i := range buf {
+		owner[i] = int(buf[i])
+	}
+	return owner, int(ns), true
+}
+
 // ParamRef names one sweepable parameter: device name + index into the device kind's parameter layout (tspice_b200.h).
 type ParamRef struct {
 	Device string

@@ -650,7 +650,6 @@ int autotune_min_blocks(tsb_batch* b, const tsb_opts& o_auto, const std::string&
 // for the 2.4e4 attempts of an inductor deck), hence the instance threshold of the automatic mode.
 const int64_t TSB_TGRID_MIN_INSTANCES = 1 << 18;
 const int TSB_COOP_AUTO_MIN_N = 16;        // tsb_opts.coop_parts = -1: two parts from this many unknowns up
-const int TSB_COOP4_AUTO_MIN_N = 1 << 20;   //                             four parts from this many (no measured win yet)
 const int TSB_TGRID_CAP = 1 << 16;
 
 // The table is a pure function of the analysis arguments, the tolerances that steer the step control, the uniform
@@ -1107,14 +1106,14 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         const Plan& cpl = b->plan->p;
         o.coop_parts = 0;
         if (!cpl.has_bjt && !cpl.has_mutual && !o.strict_fp && !(out_flags & TSB_OUT_GRID) && o.skip_linear_resolve && !o.lane_refill) {
-            int pick = 0;
-            if (cpl.n() >= TSB_COOP_AUTO_MIN_N && cpl.coop.count(2)) pick = 2;
-            if (cpl.n() >= TSB_COOP4_AUTO_MIN_N && cpl.coop.count(4)) pick = 4;
-            if (pick) {
-                int nx = 0, nown = 0;
-                coop_dimensions(cpl, cpl.coop.at(pick), nx, nown);
-                if (((size_t)4 * nown * 32 * pick + (size_t)2 * pick * nx * 32) * sizeof(double) <= 100 * 1024) o.coop_parts = pick;
-            }
+            // two parts where they fit; more parts only when the statistics of fewer do not leave an SM two blocks
+            if (cpl.n() >= TSB_COOP_AUTO_MIN_N)
+                for (int pick : {2, 4, 8}) {
+                    if (!cpl.coop.count(pick)) continue;
+                    int nx = 0, nown = 0;
+                    coop_dimensions(cpl, cpl.coop.at(pick), nx, nown);
+                    if (((size_t)4 * nown * 32 * pick + (size_t)2 * pick * nx * 32) * sizeof(double) <= 110 * 1024) { o.coop_parts = pick; break; }
+                }
         }
     }
     if (o.coop_parts != 0) {
