@@ -20,10 +20,13 @@ def main():
     if deck.startswith("ladder"):
         from random_decks import rc_ladder
         text = rc_ladder(int(deck[6:]))
+    elif deck.startswith("diodeladder"):
+        from random_decks import diode_rc_ladder
+        text = diode_rc_ladder(int(deck[11:]))
     else:
         text = T.BUNDLED[deck]
     ckt = T.Circuit.from_netlist(text, ctx)
-    ov = PU.draws(deck, ckt, n, seed=5 if deck.startswith("ladder") else None)
+    ov = PU.draws(deck, ckt, n, seed=5 if "ladder" in deck else None)
     dev = {k: torch.from_numpy(v).cuda() for k, v in ov.items()}
     torch.cuda.synchronize()
     card = ckt.analysis_card()
