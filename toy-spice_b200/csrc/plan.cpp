@@ -832,7 +832,7 @@ int plan_finalize(Plan& pl) {
         Nominal nom3(pl);
         nom3.derive();
         CoopPlan cp;
-        if (build_coop(pl, nom3, parts, cp)) pl.coop[parts] = cp;
+        if (build_coop(pl, nom3, parts, cp)) { coop_dimensions(pl, cp, cp.nx, cp.nown_max); pl.coop[parts] = cp; }
     }
     pl.finalized = true;
     return TSB_OK;

@@ -1110,8 +1110,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
             if (cpl.n() >= TSB_COOP_AUTO_MIN_N)
                 for (int pick : {2, 4, 8}) {
                     if (!cpl.coop.count(pick)) continue;
-                    int nx = 0, nown = 0;
-                    coop_dimensions(cpl, cpl.coop.at(pick), nx, nown);
+                    const int nx = cpl.coop.at(pick).nx, nown = cpl.coop.at(pick).nown_max;
                     if (((size_t)4 * nown * 32 * pick + (size_t)2 * pick * nx * 32) * sizeof(double) <= 110 * 1024) { o.coop_parts = pick; break; }
                 }
         }
@@ -1160,8 +1159,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         TsbArgsHost a1 = a;
         a1.out_flags = 0;
         if ((rc = launch(b, o, m->optran, a1, false, m->min_blocks)) != TSB_OK) return rc;
-        int nx = 0, nown = 0;
-        coop_dimensions(pl, cp, nx, nown);
+        const int nx = cp.nx, nown = cp.nown_max;
         const int groups = 1, block = 32 * cp.parts * groups;
         const size_t smem = ((size_t)4 * nown * block + (size_t)groups * 2 * cp.parts * nx * 32) * sizeof(double);
         if (smem > 227 * 1024) return fail(ctx, TSB_E_UNSUPPORTED, "coop_parts: the statistics of one block do not fit in shared memory");

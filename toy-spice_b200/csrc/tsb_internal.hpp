@@ -75,6 +75,7 @@ struct CoopPlan {
     std::vector<int> col_owner;      // [transient columns] result column -> part (column 0, TIME: part 0)
     int n_int = 0;                   // steps 1..n_int eliminate interiors (part 0's first, then part 1's, ...), the rest the separator
     LuProgram lu;                    // elimination program of the nested-dissection order over the stamped pattern
+    int nx = 0, nown_max = 0;        // exchange slots per part and attempt, result columns of the widest part (codegen.cpp: coop_dimensions, filled at finalize)
 };
 
 struct Plan {
