@@ -1,5 +1,7 @@
 // coop.cuh — cooperative mapping of the transient analysis: ONE circuit instance is advanced by P threads that sit in P
-// different warps of a block (hand-written, generic; the per-part code comes from codegen.cpp: emit_coop).
+// different warps of a block (hand-written, generic; the per-part code comes from codegen.cpp: emit_coop).  Two drivers:
+// tsb_coop_tran_part (circuits without nonlinear devices: one solve per step attempt, described below) and
+// tsb_coop_tran_nl_part (diodes / MOSFETs: the Newton loop around the same two phases, at the end of this file).
 //
 // Why: the thread-per-circuit mapping (skeleton.cuh) keeps a whole instance in one thread's registers.  Past n ~ 12-14
 // unknowns the state no longer fits (255 registers), the kernels spill, and the per-thread statistics (32 bytes per result
