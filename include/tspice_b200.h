@@ -227,8 +227,11 @@ void tsb_batch_destroy(tsb_batch* batch);
 /* Per-instance parameter values for (dev, param): n_inst doubles, host memory of any kind.  COPY semantics: the values
  * are staged through a library-owned pinned buffer, the caller's buffer is free again when the call returns. */
 int tsb_batch_set_param(tsb_batch* batch, int dev, int param, const double* values);
-/* Zero-copy variant for pinned host buffers: the H2D DMA reads `values` later, on the context's stream.  The buffer must
- * stay valid and unmodified until the next tsb_batch_sync() (or any blocking tsb_result_* read). */
+/* Zero-copy variant for pinned host buffers: the H2D DMA reads `values` later.  The buffer must stay valid and unmodified
+ * until the next tsb_batch_sync() (or a blocking tsb_result_* read of a run launched after this call).
+ * Both variants copy on an upload stream of the context: behind this batch's own last launch and ahead of its next one, but
+ * BESIDE whatever another batch of the context is running — a host that alternates two batches uploads the parameters of
+ * step i + 1 while step i computes. */
 int tsb_batch_set_param_async(tsb_batch* batch, int dev, int param, const double* values);
 /* Same, values already resident in HBM (device pointer, n_inst doubles; borrowed until the batch
  * is destroyed or the parameter is set again). */

@@ -80,6 +80,7 @@ struct tsb_ctx {
     int sms = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;                // tsb_result_fetch_async: device -> host copies beside the next launches
+    cudaStream_t upload_stream = nullptr;              // tsb_batch_set_param*: host -> device copies beside another batch's running launch
     cudaStream_t pilot_stream = nullptr;               // shared time grid: the pilot launch runs beside the main one
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
@@ -135,6 +136,11 @@ struct tsb_batch {
     int tgrid_used = 0;                                // the last transient run had a pilot
     std::string tgrid_sig;                             // what the table on the device was built for (analysis + uniform values)
     cudaEvent_t ev_run = nullptr, ev_fetch = nullptr;  // tsb_result_fetch_async: run finished / copies finished
+    // Parameter uploads run on the context's upload stream: behind this batch's own last launch (ev_launched, recorded on the
+    // launch stream after every launch of this batch) and ahead of its next one (ev_params, waited for in fill_common) — but
+    // beside whatever ANOTHER batch is running, so a host that alternates two batches uploads step i + 1 during step i.
+    cudaEvent_t ev_launched = nullptr, ev_params = nullptr;
+    bool params_pending = false;
     bool fetch_pending = false;
     double* d_partial = nullptr;                       // tsb_result_summary: per-block partial results
     std::map<void*, size_t> guarded;                   // TSB_GUARD: user pointer -> payload bytes of every guarded buffer
@@ -513,6 +519,14 @@ int alloc_results(tsb_batch* b, int analysis, int out_flags, int64_t cap_rows, i
     return TSB_OK;
 }
 
+// Marks "everything of this batch queued on the launch stream so far": the next parameter upload waits for it.
+int note_launched(tsb_batch* b) {
+    tsb_ctx* ctx = b->ctx;
+    if (!b->ev_launched) CU(ctx, cudaEventCreateWithFlags(&b->ev_launched, cudaEventDisableTiming));
+    CU(ctx, cudaEventRecord(b->ev_launched, ctx->stream));
+    return TSB_OK;
+}
+
 int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& args, bool persistent = false, int min_blocks = 0) {
     tsb_ctx* ctx = b->ctx;
     int block = o.block_size > 0 ? o.block_size : 128;
@@ -542,7 +556,7 @@ int launch(tsb_batch* b, const tsb_opts& o, cudaKernel_t kernel, TsbArgsHost& ar
     void* kargs[] = {&args};
     CU(ctx, cudaLaunchKernel((const void*)kernel, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
     ++ctx->launches;
-    return TSB_OK;
+    return note_launched(b);
 }
 
 int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
@@ -550,6 +564,10 @@ int fill_common(tsb_batch* b, const tsb_opts& o, TsbArgsHost& a) {
     if (b->fetch_pending) {            // results of the previous run are still being copied out: the next run overwrites them
         CU(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_fetch, 0));
         b->fetch_pending = false;
+    }
+    if (b->params_pending) {           // parameter uploads of tsb_batch_set_param* are on the upload stream
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_params, 0));
+        b->params_pending = false;
     }
     memset(&a, 0, sizeof a);
     a.n_inst = b->n_inst;
@@ -762,6 +780,7 @@ static void ctx_release(tsb_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->pilot_stream) cudaStreamDestroy(ctx->pilot_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -979,6 +998,8 @@ void tsb_batch_destroy(tsb_batch* b) {
         cudaFree(b->d_tgrid); cudaFree(b->d_tgrid_pub); cudaFree(b->d_partial);
         if (b->ev_fetch) { cudaEventSynchronize(b->ev_fetch); cudaEventDestroy(b->ev_fetch); }
         if (b->ev_run) cudaEventDestroy(b->ev_run);
+        if (b->ev_params) { cudaEventSynchronize(b->ev_params); cudaEventDestroy(b->ev_params); }
+        if (b->ev_launched) cudaEventDestroy(b->ev_launched);
         free_results(b);
     }
     plan_release(b->plan);
@@ -1033,8 +1054,24 @@ static int set_param_host(tsb_batch* b, int dev, int param, const double* values
         memcpy(b->slot_stage[slot], values, bytes);
         src = b->slot_stage[slot];
     }
-    CU(ctx, cudaMemcpyAsync(b->slot_ptr[slot], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (staged) CU(ctx, cudaEventRecord(b->slot_staged[slot], ctx->stream));
+    // On the upload stream (see tsb_batch.ev_launched) unless the launch stream is being captured into a graph, where the
+    // copy has to be a node of that graph.
+    cudaStream_t up = ctx->stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    const bool beside = cap == cudaStreamCaptureStatusNone;
+    if (beside) {
+        if (!ctx->upload_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        up = ctx->upload_stream;
+        if (b->ev_launched) CU(ctx, cudaStreamWaitEvent(up, b->ev_launched, 0));     // this batch's last launch has read the old values
+    }
+    CU(ctx, cudaMemcpyAsync(b->slot_ptr[slot], src, bytes, cudaMemcpyHostToDevice, up));
+    if (staged) CU(ctx, cudaEventRecord(b->slot_staged[slot], up));
+    if (beside) {
+        if (!b->ev_params) CU(ctx, cudaEventCreateWithFlags(&b->ev_params, cudaEventDisableTiming));
+        CU(ctx, cudaEventRecord(b->ev_params, up));
+        b->params_pending = true;
+    }
     return TSB_OK;
 }
 int tsb_batch_set_param(tsb_batch* b, int dev, int param, const double* values) { return set_param_host(b, dev, param, values, true); }
@@ -1170,7 +1207,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         void* kargs[] = {&a};
         CU(ctx, cudaLaunchKernel((const void*)m->coop, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
         ++ctx->launches;
-        return TSB_OK;
+        return note_launched(b);
     }
     const bool tg_possible = !pl.has_nonlinear && o.skip_linear_resolve != 0 && o.share_time_grid != 0 && !persistent;
     if (tg_possible && (o.share_time_grid > 0 || b->n_inst >= TSB_TGRID_MIN_INSTANCES)) {
@@ -1181,6 +1218,7 @@ int tsb_run_tran(tsb_batch* b, double tstart, double tstop, double tstep, double
         // join: whatever follows on the context's stream (result reads, the next run) also follows the pilot
         CU(ctx, cudaEventRecord(ctx->ev_join, ctx->pilot_stream));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        if ((rc = note_launched(b)) != TSB_OK) return rc;      // the pilot reads the parameters too
     }
     return rc;
 }
@@ -1319,7 +1357,7 @@ int tsb_batch_stamp_dev(tsb_batch* b, int mode, double time, double dt, double g
     void* kargs[] = {&a};
     CU(ctx, cudaLaunchKernel((const void*)kern, dim3((unsigned)blocks), dim3((unsigned)block), kargs, smem, ctx->stream));
     ++ctx->launches;
-    return TSB_OK;
+    return note_launched(b);
 }
 
 // Processing order.  Instances are independent, so WHICH lane works on which instance is free; what is not free is
@@ -1349,6 +1387,7 @@ int tsb_batch_sync(tsb_batch* b) {
     CU(b->ctx, cudaSetDevice(b->ctx->device));
     CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
     if (b->ev_fetch) CU(b->ctx, cudaEventSynchronize(b->ev_fetch));
+    if (b->ev_params) CU(b->ctx, cudaEventSynchronize(b->ev_params));      // zero-copy uploads: the caller's buffers are free again
     return guard_check(b);
 }
 
