@@ -315,12 +315,13 @@ def main():
     d2h_bytes = sum(n * (4 * d["ncol"] * 8 + 8 + 4) for d in decks)
 
     def step_e2e(i):
-        """Host buffers in, host buffers out: parameters H2D from pinned memory (DMA on the launch stream), launch, and
-        the read-back of every instance's statistics / rows / status queued behind the launch on the copy stream."""
+        """Host buffers in, host buffers out: parameters H2D from pinned memory (DMA on the context's upload stream: beside the
+        other batch's running launch), launch, and the read-back of every instance's statistics / rows / status queued behind
+        the launch on the copy stream."""
         for d in decks:
             e = d["e2e"][i & 1]
             b = e["batch"]
-            b.sync()                                   # the buffers of step i - 2 are complete (results consumed by the host here)
+            b.sync()                                   # THIS batch's step i - 2 and its read-back are complete (results consumed by the host here)
             for (dv, p), v in d["host"].items():
                 b.set_param(dv, p, v.numpy(), zero_copy=True)
             launch_deck(d, b)
@@ -642,7 +643,7 @@ def main():
             "newton_solves_per_sec": solves_job * args.steps / t_job if t_job > 0 else 0.0,
             "executed_solves_per_step": exec_job,
             "e2e": {"value": e2e_value, "unit": "circuit-timesteps/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
-                    "pipelined": "read-back of step i overlaps step i+1 (two batches per deck, tsb_result_fetch_async)", "results_check": bool(e2e_ok)},
+                    "pipelined": "two batches per deck: the read-back of step i (tsb_result_fetch_async) and the parameter upload of step i+1 overlap the launches", "results_check": bool(e2e_ok)},
             "gpu_launches": int(launches), "failed_instances": bad_status,
             "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp,
             "configs": configs, "strong": strong, "larger_n": larger_n, "cpu_baseline": cpu,

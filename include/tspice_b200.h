@@ -276,7 +276,8 @@ int tsb_run_dc2(tsb_batch* batch, int src1_dev, double start1, double stop1, dou
  * Bjt.Stamp never dispatches to StampAC (bjt.go:315-374), and the small-signal values of diodes and MOSFETs come from that
  * scrambled point: a result that depends on the vector layout of a module whose source is not available. */
 int tsb_run_ac(tsb_batch* batch, int sweep_type, int n_points, double fstart, double fstop, int out_flags, const tsb_opts* opts);
-/* Block until the last run has finished (runs are asynchronous on the context's stream). */
+/* Block until the last run OF THIS BATCH has finished, its asynchronous read-back (tsb_result_fetch_async) and its parameter
+ * uploads included (runs are asynchronous on the context's stream; another batch's run queued behind it is not waited for). */
 int tsb_batch_sync(tsb_batch* batch);
 
 /* ---- results of the last run -----------------------------------------------------------------

@@ -1385,7 +1385,10 @@ int tsb_batch_set_order(tsb_batch* b, const int64_t* perm) {
 int tsb_batch_sync(tsb_batch* b) {
     int rc = check_batch(b); if (rc != TSB_OK) return rc;
     CU(b->ctx, cudaSetDevice(b->ctx->device));
-    CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    // THIS batch's last launch (ev_launched is recorded on the launch stream after every launch of the batch), not the whole
+    // stream: a host that alternates two batches must not wait here for the other batch's run that is computing right now
+    if (b->ev_launched && !b->ctx->guard) CU(b->ctx, cudaEventSynchronize(b->ev_launched));
+    else CU(b->ctx, cudaStreamSynchronize(b->ctx->stream));
     if (b->ev_fetch) CU(b->ctx, cudaEventSynchronize(b->ev_fetch));
     if (b->ev_params) CU(b->ctx, cudaEventSynchronize(b->ev_params));      // zero-copy uploads: the caller's buffers are free again
     return guard_check(b);
