@@ -92,6 +92,45 @@ def test_fast_build_within_tolerance_and_zero_pivot_is_data(ctx, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["1,0,0", "1,0,1", "2,0,0", "2,0,1", "3,0,0", "3,0,1", "4,0,1"])
+def test_every_mapping_variant_gives_the_same_answers(ctx, variant, monkeypatch):
+    """$TSB_LU_VARIANT = "rows per lane, shared-memory broadcast, asynchronous staging" forces a mapping other than the
+    measured default (csrc/lu_warp.cu: launch_lu_warp): the strict build stays bit-identical to Sparse 1.3 whatever the
+    mapping, the fast build stays within the backward error of the oracle's own solution."""
+    monkeypatch.setenv("TSB_LU_VARIANT", variant)
+    for n in (3, 8, 11, 16, 23, 32):
+        n_inst = 261
+        base, A, b = mna_like(n, n_inst, 13 * n + 1)
+        order = T.lu_order(base)
+        xo, sto, _ = O.lu_batch(base, A, b)
+        x, st = ctx.lu_solve_batched(A, b, order, strict=True)
+        assert np.array_equal(st, sto) and np.array_equal(x, xo), (variant, n, float(np.max(np.abs(x - xo))))
+        xf, stf = ctx.lu_solve_batched(A, b, order, strict=False)
+        assert np.array_equal(stf, sto)
+        den = np.abs(A).sum(axis=2).max(axis=1) * np.abs(xf).max(axis=1) + np.abs(b).max(axis=1)
+        berr = (np.abs(np.einsum("qij,qj->qi", A, xf) - b).max(axis=1) / den).max()
+        berr_o = (np.abs(np.einsum("qij,qj->qi", A, xo) - b).max(axis=1) / den).max()
+        assert berr <= 8 * berr_o + 1e-15, (variant, n, float(berr), float(berr_o))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,strict", [(8, False), (12, False), (12, True), (32, False)])
+def test_every_pass_of_the_grid_stride_loop_computes_alike(ctx, n, strict):
+    """More systems than one pass of the resident grid holds (the next system of a lane group is copied into the staging
+    tile while the current one is eliminated): copies of the same system give the same bits in every pass, the last,
+    ragged one included."""
+    reps, m = (300 if n <= 16 else 90), 509        # a pass holds 2 368 blocks x 32 systems (4 lanes each) or x 8 (16 lanes)
+    base, A, b = mna_like(n, m, 3 * n)
+    order = T.lu_order(base)
+    x, st = ctx.lu_solve_batched(np.tile(A, (reps, 1, 1))[: reps * m - 7], np.tile(b, (reps, 1))[: reps * m - 7], order, strict=strict)
+    assert np.all(st == 0)
+    x0 = x[:m]
+    for r in range(1, reps):
+        seg = x[r * m:(r + 1) * m]
+        assert np.array_equal(seg, x0[: len(seg)]), (r, n)
+
+
+@pytest.mark.gpu
 def test_device_pointer_entry_and_permutation_equivariance(ctx):
     import torch
     n, n_inst = 16, 1 << 16

@@ -1560,13 +1560,10 @@ int tsb_lu_solve_batched_dev(tsb_ctx* ctx, int n, const int* pivot_row, const in
     if (rc != TSB_OK) return rc;
     if (n_inst == 0) return TSB_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    int* d_perm = nullptr;
-    CU(ctx, cudaMallocAsync(&d_perm, sizeof h, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(d_perm, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    // the pivot order goes to the kernel by value (a kernel parameter): nothing to allocate or copy per call
     cudaError_t e = launch_lu_warp((const double*)(uintptr_t)A_dev, (const double*)(uintptr_t)b_dev, (double*)(uintptr_t)x_dev,
-                                   (int*)(uintptr_t)status_dev, n_inst, n, d_perm, d_perm + 32, strict_fp != 0, ctx->sms, ctx->stream);
+                                   (int*)(uintptr_t)status_dev, n_inst, n, h, h + 32, strict_fp != 0, ctx->sms, ctx->stream);
     ++ctx->launches;
-    cudaFreeAsync(d_perm, ctx->stream);
     CU(ctx, e);
     return TSB_OK;
 }
