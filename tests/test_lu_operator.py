@@ -49,6 +49,23 @@ def test_order_rejects_singular_and_oversize(built):
         T.lu_order(np.eye(33))
 
 
+def test_every_built_mapping_keeps_the_matrix_in_registers(built):
+    """The rows a lane owns are C arrays indexed by the (compile-time) elimination step; if the optimiser loses that, the
+    whole matrix goes to local memory (R x N x 8 bytes of stack: it happened to the 3- and 4-row mappings under
+    `#pragma unroll`, hence static_for).  Checked on the kernels in the built library: a few spilled registers at most."""
+    import os
+    import re
+    import subprocess
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "toy-spice_b200", "libtspice_b200.so")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    found = re.findall(r"tsb_k_lu_warpILi(\d+)ELi(\d+)ELb([01])ELb([01])ELb([01])\S*:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(found) >= 18, len(found)              # 9 lane x row mappings x {strict, fast} at least
+    for w, r, strict, bcast, asyn, reg, stack in found:
+        matrix_bytes = int(w) * int(r) * int(r) * 8
+        assert int(stack) <= 160 and int(stack) < max(matrix_bytes, 161), (w, r, strict, bcast, asyn, reg, stack)
+        assert int(reg) <= 170, (w, r, strict, bcast, asyn, reg)     # three 128-thread blocks per SM for the widest mappings
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 3, 5, 8, 10, 16, 21, 32])
 def test_strict_build_is_bit_identical_to_sparse13(ctx, n):
