@@ -49,6 +49,8 @@ def lib():
                               C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_int64, C.POINTER(C.c_double),
                               C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.orc_go_sin.restype = C.c_double
+        L.orc_set_order_sig_buffer.argtypes = [C.c_void_p]
+        L.orc_set_order_sig_buffer.restype = None
         L.orc_go_sin.argtypes = [C.c_double]
         L.orc_format_value_factor.argtypes = [C.c_double, C.c_char_p, C.c_int]
         for fn in ("orc_go_max", "orc_go_min", "orc_go_pow"):
@@ -103,7 +105,7 @@ class OracleCircuit:
         return dict(rc=rc, ext2int=list(e2i)[1:], pivot_row=list(pr)[1:], pivot_col=list(pc)[1:])
 
     def run(self, n_inst=1, overrides=None, analysis=None, tran=None, dc=None, threads=1, cap_rows=None,
-            want_wave=True, want_stats=False, dc2=None, ac=None, ac_refread=False):
+            want_wave=True, want_stats=False, dc2=None, ac=None, ac_refread=False, want_order_sig=False):
         """overrides: {(device_name_or_index, param_index): array[n_inst]}.
         Returns dict(wave [n_inst, cap, ncol], n_rows, status, counters, stats, signals)."""
         nl = self.netlist
@@ -151,15 +153,20 @@ class OracleCircuit:
         status = np.zeros(n_inst, dtype=np.int32)
         counters = np.zeros((n_inst, 6), dtype=np.int64)
         dp = C.POINTER(C.c_double)
+        order_sig = np.zeros(n_inst, dtype=np.uint64) if want_order_sig else None
+        if want_order_sig:       # per instance: signature of the pivot choices the reference makes on ITS values (sparse13.hpp)
+            lib().orc_set_order_sig_buffer(order_sig.ctypes.data_as(C.c_void_p))
         rc = lib().orc_run(self.h, C.byref(job), n_inst, len(keys), _arr(C.c_int, ov_dev), _arr(C.c_int, ov_par),
                            vals.ctypes.data_as(dp), threads, cap_rows,
                            wave.ctypes.data_as(dp) if wave is not None else None,
                            n_rows.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(C.POINTER(C.c_int32)),
                            counters.ctypes.data_as(C.POINTER(C.c_int64)),
                            stats.ctypes.data_as(dp) if stats is not None else None)
+        if want_order_sig:
+            lib().orc_set_order_sig_buffer(None)
         if rc != 0:
             raise RuntimeError(f"orc_run failed rc={rc}")
-        return dict(wave=wave, n_rows=n_rows, status=status, counters=counters, stats=stats,
+        return dict(wave=wave, n_rows=n_rows, status=status, counters=counters, stats=stats, order_sig=order_sig,
                     signals=(["SWEEP1", "SWEEP2"] + self.signals(an)[1:]) if nested else self.signals(an), ncol=ncol)
 
 

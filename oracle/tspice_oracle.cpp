@@ -174,6 +174,11 @@ int orc_structure(void* h, int* ext2int, int* pivot_row, int* pivot_col) {
 //   status   [n_inst]                                   counters [n_inst][6]: accepted, rejected,
 //            tran_solves, op_solves, op_path, (double bits of) fail time/value
 //   stats    [n_inst][4][ncol]: min, max, sum, last over stored rows (may be NULL)
+// Optional: where orc_run leaves, per instance, the signature of every pivot choice of every matrix of that instance
+// (sparse13.hpp: sp13_order_sig).  Set before orc_run, reset to NULL after; not thread-safe across concurrent orc_run calls.
+static uint64_t* g_order_sig = nullptr;
+void orc_set_order_sig_buffer(uint64_t* buf) { g_order_sig = buf; }
+
 int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov_dev, const int* ov_par,
             const double* ov_vals, int n_threads, int64_t cap_rows, double* wave, int64_t* n_rows,
             int32_t* status, int64_t* counters, double* stats) {
@@ -191,6 +196,7 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
             int64_t i = next.fetch_add(1);
             if (i >= n_inst) break;
             for (int k = 0; k < n_ov; ++k) devs[ov_dev[k]].p[ov_par[k]] = ov_vals[(int64_t)k * n_inst + i];
+            sp13_order_sig_reset();
             std::unique_ptr<Circuit> c = build(*t, devs);
             if (!c) { bad = 1; break; }
             ResultStore rs; rs.nsig = ncol;
@@ -232,6 +238,7 @@ int orc_run(void* h, const orc_job* job, int64_t n_inst, int n_ov, const int* ov
                 } else st = dc.Execute(rs);
                 cnt.op_solves = c->Matrix->n_solves; fail_at = dc.fail_val;
             }
+            if (g_order_sig) g_order_sig[i] = sp13_order_sig;
             if (status) status[i] = st;
             if (n_rows) n_rows[i] = rs.n_rows;
             if (counters) {
