@@ -3,9 +3,8 @@ skeleton.cuh + the generated `struct Ckt` + the `__global__` entries, exactly th
 (`Batch.kernel_source`) — compiled for the HOST with g++ behind a shim of the CUDA built-ins and run one "thread" at a time
 (a warp of one lane: every vote is the lane's own predicate; shared memory is a static array; threadIdx / blockIdx are
 set per instance).  With `strict_fp = 1` and `-ffp-contract=off` this is the arithmetic of the strict GPU build, so whole
-analyses (operating point incl. its Gmin / source-stepping fallbacks, transient) can be held against the oracle on a
-machine without a GPU: row counts, status, counters and values.  (DC sweeps: the swept parameter is a specialisation
-the source accessor does not expose; their Newton and device code is the operating point's.)
+analyses (operating point incl. its Gmin / source-stepping fallbacks, transient, single and nested DC sweeps) can be held
+against the oracle on a machine without a GPU: row counts, status, counters and values.
 
 What it does NOT cover: anything that is a property of the parallel execution (warp votes across different lanes, lane
 refill, the shared time grid, the cooperative mapping) and the fast build's device-only arithmetic (`__CUDA_ARCH__`
@@ -155,10 +154,12 @@ def _flat_parameters(ckt):
     return nominal, index
 
 
-def build(text, overrides, tmpdir, strict=True, analysis_kind=None):
-    """g++-compile the kernel source of this netlist / set of per-instance parameters; returns (exe, info)."""
+def build(text, overrides, tmpdir, strict=True, dc_src=-1, dc_src2=-1):
+    """g++-compile the kernel source of this netlist / set of per-instance parameters [/ swept source(s)]; returns (exe, info)."""
     ckt = T.Circuit.from_netlist(text)
     b = ckt.batch(2)
+    if dc_src != -1:
+        b.kernel_variant(dc_src, dc_src2)               # the DC kernels are specialised on the swept parameter(s)
     for (dev, par), vals in overrides.items():
         b.set_param(dev, par, np.resize(np.asarray(vals, dtype=np.float64), 2))      # (which parameters vary is what specialises the source)
     opts = T.default_opts(strict_fp=1 if strict else 0, min_blocks=1, block_size=32, share_time_grid=0, coop_parts=0)
@@ -181,9 +182,31 @@ def build(text, overrides, tmpdir, strict=True, analysis_kind=None):
     return exe, info
 
 
-def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, strict=True, cap_rows=None):
-    """Whole analysis of `n` instances on the host-compiled device source.  Returns (circuit, HostBatch, column names)."""
-    exe, info = build(text, overrides, tmpdir, strict)
+def _sweep_points(start, stop, inc):
+    """dc.go:36-42 as tsb_run_dc restates it: for v := start; v <= stop; v += inc."""
+    out, v = [], float(start)
+    while v <= stop:
+        out.append(v)
+        v += inc
+    return out
+
+
+def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None, strict=True, cap_rows=None):
+    """Whole analysis of `n` instances on the host-compiled device source.  dc = (source, start, stop, inc) overrides the
+    deck's .dc card; dc2 = ((outer ...), (inner ...)) runs the nested sweep.  Returns (circuit, HostBatch, column names)."""
+    probe = T.Circuit.from_netlist(text)
+    pcard = probe.analysis_card()
+    pkind = pcard["analysis"] if analysis is None else analysis
+    dc_src = dc_src2 = -1
+    if pkind == T.AN_DC:
+        if dc2 is not None:
+            dc_src, dc_src2 = dc2[0][0], dc2[1][0]
+        elif dc is not None:
+            dc_src = dc[0]
+        else:
+            dc_src = probe.devices()[pcard["dc_src_dev"]]["name"]
+            dc = (dc_src, pcard["dc_start"], pcard["dc_stop"], pcard["dc_inc"])
+    exe, info = build(text, overrides, tmpdir, strict, dc_src, dc_src2)
     ckt, opts = info["ckt"], info["opts"]
     card = ckt.analysis_card()
     if tran:
@@ -204,6 +227,7 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, strict=Tr
         pv.append(np.ascontiguousarray(vals, dtype=np.float64)[:n])
     tstart = tstop = tstep = tmax = minstep = 0.0
     sweep = np.zeros(0)
+    sweep2 = None
     kernel = 0
     if kind == T.AN_OP:
         ncol, rows_cap, an = len(ckt.columns(T.AN_OP)), 1, 0
@@ -217,12 +241,21 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, strict=Tr
         ncol, an = len(ckt.columns(T.AN_TRAN)), 1
         rows_cap = cap_rows or 65536
     else:
-        raise NotImplementedError("host emulation: OP and transient only")
+        kernel, an = 1, 3
+        if dc2 is not None:                             # tsb_run_dc2: the nested loops flattened into one list of points
+            s1, s2 = _sweep_points(*dc2[0][1:]), _sweep_points(*dc2[1][1:])
+            sweep = np.array([v1 for v1 in s1 for _ in s2], dtype=np.float64)
+            sweep2 = np.array([v2 for _ in s1 for v2 in s2], dtype=np.float64)
+            ncol = len(ckt.columns(T.AN_DC)) + 1
+        else:
+            sweep = np.array(_sweep_points(*dc[1:]), dtype=np.float64)
+            ncol = len(ckt.columns(T.AN_DC))
+        rows_cap = len(sweep)
     hdr = np.zeros(16, dtype=np.int64)
     hdr[:10] = [n, len(pv), len(nominal), an, int(card.get("uic", False)), opts.max_iter, T.OUT_WAVE | T.OUT_STATS, rows_cap, len(sweep), kernel]
     dbl = np.array([tstart, tstop, tstep, tmax, minstep, opts.abstol, opts.reltol, opts.trtol], dtype=np.float64)
     blob = hdr.tobytes() + dbl.tobytes() + np.asarray(nominal, dtype=np.float64).tobytes() + b"".join(v.tobytes() for v in pv) \
-        + sweep.tobytes() + sweep.tobytes()
+        + sweep.tobytes() + (sweep if sweep2 is None else sweep2).tobytes()
     fin, fout = os.path.join(tmpdir, "in.bin"), os.path.join(tmpdir, "out.bin")
     with open(fin, "wb") as f:
         f.write(blob)
@@ -236,4 +269,4 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, strict=Tr
     rows = np.frombuffer(raw, dtype=np.int64, count=nn, offset=off); off += rows.nbytes
     counters = np.frombuffer(raw, dtype=np.int64, count=8 * nn, offset=off).reshape(8, nn); off += counters.nbytes
     status = np.frombuffer(raw, dtype=np.int32, count=nn, offset=off)
-    return ckt, HostBatch(nn, ncol, wave, stats, rows, counters, status), ckt.columns(kind)
+    return ckt, HostBatch(nn, ncol, wave, stats, rows, counters, status), ckt.columns(kind if kind != T.AN_DC else T.AN_DC)

@@ -25,6 +25,31 @@ def test_device_gomath_program_compiles_for_sm100a(tmp_path):
     _build(tmp_path)
 
 
+def test_fractional_pow_follows_go_on_the_host(tmp_path):
+    """math.Pow with a fractional exponent other than +-0.5 (MOSFET Level 2 / 3 mobility degradation, junction capacitances
+    with MJ != 0.5): Go computes Exp(yf * Log(x)) times the integer power (pow.go), not the correctly rounded power of
+    libm.  tsb_go_pow, compiled for the host as the symbolic pass and tests/host_emul.py compile it, reproduces the oracle's
+    restatement bit for bit; on the device the same operations run on CUDA's exp / log (each within 1 ulp of glibc's)."""
+    src = tmp_path / "p.cpp"
+    src.write_text('''#include <cstdio>
+#include <cmath>
+#include "%s"
+int main() { double x, y; while (scanf("%%la %%la", &x, &y) == 2) printf("%%a\\n", tsb_go_pow(x, y)); return 0; }
+''' % os.path.join(ROOT, "toy-spice_b200", "csrc", "device", "models.cuh"))
+    exe = str(tmp_path / "p")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-w", "-o", exe, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rng = np.random.default_rng(23)
+    cases = [(float(x), float(y)) for x in np.concatenate([rng.uniform(0.01, 40.0, 300), 10.0 ** rng.uniform(-8, 8, 100)])
+             for y in (0.33, -0.33, 0.25, 0.75, -0.75, 1.5, -1.5, 2.4, 0.1, 3.9, -7.2)]
+    out = subprocess.run([exe], input="".join(f"{x.hex()} {y.hex()}\n" for x, y in cases), capture_output=True, text=True).stdout.split()
+    L = PU.O.lib()
+    assert len(out) == len(cases)
+    for (x, y), g in zip(cases, out):
+        assert float.fromhex(g) == L.orc_go_pow(x, y), (x, y, float.fromhex(g), L.orc_go_pow(x, y))
+        assert abs(float.fromhex(g) - x ** y) <= 4e-15 * x ** y            # and it IS a power: (|yf ln x| + 2) ulp from the exact one
+
+
 @pytest.mark.gpu
 def test_device_gomath_matches_the_oracle_bit_for_bit(tmp_path):
     exe = _build(tmp_path)
