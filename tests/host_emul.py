@@ -80,14 +80,14 @@ int main(int argc, char** argv) {
     std::vector<char> in = slurp(argv[1]);
     const long long* h = (const long long*)in.data();
     const long long n = h[0], nvar = h[1], npar = h[2], analysis = h[3], uic = h[4], max_iter = h[5], out_flags = h[6],
-                    cap_rows = h[7], n_sweep = h[8], kernel = h[9];
+                    cap_rows = h[7], n_sweep = h[8], kernel = h[9], n_grid = h[10];
     const double* d = (const double*)(h + 16);
     TsbArgs a; memset(&a, 0, sizeof a);
     a.n_inst = n; a.n_run = n; a.analysis = (int)analysis; a.uic = (int)uic; a.max_iter = (int)max_iter;
     a.tstart = d[0]; a.tstop = d[1]; a.tstep = d[2]; a.maxstep = d[3]; a.minstep = d[4];
-    a.abstol = d[5]; a.reltol = d[6]; a.trtol = d[7];
+    a.abstol = d[5]; a.reltol = d[6]; a.trtol = d[7]; a.grid_dt = d[8]; a.n_grid = (int)n_grid;
     a.out_flags = (int)out_flags; a.cap_rows = cap_rows; a.skip_linear_resolve = TSB_SKIP_LINEAR_RESOLVE;
-    const double* p = d + 8;
+    const double* p = d + 9;
     a.U = p; for (long long k = 0; k < npar && k < TSB_UC_MAX; ++k) a.Uc[k] = p[k];
     p += npar;
     for (long long s = 0; s < nvar; ++s) { a.pv[s] = p; p += n; }
@@ -154,15 +154,17 @@ def _flat_parameters(ckt):
     return nominal, index
 
 
-def build(text, overrides, tmpdir, strict=True, dc_src=-1, dc_src2=-1):
+def build(text, overrides, tmpdir, strict=True, dc_src=-1, dc_src2=-1, opts_kw=None, grid=False):
     """g++-compile the kernel source of this netlist / set of per-instance parameters [/ swept source(s)]; returns (exe, info)."""
     ckt = T.Circuit.from_netlist(text)
     b = ckt.batch(2)
     if dc_src != -1:
         b.kernel_variant(dc_src, dc_src2)               # the DC kernels are specialised on the swept parameter(s)
+    elif grid:
+        b.kernel_variant(grid=True)                     # TSB_OUT_GRID is a specialisation too
     for (dev, par), vals in overrides.items():
         b.set_param(dev, par, np.resize(np.asarray(vals, dtype=np.float64), 2))      # (which parameters vary is what specialises the source)
-    opts = T.default_opts(strict_fp=1 if strict else 0, min_blocks=1, block_size=32, share_time_grid=0, coop_parts=0)
+    opts = T.default_opts(**{**dict(strict_fp=1 if strict else 0, min_blocks=1, block_size=32, share_time_grid=0, coop_parts=0), **(opts_kw or {})})
     src = b.kernel_source(opts)
     key = (src, strict, tmpdir)
     info = dict(ckt=ckt, opts=opts,
@@ -191,7 +193,7 @@ def _sweep_points(start, stop, inc):
     return out
 
 
-def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None, strict=True, cap_rows=None):
+def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None, strict=True, cap_rows=None, opts_kw=None, grid_dt=None):
     """Whole analysis of `n` instances on the host-compiled device source.  dc = (source, start, stop, inc) overrides the
     deck's .dc card; dc2 = ((outer ...), (inner ...)) runs the nested sweep.  Returns (circuit, HostBatch, column names)."""
     probe = T.Circuit.from_netlist(text)
@@ -206,7 +208,7 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
         else:
             dc_src = probe.devices()[pcard["dc_src_dev"]]["name"]
             dc = (dc_src, pcard["dc_start"], pcard["dc_stop"], pcard["dc_inc"])
-    exe, info = build(text, overrides, tmpdir, strict, dc_src, dc_src2)
+    exe, info = build(text, overrides, tmpdir, strict, dc_src, dc_src2, opts_kw, grid=grid_dt is not None)
     ckt, opts = info["ckt"], info["opts"]
     card = ckt.analysis_card()
     if tran:
@@ -229,6 +231,7 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
     sweep = np.zeros(0)
     sweep2 = None
     kernel = 0
+    n_grid, gdt, out_flags = 0, 0.0, T.OUT_WAVE | T.OUT_STATS
     if kind == T.AN_OP:
         ncol, rows_cap, an = len(ckt.columns(T.AN_OP)), 1, 0
     elif kind == T.AN_TRAN:
@@ -240,6 +243,10 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
             tmax = tstep
         ncol, an = len(ckt.columns(T.AN_TRAN)), 1
         rows_cap = cap_rows or 65536
+        if grid_dt is not None:                        # tsb_run_tran: TSB_OUT_GRID (statistics carry the previous stored row)
+            gdt = grid_dt if grid_dt > 0 else tstep
+            n_grid = max(1, int(np.floor((tstop - tstart) / gdt * (1.0 + 1e-12) + 1e-9)))
+            rows_cap, out_flags = n_grid, T.OUT_GRID | T.OUT_STATS
     else:
         kernel, an = 1, 3
         if dc2 is not None:                             # tsb_run_dc2: the nested loops flattened into one list of points
@@ -252,8 +259,8 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
             ncol = len(ckt.columns(T.AN_DC))
         rows_cap = len(sweep)
     hdr = np.zeros(16, dtype=np.int64)
-    hdr[:10] = [n, len(pv), len(nominal), an, int(card.get("uic", False)), opts.max_iter, T.OUT_WAVE | T.OUT_STATS, rows_cap, len(sweep), kernel]
-    dbl = np.array([tstart, tstop, tstep, tmax, minstep, opts.abstol, opts.reltol, opts.trtol], dtype=np.float64)
+    hdr[:11] = [n, len(pv), len(nominal), an, int(card.get("uic", False)), opts.max_iter, out_flags, rows_cap, len(sweep), kernel, n_grid]
+    dbl = np.array([tstart, tstop, tstep, tmax, minstep, opts.abstol, opts.reltol, opts.trtol, gdt], dtype=np.float64)
     blob = hdr.tobytes() + dbl.tobytes() + np.asarray(nominal, dtype=np.float64).tobytes() + b"".join(v.tobytes() for v in pv) \
         + sweep.tobytes() + (sweep if sweep2 is None else sweep2).tobytes()
     fin, fout = os.path.join(tmpdir, "in.bin"), os.path.join(tmpdir, "out.bin")
@@ -269,4 +276,8 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
     rows = np.frombuffer(raw, dtype=np.int64, count=nn, offset=off); off += rows.nbytes
     counters = np.frombuffer(raw, dtype=np.int64, count=8 * nn, offset=off).reshape(8, nn); off += counters.nbytes
     status = np.frombuffer(raw, dtype=np.int32, count=nn, offset=off)
-    return ckt, HostBatch(nn, ncol, wave, stats, rows, counters, status), ckt.columns(kind if kind != T.AN_DC else T.AN_DC)
+    hb = HostBatch(nn, ncol, wave, stats, rows, counters, status)
+    if n_grid:
+        t = tstart + (np.arange(n_grid) + 1.0) * gdt    # Batch.grid_times: two roundings, the last point clamped to tstop
+        hb.grid_times = np.where(t < tstop, t, tstop)
+    return ckt, hb, ckt.columns(kind)

@@ -57,15 +57,16 @@ def _host_vs_oracle(name, kind, n):
     okw = dict(kw)
     if "analysis" in okw:
         okw["analysis"] = {T.AN_OP: 0, T.AN_TRAN: 1, T.AN_DC: 3}[okw["analysis"]]
-    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True, **okw)
+    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True, want_stats=True, **okw)
     nominal_sig = PU.run_oracle(text, 1, {}, want_wave=False, want_order_sig=True, **okw)[1]["order_sig"][0]
-    return hb, ores, ores["order_sig"] == nominal_sig
+    is_op = kw.get("analysis", ckt0.analysis_card()["analysis"]) == T.AN_OP
+    return hb, ores, ores["order_sig"] == nominal_sig, is_op
 
 
 @pytest.mark.parametrize("name,kind", CASES, ids=[f"{n}-{k}" for n, k in CASES])
 def test_device_source_reproduces_the_oracle(built, name, kind):
     n = N_INST
-    hb, ores, same_order = _host_vs_oracle(name, kind, n)
+    hb, ores, same_order, is_op = _host_vs_oracle(name, kind, n)
     st, rows, cnt = hb.status(), hb.rows(), hb.counters()
     n_exact = 0
     for i in range(n):
@@ -86,6 +87,8 @@ def test_device_source_reproduces_the_oracle(built, name, kind):
         if same_order[i]:
             assert counters_equal, (name, i, cnt[:4, i].tolist(), ores["counters"][i, :4].tolist())
             assert np.array_equal(wg, wo, equal_nan=True), (name, i, float(np.nanmax(np.abs(wg - wo))))
+            if nr > 0 and not is_op and not np.isnan(wo).any():        # the running statistics of the result store: min, max, sum, last per column
+                assert np.array_equal(hb.stats_all()[:, :, i], ores["stats"][i][:, : ores["ncol"]]), (name, i)
             n_exact += 1
         else:
             # another elimination order: NaN / Inf classes and values inside the contract (a solve COUNT may move by one on an
@@ -96,6 +99,59 @@ def test_device_source_reproduces_the_oracle(built, name, kind):
     if name not in FAILING:
         assert n_exact == int(same_order.sum())
     print(name, kind, f"same pivot order as the nominal instance: {int(same_order.sum())}/{n}, all of them bit-identical")
+
+
+VARIANTS = {
+    # the transient inside the state machine instead of the warp-synchronous loops (tsb_opts.lane_refill: the code path of
+    # free-running lanes), the reference's literal second solve per linear step, and the host-compilable part of the fast
+    # build (x * (1/dt), hoisted invariants, condensed transient elimination; the device-only reciprocal seeds are not here)
+    "lane_refill": dict(opts_kw=dict(lane_refill=1)),
+    "literal_second_solve": dict(opts_kw=dict(skip_linear_resolve=0)),
+    "fast_build": dict(strict=False),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", ["rc", "rlc", "diode1", "diode2", "mosfet1", "bjt2", "transformer1", "mos2n"])
+def test_other_code_paths_of_the_device_source(built, name, variant):
+    """Same check over the other drivers / builds of the same source: bit identity where the arithmetic is the reference's
+    (any mapping of the strict build), the 1e-9 / 1e-12 contract with identical rows, status and step counts for the fast
+    build's re-associations."""
+    n = N_INST
+    text = DECKS[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    with tempfile.TemporaryDirectory() as tmp:
+        _, hb, _ = H.run(text, n, ov, tmp, **VARIANTS[variant])
+    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True)
+    same_order = ores["order_sig"] == PU.run_oracle(text, 1, {}, want_wave=False, want_order_sig=True)[1]["order_sig"][0]
+    rep = PU.compare_waves(hb, ores, n)
+    assert PU.report_ok(rep), PU.report_str(rep)
+    assert rep["counter_mismatch"] <= (1 if name == "diode1" else 0), PU.report_str(rep)
+    if variant != "fast_build":
+        for i in np.nonzero(same_order)[0]:
+            nr = int(ores["n_rows"][i])
+            assert np.array_equal(hb.waveform(i), ores["wave"][i, :nr, : ores["ncol"]], equal_nan=True), (name, variant, int(i))
+
+
+@pytest.mark.parametrize("name,grid_dt", [("rc", 0.0), ("rlc", 1e-6), ("diode2", 2e-5), ("mosfet1", 0.0)])
+def test_fixed_grid_output_of_the_device_source(built, name, grid_dt):
+    """TSB_OUT_GRID (interpolated output points under adaptive stepping): the device resamples the series while it runs;
+    here its source does so on the host, against the same definition applied in numpy to the oracle's full series."""
+    n = 6
+    text = T.BUNDLED[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    with tempfile.TemporaryDirectory() as tmp:
+        _, hb, _ = H.run(text, n, ov, tmp, grid_dt=grid_dt)
+    _, ores = PU.run_oracle(text, n, ov, cap_rows=24000)
+    tg = hb.grid_times
+    assert np.array_equal(hb.status(), ores["status"]) and np.all(hb.rows() == len(tg))
+    assert np.array_equal(hb.counters()[7], ores["n_rows"])            # rows of the reference series
+    for i in range(n):
+        ref = PU.resample_reference(ores["wave"][i], int(ores["n_rows"][i]), ores["ncol"], tg)
+        g = hb.wave_all()[: len(tg), :, i]
+        assert np.array_equal(g[:, 0], tg)
+        scale = np.maximum(np.abs(ref), np.nanmax(np.abs(ref), axis=0, keepdims=True) * 1e-3)
+        assert np.all(np.abs(g - ref) <= PU.RELTOL * scale + PU.ABSTOL), (name, i, float(np.max(np.abs(g - ref))))
 
 
 def test_the_reference_orders_some_instances_differently(built):
