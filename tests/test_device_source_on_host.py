@@ -18,6 +18,7 @@ import pytest
 import host_emul as H
 import parity_util as PU
 from extra_decks import EXTRA
+from random_decks import diode_rc_ladder, random_active_deck, random_deck, rc_ladder
 
 T = PU.T
 N_INST = 12
@@ -152,6 +153,30 @@ def test_fixed_grid_output_of_the_device_source(built, name, grid_dt):
         assert np.array_equal(g[:, 0], tg)
         scale = np.maximum(np.abs(ref), np.nanmax(np.abs(ref), axis=0, keepdims=True) * 1e-3)
         assert np.all(np.abs(g - ref) <= PU.RELTOL * scale + PU.ABSTOL), (name, i, float(np.max(np.abs(g - ref))))
+
+
+RANDOM = {f"random{s}": random_deck(s)[0] for s in range(10)}
+RANDOM.update({f"active{s}": random_active_deck(s)[0] for s in range(1, 9)})
+RANDOM.update({"rc_ladder12": rc_ladder(12), "diode_ladder8": diode_rc_ladder(8)})
+
+
+@pytest.mark.parametrize("name", sorted(RANDOM))
+def test_device_source_on_random_decks(built, name):
+    """Seeded random topologies (passive; with Q / M / K / core inductors; ladders of 10 - 14 unknowns): whatever the code
+    generator makes of them is the reference's arithmetic — bit for bit on the instances ordered like the nominal one."""
+    n = 8
+    text = RANDOM[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    with tempfile.TemporaryDirectory() as tmp:
+        _, hb, _ = H.run(text, n, ov, tmp)
+    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True)
+    same_order = ores["order_sig"] == PU.run_oracle(text, 1, {}, want_wave=False, want_order_sig=True)[1]["order_sig"][0]
+    rep = PU.compare_waves(hb, ores, n)
+    assert PU.report_ok(rep) and rep["counter_mismatch"] == 0, PU.report_str(rep)
+    for i in np.nonzero(same_order)[0]:
+        nr = int(ores["n_rows"][i])
+        assert np.array_equal(hb.waveform(i), ores["wave"][i, :nr, : ores["ncol"]], equal_nan=True), (name, int(i))
+        assert np.array_equal(hb.counters()[:4, i], ores["counters"][i, :4]), (name, int(i))
 
 
 def test_the_reference_orders_some_instances_differently(built):
