@@ -6,9 +6,11 @@ set per instance).  With `strict_fp = 1` and `-ffp-contract=off` this is the ari
 analyses (operating point incl. its Gmin / source-stepping fallbacks, transient, single and nested DC sweeps) can be held
 against the oracle on a machine without a GPU: row counts, status, counters and values.
 
-What it does NOT cover: anything that is a property of the parallel execution (warp votes across different lanes, lane
-refill, the shared time grid, the cooperative mapping) and the fast build's device-only arithmetic (`__CUDA_ARCH__`
-branches of models.cuh: reciprocal seeds, table-driven exp) — those are the GPU tests' job."""
+The shared time grid is emulated sequentially (the pilot instance runs to completion and publishes, then the readers run).
+What it does NOT cover: anything that is a property of the parallel execution (warp votes across different lanes, lanes
+refilling from the work counter, a reader overtaking the pilot, the cooperative mapping — which has its own host check) and
+the fast build's device-only arithmetic (`__CUDA_ARCH__` branches of models.cuh: reciprocal seeds, table-driven exp) —
+those are the GPU tests' job."""
 import os
 import re
 import struct
@@ -100,6 +102,19 @@ int main(int argc, char** argv) {
     a.wave = wave.data(); a.stats = stats.data(); a.scratch = scratch.data(); a.rows = rows.data(); a.counters = counters.data();
     a.status = status.data(); a.work_counter = &work; a.first_free = n;
     blockDim.x = TSB_BLOCK;
+#if TSB_TGRID
+    // shared time grid (runtime.cpp: launch_pilot): the pilot — instance 0, no outputs — publishes its attempts, then the readers run
+    std::vector<double> tgrid((size_t)(1 << 16) * TsbTgLayout<Ckt::NSRC>::ND, 0.0);
+    unsigned long long tgrid_pub = 0;
+    a.tgrid = tgrid.data(); a.tgrid_pub = &tgrid_pub; a.tgrid_cap = 1 << 16; a.tgrid_role = 0;
+    if (kernel == 0 && analysis == 1) {
+        TsbArgs ap = a;
+        ap.tgrid_role = 1; ap.n_run = 1; ap.out_flags = 0; ap.first_free = 1;
+        blockIdx.x = 0; threadIdx.x = 0;
+        tsb_optran(ap);
+        fprintf(stderr, "tgrid entries published: %llu\n", tgrid_pub);
+    }
+#endif
     for (long long i = 0; i < n; ++i) {
         blockIdx.x = (unsigned)(i / TSB_BLOCK); threadIdx.x = (unsigned)(i % TSB_BLOCK);
         if (kernel == 0) tsb_optran(a); else tsb_dc(a);
@@ -143,6 +158,17 @@ class HostBatch:
 
 _BUILT = {}
 
+# The five PTX one-liners of the shared time grid (acquire / release / relaxed accesses of the published count, a fence, a
+# prefetch) have no host spelling; in the sequential emulation — the pilot runs to completion before the first reader — plain
+# accesses are what they mean.
+_ASM_HOST = [
+    (r'asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");', "v = *p;"),
+    (r'asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");', "*p = v;"),
+    (r'asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");', "v = *p;"),
+    (r'asm volatile("fence.acq_rel.gpu;" ::: "memory");', ""),
+    (r'asm volatile("prefetch.global.L1 [%0];" ::"l"(p));', "(void)p;"),
+]
+
 
 def _flat_parameters(ckt):
     """The plan's flat parameter table (runtime.cpp: b->uniform = plan nominal) and the flat index of (device, param)."""
@@ -176,7 +202,10 @@ def build(text, overrides, tmpdir, strict=True, dc_src=-1, dc_src2=-1, opts_kw=N
     cpp = os.path.join(tmpdir, tag + ".cpp")
     exe = os.path.join(tmpdir, tag)
     with open(cpp, "w") as f:
-        f.write(SHIM + src.replace("extern __shared__ double tsb_smem[];", "") + MAIN)
+        host_src = src.replace("extern __shared__ double tsb_smem[];", "")
+        for ptx, c in _ASM_HOST:
+            host_src = host_src.replace(ptx, c)
+        f.write(SHIM + host_src + MAIN)
     flags = ["-O1", "-std=c++17", "-ffp-contract=off", "-w"] + ([] if strict else ["-DTSB_FAST_DIV"])
     r = subprocess.run(["g++"] + flags + ["-o", exe, cpp], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -277,6 +306,8 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
     counters = np.frombuffer(raw, dtype=np.int64, count=8 * nn, offset=off).reshape(8, nn); off += counters.nbytes
     status = np.frombuffer(raw, dtype=np.int32, count=nn, offset=off)
     hb = HostBatch(nn, ncol, wave, stats, rows, counters, status)
+    m = re.search(r"tgrid entries published: (\d+)", r.stderr)
+    hb.tgrid_entries = int(m.group(1)) if m else None     # shared time grid: what the pilot published (None: not a TSB_TGRID kernel)
     if n_grid:
         t = tstart + (np.arange(n_grid) + 1.0) * gdt    # Batch.grid_times: two roundings, the last point clamped to tstop
         hb.grid_times = np.where(t < tstop, t, tstop)

@@ -155,6 +155,26 @@ def test_fixed_grid_output_of_the_device_source(built, name, grid_dt):
         assert np.all(np.abs(g - ref) <= PU.RELTOL * scale + PU.ABSTOL), (name, i, float(np.max(np.abs(g - ref))))
 
 
+@pytest.mark.parametrize("name", ["rc", "rl", "rlc", "vpulse", "transformer1"])
+def test_shared_time_grid_of_the_device_source(built, name):
+    """tsb_opts.share_time_grid: a pilot instance publishes the time-only quantities of its step attempts, the other
+    instances verify (time, dt) and reuse them, falling back to their own arithmetic where their step sequence departs from
+    the pilot's.  Emulated sequentially (pilot first), the readers must give the reference's bits like any other mapping."""
+    n = 8
+    text = T.BUNDLED[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    with tempfile.TemporaryDirectory() as tmp:
+        _, hb, _ = H.run(text, n, ov, tmp, opts_kw=dict(share_time_grid=1))
+    assert hb.tgrid_entries is not None and hb.tgrid_entries > 100, hb.tgrid_entries
+    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True)
+    same_order = ores["order_sig"] == PU.run_oracle(text, 1, {}, want_wave=False, want_order_sig=True)[1]["order_sig"][0]
+    rep = PU.compare_waves(hb, ores, n)
+    assert PU.report_ok(rep) and rep["counter_mismatch"] == 0, PU.report_str(rep)
+    for i in np.nonzero(same_order)[0]:
+        nr = int(ores["n_rows"][i])
+        assert np.array_equal(hb.waveform(i), ores["wave"][i, :nr, : ores["ncol"]], equal_nan=True), (name, int(i))
+
+
 RANDOM = {f"random{s}": random_deck(s)[0] for s in range(10)}
 RANDOM.update({f"active{s}": random_active_deck(s)[0] for s in range(1, 9)})
 RANDOM.update({"rc_ladder12": rc_ladder(12), "diode_ladder8": diode_rc_ladder(8)})
