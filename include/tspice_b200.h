@@ -342,7 +342,7 @@ int tsb_job_result_summary(tsb_job* job, double* out, int64_t* rows_total, int64
 /* ---- operator level: batched factor + solve -------------------------------------------------------
  * Drop-in for the reference's matrix OPERATOR (pkg/matrix/circuit.go:126-150 Solve() = sparse Factor + Solve, fed by
  * AddElement / AddRHS, matrix/device.go:3-8) for hosts that stamp themselves: n_inst systems A x = b of one order
- * n <= 32 that share one pivot order.  One circuit per warp (8 / 16 / 32 lanes per system), matrix in registers,
+ * n <= 32 that share one pivot order.  One circuit per 4 / 8 / 16 lanes of a warp (2 or 3 rows per lane), matrix in registers,
  * pivot-row broadcast by warp shuffles (csrc/lu_warp.cu).  Layout: instance-major, A[inst][row][col] row-major
  * (0-based), b[inst][row], x[inst][col]; status[inst] = 0, or 1 for a zero pivot ("matrix factorization failed").
  * pivot_row[k] / pivot_col[k] (k = 0..n-1): 1-based external row / column eliminated at step k+1.

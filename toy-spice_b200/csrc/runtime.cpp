@@ -1539,7 +1539,7 @@ int tsb_lu_order(int n, const double* A_nominal, int* pivot_row, int* pivot_col)
 }
 
 static int lu_check_order(tsb_ctx* ctx, int n, const int* pr, const int* pc, int* prow0, int* pcol0) {
-    if (n < 1 || n > 32) return fail(ctx, TSB_E_UNSUPPORTED, "tsb_lu_solve_batched: order must be 1..32 (one row per lane)");
+    if (n < 1 || n > 32) return fail(ctx, TSB_E_UNSUPPORTED, "tsb_lu_solve_batched: order must be 1..32 (the matrix of a system lives in the registers of at most 16 lanes)");
     unsigned seen_r = 0, seen_c = 0;
     for (int k = 0; k < n; ++k) {
         if (pr[k] < 1 || pr[k] > n || pc[k] < 1 || pc[k] > n) return fail(ctx, TSB_E_INVALID, "pivot order: index out of range");
