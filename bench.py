@@ -16,6 +16,9 @@ One "step" = one pass of the hot path over that batch: one transient launch per 
             with 2^24 instances split over the N GPUs): ms per launch, circuit-timesteps/s, executed solves, FP64
             roofline fraction of an executed-flop model, lane utilisation
   strong    transformer1.cir, 2^24 instances IN TOTAL over the N GPUs (strong scaling)
+  operator_lu
+            the operator-level batched LU (tsb_lu_solve_batched_dev): dense systems of order 8 / 16 / 32, systems/s, dense-count
+            TFLOP/s against the same FP64 peak, backward error of a sample
   cpu_baseline / --impl reference
             the CPU restatement of the reference solver (oracle/, `kind: port` — the Go reference cannot be built
             here), one task per instance on all host threads, bounded sample.  The reference arm imports nothing of
@@ -82,6 +85,48 @@ def executed_flops(deck: str, strict: int = 0):
         return float(e["flops_per_executed_solve"]) if e else None
     except Exception:
         return None
+
+
+def lu_dense_flops(n: int) -> int:
+    """Factor + solve of one dense system of order n as the reference's sparse module does it."""
+    return sum(1 + (n - k) + 2 * (n - k) ** 2 for k in range(1, n + 1)) + n + 2 * n * (n - 1)
+
+
+def measure_lu_operator(T, ctx, timed_launches, dev_name: str, fp64_peak, budget_bytes: float = 1e9, orders=(8, 16, 32)) -> dict:
+    """Operator-level entry (tsb_lu_solve_batched_dev, csrc/lu_warp.cu: the drop-in for the reference's matrix operator): batches
+    of dense systems of one order sharing the pivot order of a nominal matrix, device pointers, fast build.  Synthetic systems: a
+    diagonally dominant conductance-like nominal matrix, every entry of every instance scaled by LogUniform[0.5, 2]."""
+    import torch
+    out = {"kernel": "tsb_k_lu_warp (2 - 3 rows per lane, cp.async staging; fast build)", "orders": []}
+    for n in orders:
+        rng = np.random.default_rng(1234 + n)
+        base = rng.uniform(-1e-3, 0.0, (n, n)) * (rng.random((n, n)) < 0.35)
+        base = base + base.T
+        np.fill_diagonal(base, 0.0)
+        np.fill_diagonal(base, -base.sum(axis=1) + 1e-4)
+        order = T.lu_order(base)
+        n_inst = int(min(1 << 22, budget_bytes // (n * n * 8)))
+        gen = torch.Generator(device=dev_name); gen.manual_seed(99 + n)
+        scale = torch.exp(torch.empty((n_inst, n, n), dtype=torch.float64, device=dev_name).uniform_(float(np.log(0.5)), float(np.log(2.0)), generator=gen))
+        dA = (torch.from_numpy(base).to(dev_name)[None] * scale).contiguous()
+        del scale
+        db = torch.empty((n_inst, n), dtype=torch.float64, device=dev_name).normal_(generator=gen)
+        dx = torch.empty_like(db)
+        dst = torch.empty(n_inst, dtype=torch.int32, device=dev_name)
+        ms = min(timed_launches(lambda: ctx.lu_solve_batched_dev(n, n_inst, dA.data_ptr(), db.data_ptr(), dx.data_ptr(), dst.data_ptr(), order, strict=False), reps=3))
+        # normwise backward error of the first 256 systems (the check travels with the number)
+        k = min(256, n_inst)
+        A, b, x = dA[:k].cpu().numpy(), db[:k].cpu().numpy(), dx[:k].cpu().numpy()
+        den = np.abs(A).sum(axis=2).max(axis=1) * np.abs(x).max(axis=1) + np.abs(b).max(axis=1)
+        berr = float((np.abs(np.einsum("qij,qj->qi", A, x) - b).max(axis=1) / den).max())
+        tf = n_inst * lu_dense_flops(n) / (ms * 1e-3) / 1e12
+        out["orders"].append({"n": n, "systems": n_inst, "ms_per_launch": ms, "systems_per_sec": n_inst / (ms * 1e-3), "tflops_dense_count": tf,
+                              "frac_fp64": tf / fp64_peak if fp64_peak else None,
+                              "algorithmic_gbs": n_inst * ((n * n + 2 * n) * 8 + 4) / (ms * 1e-3) / 1e9,
+                              "singular": int(dst.sum().item()), "max_backward_error": berr})
+        del dA, db, dx, dst
+        torch.cuda.empty_cache() if dev_name.startswith("cuda") else None
+    return out
 
 
 def flop_fields(deck: str, strict: int, executed_solves: int, ms: float, model_flops: int, fp64_peak, n_gpus: int = 1) -> dict:
@@ -625,6 +670,14 @@ def main():
         except Exception as ex:
             larger_n = {"error": repr(ex)[:300]}
 
+    # ---- operator level: the batched LU behind tsb_lu_solve_batched (drop-in for the reference's matrix operator) -----------------
+    operator_lu = None
+    if not args.no_configs:
+        try:
+            operator_lu = measure_lu_operator(T, ctx, timed_launches, dev_name, fp64_peak, budget_bytes=1e9 * min(1.0, args.config_scale))
+        except Exception as ex:
+            operator_lu = {"error": repr(ex)[:300]}
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -646,7 +699,7 @@ def main():
                     "pipelined": "two batches per deck: the read-back of step i (tsb_result_fetch_async) and the parameter upload of step i+1 overlap the launches", "results_check": bool(e2e_ok)},
             "gpu_launches": int(launches), "failed_instances": bad_status,
             "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_stamp": roofline_stamp,
-            "configs": configs, "strong": strong, "larger_n": larger_n, "cpu_baseline": cpu,
+            "configs": configs, "strong": strong, "larger_n": larger_n, "operator_lu": operator_lu, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
