@@ -82,7 +82,7 @@ int main(int argc, char** argv) {
     std::vector<char> in = slurp(argv[1]);
     const long long* h = (const long long*)in.data();
     const long long n = h[0], nvar = h[1], npar = h[2], analysis = h[3], uic = h[4], max_iter = h[5], out_flags = h[6],
-                    cap_rows = h[7], n_sweep = h[8], kernel = h[9], n_grid = h[10];
+                    cap_rows = h[7], n_sweep = h[8], kernel = h[9], n_grid = h[10], refill_chain = h[11];
     const double* d = (const double*)(h + 16);
     TsbArgs a; memset(&a, 0, sizeof a);
     a.n_inst = n; a.n_run = n; a.analysis = (int)analysis; a.uic = (int)uic; a.max_iter = (int)max_iter;
@@ -115,7 +115,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "tgrid entries published: %llu\n", tgrid_pub);
     }
 #endif
-    for (long long i = 0; i < n; ++i) {
+    if (refill_chain) a.first_free = 1;          // lane refill: ONE lane starts on instance 0 and takes every further instance from the work counter
+    for (long long i = 0; i < (refill_chain ? 1 : n); ++i) {
         blockIdx.x = (unsigned)(i / TSB_BLOCK); threadIdx.x = (unsigned)(i % TSB_BLOCK);
         if (kernel == 0) tsb_optran(a); else tsb_dc(a);
     }
@@ -222,7 +223,8 @@ def _sweep_points(start, stop, inc):
     return out
 
 
-def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None, strict=True, cap_rows=None, opts_kw=None, grid_dt=None):
+def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None, strict=True, cap_rows=None, opts_kw=None, grid_dt=None,
+        refill_chain=False):
     """Whole analysis of `n` instances on the host-compiled device source.  dc = (source, start, stop, inc) overrides the
     deck's .dc card; dc2 = ((outer ...), (inner ...)) runs the nested sweep.  Returns (circuit, HostBatch, column names)."""
     probe = T.Circuit.from_netlist(text)
@@ -288,7 +290,8 @@ def run(text, n, overrides, tmpdir, analysis=None, tran=None, dc=None, dc2=None,
             ncol = len(ckt.columns(T.AN_DC))
         rows_cap = len(sweep)
     hdr = np.zeros(16, dtype=np.int64)
-    hdr[:11] = [n, len(pv), len(nominal), an, int(card.get("uic", False)), opts.max_iter, out_flags, rows_cap, len(sweep), kernel, n_grid]
+    hdr[:12] = [n, len(pv), len(nominal), an, int(card.get("uic", False)), opts.max_iter, out_flags, rows_cap, len(sweep), kernel, n_grid,
+                int(bool(refill_chain))]
     dbl = np.array([tstart, tstop, tstep, tmax, minstep, opts.abstol, opts.reltol, opts.trtol, gdt], dtype=np.float64)
     blob = hdr.tobytes() + dbl.tobytes() + np.asarray(nominal, dtype=np.float64).tobytes() + b"".join(v.tobytes() for v in pv) \
         + sweep.tobytes() + (sweep if sweep2 is None else sweep2).tobytes()

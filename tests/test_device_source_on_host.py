@@ -134,6 +134,26 @@ def test_other_code_paths_of_the_device_source(built, name, variant):
             assert np.array_equal(hb.waveform(i), ores["wave"][i, :nr, : ores["ncol"]], equal_nan=True), (name, variant, int(i))
 
 
+@pytest.mark.parametrize("name", ["diode1", "diode2", "mosfet1", "bjt2", "pnp_tran"])
+def test_one_lane_refilling_itself_through_the_whole_batch(built, name):
+    """Lane refill (tsb_opts.lane_refill, nonlinear circuits): a lane that finishes an instance writes its results, takes the
+    next unprocessed instance from the work counter and re-enters the same loop.  Here ONE emulated lane starts on instance 0
+    and works through all of them that way — whatever state an instance leaves behind (device state, result store, step
+    control, operating-point fallback stage) must not reach the next one."""
+    n = 10
+    text = DECKS[name]
+    ov = PU.draws(name, T.Circuit.from_netlist(text), n)
+    with tempfile.TemporaryDirectory() as tmp:
+        _, hb, _ = H.run(text, n, ov, tmp, opts_kw=dict(lane_refill=1), refill_chain=True)
+    _, ores = PU.run_oracle(text, n, ov, want_order_sig=True)
+    same_order = ores["order_sig"] == PU.run_oracle(text, 1, {}, want_wave=False, want_order_sig=True)[1]["order_sig"][0]
+    rep = PU.compare_waves(hb, ores, n)
+    assert PU.report_ok(rep) and rep["counter_mismatch"] <= (1 if name == "diode1" else 0), PU.report_str(rep)
+    for i in np.nonzero(same_order)[0]:
+        nr = int(ores["n_rows"][i])
+        assert np.array_equal(hb.waveform(i), ores["wave"][i, :nr, : ores["ncol"]], equal_nan=True), (name, int(i))
+
+
 @pytest.mark.parametrize("name,grid_dt", [("rc", 0.0), ("rlc", 1e-6), ("diode2", 2e-5), ("mosfet1", 0.0)])
 def test_fixed_grid_output_of_the_device_source(built, name, grid_dt):
     """TSB_OUT_GRID (interpolated output points under adaptive stepping): the device resamples the series while it runs;
