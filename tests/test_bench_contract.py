@@ -73,3 +73,40 @@ def test_live_bench_line(built):
     assert "error" not in ln and len(ln["workloads"]) == 2, ln
     for w in ln["workloads"]:
         assert [m["coop_parts"] for m in w["mappings"]] == [0, 2, 4] and all(m["failed"] == 0 and m["steps"] > 0 for m in w["mappings"]), w
+
+
+def test_operator_lu_entry_with_a_stand_in_context(built):
+    """bench.py's `operator_lu` entry (measure_lu_operator) end to end on the CPU: the synthetic systems, the pivot order of the
+    nominal matrix (tsb_lu_order, host only), the call shape of tsb_lu_solve_batched_dev, the figures it derives — with a
+    stand-in context that solves the systems with torch.linalg.solve where the real one launches csrc/lu_warp.cu."""
+    import gc
+    import importlib.util
+    import time
+
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as PU
+
+    class StandIn:
+        def lu_solve_batched_dev(self, n, n_inst, a_ptr, b_ptr, x_ptr, st_ptr, order, strict=False):
+            assert len(order[0]) == n and sorted(order[0]) == list(range(1, n + 1))
+            ts = {t.data_ptr(): t for t in gc.get_objects() if isinstance(t, torch.Tensor)}
+            A, b, x, st = ts[a_ptr], ts[b_ptr], ts[x_ptr], ts[st_ptr]
+            assert A.shape == (n_inst, n, n) and A.is_contiguous()
+            x.copy_(torch.linalg.solve(A, b.unsqueeze(-1)).squeeze(-1)); st.zero_()
+
+    def timed(fn, reps=3, warm=1):
+        out = []
+        for _ in range(reps):
+            t0 = time.time(); fn(); out.append((time.time() - t0) * 1e3)
+        return out
+
+    r = B.measure_lu_operator(PU.T, StandIn(), timed, "cpu", 36.6, budget_bytes=2e6)
+    assert [o["n"] for o in r["orders"]] == [8, 16, 32]
+    for o in r["orders"]:
+        assert o["singular"] == 0 and o["max_backward_error"] < 1e-13 and o["systems"] > 100
+        assert abs(o["tflops_dense_count"] - o["systems_per_sec"] * B.lu_dense_flops(o["n"]) / 1e12) < 1e-9 * o["tflops_dense_count"] + 1e-18
+    assert B.lu_dense_flops(5) == 120 and B.lu_dense_flops(32) == 23376          # SURVEY a11: the reference's dense count
