@@ -1,5 +1,6 @@
 """Development driver (not a pytest file): every variant of the operator-level batched LU (csrc/lu_warp.cu: rows per lane,
-shared-memory pivot-row broadcast, asynchronous staging — $TSB_LU_VARIANT = "R,B,A", read per call) in ONE process: the
+shared-memory pivot-row broadcast [only in a -DTSB_LU_WITH_BCAST=1 build: measured slower everywhere and compiled out, B is
+ignored otherwise], asynchronous staging — $TSB_LU_VARIANT = "R,B,A", read per call) in ONE process: the
 strict build against the oracle bit for bit, the fast build's backward error, and throughput with CUDA events.
 Usage: python tests/gpu_lu_variants.py [bytes_of_A, default 1e9] [n,n,...]"""
 import os
@@ -12,7 +13,7 @@ import parity_util as PU
 from test_lu_operator import mna_like
 
 T, O = PU.T, PU.O
-VARIANTS = tuple(os.environ.get("LU_VARIANTS", "1,0,0;1,0,1;1,1,0;1,1,1;2,0,0;2,0,1;2,1,0;2,1,1;4,1,0;4,1,1;4,0,0").split(";"))
+VARIANTS = tuple(os.environ.get("LU_VARIANTS", "1,0,0;1,0,1;2,0,0;2,0,1;3,0,0;3,0,1;4,0,1").split(";"))
 
 
 def f_lu_dense(n):
